@@ -1,0 +1,376 @@
+// deepv_b200 — HBM-bound helper kernels of the MMDiT forward (vectorised, coalesced).
+#include "kernels.cuh"
+
+namespace dv {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------
+// LayerNorm (no affine) + adaLN modulate, one warp per token row, D = 1536.
+// Reference: AdaLayerNormZero / AdaLayerNormContinuous / norm2 (+ modulate)
+// model/mmdit.py:558,505,412-413,427-428; LN eps 1e-6 inside the sqrt, biased variance.
+// ---------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(
+    const float* __restrict__ x, long long x_bs, __nv_bfloat16* __restrict__ out, long long out_bs,
+    const float* __restrict__ shift, const float* __restrict__ scale, int mod_bs, int B, int L,
+    float eps) {
+  constexpr int V = D / 128;  // float4 per lane
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * L) return;
+  const int b = warp / L, l = warp - b * L;
+  const float4* xr = reinterpret_cast<const float4*>(x + b * x_bs + static_cast<long long>(l) * D);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + bq * bq + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const float4* sh = reinterpret_cast<const float4*>(shift + static_cast<long long>(b) * mod_bs);
+  const float4* sc = reinterpret_cast<const float4*>(scale + static_cast<long long>(b) * mod_bs);
+  uint2* o = reinterpret_cast<uint2*>(out + b * out_bs + static_cast<long long>(l) * D);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 h = __ldg(sh + lane + 32 * i);
+    const float4 c = __ldg(sc + lane + 32 * i);
+    float y0 = (v[i].x - mean) * rstd * (1.0f + c.x) + h.x;
+    float y1 = (v[i].y - mean) * rstd * (1.0f + c.y) + h.y;
+    float y2 = (v[i].z - mean) * rstd * (1.0f + c.z) + h.z;
+    float y3 = (v[i].w - mean) * rstd * (1.0f + c.w) + h.w;
+    uint2 pk;
+    pk.x = pack_bf16x2(y0, y1);
+    pk.y = pack_bf16x2(y2, y3);
+    o[lane + 32 * i] = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Skinny GEMV for the conditioning path (M = CFG batch <= 4): pure weight streaming.
+// One warp per output row, 16-byte loads, activations staged once per CTA in smem.
+// Reference: TimestepEmbedding / TextProjection / adaLN linears, mmdit.py:718-736,548,495.
+// ---------------------------------------------------------------------------------
+constexpr int kGemvRowsPerWarp = 8;
+constexpr int kGemvWarps = 8;
+
+template <int NB>
+__global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(
+    const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
+    const float* __restrict__ in, int in_stride, float* __restrict__ out, int out_stride, int N,
+    int K, int silu_in, int accumulate) {
+  extern __shared__ float s_in[];  // [NB][K]
+  for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
+    const int b = i / K, k = i - b * K;
+    float v = in[b * in_stride + k];
+    s_in[i] = silu_in ? silu(v) : v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * kGemvWarps + warp) * kGemvRowsPerWarp;
+  for (int rr = 0; rr < kGemvRowsPerWarp; ++rr) {
+    const int n = row0 + rr;
+    if (n >= N) break;
+    const uint4* wr = reinterpret_cast<const uint4*>(W + static_cast<long long>(n) * K);
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int k8 = lane; k8 < K / 8; k8 += 32) {
+      const uint4 w = __ldg(wr + k8);
+      const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y),
+                           bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float4 a0 = *reinterpret_cast<const float4*>(s_in + b * K + k8 * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(s_in + b * K + k8 * 8 + 4);
+        acc[b] += wf[0] * a0.x + wf[1] * a0.y + wf[2] * a0.z + wf[3] * a0.w + wf[4] * a1.x +
+                  wf[5] * a1.y + wf[6] * a1.z + wf[7] * a1.w;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float r = warp_sum(acc[b]);
+      if (lane == 0) {
+        r += bias ? bias[n] : 0.f;
+        float* o = out + b * out_stride + n;
+        *o = accumulate ? (*o + r) : r;
+      }
+    }
+  }
+}
+
+__global__ void timestep_features_kernel(const float* __restrict__ t, float* __restrict__ out,
+                                         int B) {
+  // emb[j] = t * exp(-ln(10000) * j / 128); out = [cos(emb) (128) | sin(emb) (128)]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i / 128, j = i - b * 128;
+  const float expo = -9.210340371976184f * static_cast<float>(j) / 128.0f;
+  const float arg = t[b] * expf(expo);
+  out[b * 256 + j] = cosf(arg);
+  out[b * 256 + 128 + j] = sinf(arg);
+}
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p, long long i);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p, long long i) {
+  return p[i];
+}
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, long long i) {
+  return __bfloat162float(p[i]);
+}
+
+// one thread per (b, t, gy, gx, k) output element; k fastest -> coalesced bf16 stores
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ lat, __nv_bfloat16* __restrict__ out,
+                                int rows_total, int row_offset, int Kpad, int B, int C, int Tn,
+                                int H, int W, int pool2) {
+  const int gh = (pool2 ? H / 2 : H) / 2, gw = (pool2 ? W / 2 : W) / 2;
+  const long long total = static_cast<long long>(B) * Tn * gh * gw * Kpad;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = idx % Kpad;
+  long long r = idx / Kpad;
+  const int gx = r % gw;
+  r /= gw;
+  const int gy = r % gh;
+  r /= gh;
+  const int tt = r % Tn;
+  const int b = r / Tn;
+  float val = 0.f;
+  if (k < C * 4) {
+    const int c = k >> 2, p1 = (k >> 1) & 1, p2 = k & 1;
+    const int y = 2 * gy + p1, x = 2 * gx + p2;
+    const long long plane = ((static_cast<long long>(b) * C + c) * Tn + tt) * H * W;
+    if (pool2) {
+      // bilinear resize by exactly 1/2 (align_corners=False) == 2x2 mean
+      const long long o = plane + static_cast<long long>(2 * y) * W + 2 * x;
+      val = 0.25f * (ldf(lat, o) + ldf(lat, o + 1) + ldf(lat, o + W) + ldf(lat, o + W + 1));
+    } else {
+      val = ldf(lat, plane + static_cast<long long>(y) * W + x);
+    }
+  }
+  const long long orow = static_cast<long long>(b) * rows_total + row_offset +
+                         (static_cast<long long>(tt) * gh + gy) * gw + gx;
+  out[orow * Kpad + k] = __float2bfloat16(val);
+}
+
+template <typename T>
+__global__ void to_bf16_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                               long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(ldf(in, i));
+}
+
+// base 2-D sincos table: channel layout [sin(x w) | cos(x w) | sin(y w) | cos(y w)], each D/4,
+// w_d = 10000^(-d / (D/4)), coordinates = index / (S / base_size); evaluated in fp64 like numpy.
+__global__ void pos_base_kernel(float* __restrict__ out, int S, int D, int base_size) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(S) * S * D;
+  if (idx >= total) return;
+  const int ch = idx % D;
+  const long long p = idx / D;
+  const int xi = p % S, yi = p / S;
+  const int quarter = D / 4;
+  const int sel = ch / quarter, dd = ch % quarter;
+  // numpy: arange(S, float32) / (S / base) -> float32 coordinate
+  const float coord_f = static_cast<float>(sel < 2 ? xi : yi) /
+                        static_cast<float>(static_cast<double>(S) / base_size);
+  const double omega = 1.0 / pow(10000.0, static_cast<double>(dd) / static_cast<double>(quarter));
+  const double a = static_cast<double>(coord_f) * omega;
+  out[idx] = static_cast<float>((sel & 1) ? cos(a) : sin(a));
+}
+
+// torch F.interpolate(mode='bilinear', align_corners=False) source index
+__device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size, int& i0, int& i1,
+                                             float& lam) {
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  float src = (static_cast<float>(dst) + 0.5f) * scale - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  lam = src - static_cast<float>(i0);
+}
+
+__global__ void pos_clip_kernel(const float* __restrict__ base, int S, int D,
+                                float* __restrict__ out, int row_offset, int Tn, int h, int w,
+                                int oh, int ow) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(h) * w * D;
+  if (idx >= total) return;
+  const int ch = idx % D;
+  const int p = idx / D;
+  const int x = p % w, y = p / w;
+  const int top = (S - oh) / 2, left = (S - ow) / 2;
+  float val;
+  if (oh == h && ow == w) {
+    val = base[(static_cast<long long>(top + y) * S + left + x) * D + ch];
+  } else {
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(y, oh, h, y0, y1, ly);
+    bilinear_src(x, ow, w, x0, x1, lx);
+    auto at = [&](int yy, int xx) {
+      return base[(static_cast<long long>(top + yy) * S + left + xx) * D + ch];
+    };
+    // ATen upsample_bilinear2d: w0 = 1 - lambda
+    val = (1.f - ly) * ((1.f - lx) * at(y0, x0) + lx * at(y0, x1)) +
+          ly * ((1.f - lx) * at(y1, x0) + lx * at(y1, x1));
+  }
+  for (int t = 0; t < Tn; ++t)
+    out[(static_cast<long long>(row_offset) + static_cast<long long>(t) * h * w + p) * D + ch] = val;
+}
+
+__global__ void key_bias_kernel(const float* __restrict__ ctx_mask, int Lc,
+                                float* __restrict__ key_bias, int B, int L, int Lpad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Lpad) return;
+  const int b = i / Lpad, k = i - b * Lpad;
+  float v = 0.f;
+  if (k >= L) {
+    v = -INFINITY;
+  } else if (k < Lc) {
+    v = (ctx_mask[b * Lc + k] != 0.f) ? 0.f : -INFINITY;
+  }
+  key_bias[i] = v;
+}
+
+}  // namespace
+
+int launch_ln_modulate(const float* x, long long x_bs, __nv_bfloat16* out, long long out_bs,
+                       const float* shift, const float* scale, int mod_bs, int B, int L, int D,
+                       float eps, cudaStream_t stream) {
+  DV_REQUIRE(D == 1536 || D == 512, "ln_modulate: D=%d unsupported", D);
+  const long long rows = static_cast<long long>(B) * L;
+  if (rows == 0) return 0;
+  const int blocks = static_cast<int>((rows * 32 + 255) / 256);
+  if (D == 1536)
+    ln_modulate_kernel<1536><<<blocks, 256, 0, stream>>>(x, x_bs, out, out_bs, shift, scale,
+                                                         mod_bs, B, L, eps);
+  else
+    ln_modulate_kernel<512><<<blocks, 256, 0, stream>>>(x, x_bs, out, out_bs, shift, scale, mod_bs,
+                                                        B, L, eps);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int in_stride,
+                float* out, int out_stride, int B, int N, int K, int silu_in, int accumulate,
+                cudaStream_t stream) {
+  DV_REQUIRE(B >= 1 && B <= 4, "gemv: batch %d not in [1,4]", B);
+  DV_REQUIRE(K % 8 == 0, "gemv: K=%d must be a multiple of 8", K);
+  const int rows_per_cta = kGemvWarps * kGemvRowsPerWarp;
+  const int blocks = (N + rows_per_cta - 1) / rows_per_cta;
+  const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
+#define DV_GEMV(NB)                                                                              \
+  do {                                                                                           \
+    static bool attr = false;                                                                    \
+    if (!attr) {                                                                                 \
+      DV_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<NB>,                                        \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+      attr = true;                                                                               \
+    }                                                                                            \
+    gemv_kernel<NB><<<blocks, kGemvWarps * 32, smem, stream>>>(W, bias, in, in_stride, out,      \
+                                                               out_stride, N, K, silu_in,        \
+                                                               accumulate);                      \
+  } while (0)
+  DV_REQUIRE(smem <= 96 * 1024, "gemv: B*K too large for smem staging");
+  switch (B) {
+    case 1: DV_GEMV(1); break;
+    case 2: DV_GEMV(2); break;
+    case 3: DV_GEMV(3); break;
+    default: DV_GEMV(4); break;
+  }
+#undef DV_GEMV
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_timestep_features(const float* t, float* out, int B, cudaStream_t stream) {
+  timestep_features_kernel<<<(B * 128 + 127) / 128, 128, 0, stream>>>(t, out, B);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_patchify(const void* latent, int is_bf16, __nv_bfloat16* out, int rows_total,
+                    int row_offset, int Kpad, int B, int C, int T, int H, int W, int pool2,
+                    cudaStream_t stream) {
+  DV_REQUIRE(Kpad >= C * 4, "patchify: Kpad=%d < C*4=%d", Kpad, C * 4);
+  DV_REQUIRE(H % (pool2 ? 4 : 2) == 0 && W % (pool2 ? 4 : 2) == 0, "patchify: H=%d W=%d", H, W);
+  const int gh = (pool2 ? H / 2 : H) / 2, gw = (pool2 ? W / 2 : W) / 2;
+  const long long total = static_cast<long long>(B) * T * gh * gw * Kpad;
+  const int blocks = static_cast<int>((total + 255) / 256);
+  if (is_bf16)
+    patchify_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(latent), out, rows_total, row_offset, Kpad, B, C, T,
+        H, W, pool2);
+  else
+    patchify_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(latent), out,
+                                                       rows_total, row_offset, Kpad, B, C, T, H, W,
+                                                       pool2);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_to_bf16(const void* in, int is_bf16, __nv_bfloat16* out, long long n,
+                   cudaStream_t stream) {
+  const int blocks = static_cast<int>((n + 255) / 256);
+  if (is_bf16)
+    to_bf16_kernel<__nv_bfloat16>
+        <<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, n);
+  else
+    to_bf16_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(in), out, n);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_pos_base(float* out, int S, int D, int base_size, cudaStream_t stream) {
+  const long long total = static_cast<long long>(S) * S * D;
+  pos_base_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(out, S, D, base_size);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_pos_clip(const float* base, int S, int D, float* out, int row_offset, int T, int h,
+                    int w, int oh, int ow, cudaStream_t stream) {
+  DV_REQUIRE(oh >= h && ow >= w && oh <= S && ow <= S, "pos_clip: crop %dx%d vs clip %dx%d", oh, ow,
+             h, w);  // mmdit.py:851-852
+  const long long total = static_cast<long long>(h) * w * D;
+  pos_clip_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(base, S, D, out,
+                                                                           row_offset, T, h, w, oh,
+                                                                           ow);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_key_bias(const float* ctx_mask, int Lc, float* key_bias, int B, int L, int Lpad,
+                    cudaStream_t stream) {
+  key_bias_kernel<<<(B * Lpad + 255) / 256, 256, 0, stream>>>(ctx_mask, Lc, key_bias, B, L, Lpad);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+}  // namespace dv

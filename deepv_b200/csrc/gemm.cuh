@@ -1,0 +1,78 @@
+// deepv_b200 — the one tensor-core contraction kernel of the library.
+//
+// C[b][m][n] = sum_k A[b][m][k] * W[n][k]   (bf16 x bf16 -> fp32 in TMEM)
+//
+// * A comes either from a dense (K, rows, batch) tensor or, for the VAE's causal
+//   conv3d, from a channels-last (C, W, H, T, B) activation through a 5-D TMA box
+//   per filter tap (implicit GEMM; TMA out-of-bounds zero fill IS the causal /
+//   spatial zero padding of reference model/vae.py:192-199,229-236).
+// * W is always a K-major [N][K] bf16 matrix (nn.Linear layout; conv weights are
+//   repacked to [Cout][tap][Cin] at load time).
+// * The epilogue is selected at run time (EpiMode) and fuses what the reference
+//   runs as separate ATen kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dv {
+
+enum EpiMode : int {
+  EPI_BF16 = 0,        // out_bf16 = acc + bias
+  EPI_GELU = 1,        // out_bf16 = gelu_tanh(acc + bias)            (mmdit.py:97)
+  EPI_RESID_GATE = 2,  // x_f32 += gate[b][n] * (acc + bias)          (mmdit.py:409-410,416-418,424-431)
+  EPI_F32_ADD = 3,     // out_f32 = acc + bias + addend[row_map[m]][n] (patch-embed + pos, mmdit.py:894-935)
+  EPI_QKV = 4,         // per-head RMSNorm + temporal RoPE on q,k; v plain (mmdit.py:282-307,131-136)
+  EPI_UNPATCH = 5,     // proj_out + unpatchify store               (mmdit.py:1527,1452-1457)
+  EPI_CONV = 6,        // conv3d: bias (+residual), NDHWC store with optional pixel-shuffle /
+                       // frame-interleave address map              (vae.py:251,309,382,407-409)
+  EPI_BF16_ROWBIAS = 7 // out_bf16 = acc + bias[m]  (transposed projections, V^T for VAE attention)
+};
+
+enum ConvStore : int { CONV_PLAIN = 0, CONV_SHUFFLE_HW = 1, CONV_INTERLEAVE_T = 2 };
+
+struct GemmDesc {
+  // ---- problem -------------------------------------------------------------
+  int batch;           // dense: batch count; conv: B
+  int M;               // dense: valid rows per batch; conv: ignored (T*H*W)
+  int N;               // valid output columns
+  int K;               // dense: reduction length (multiple of 64 after padding)
+  // ---- A operand -------------------------------------------------------------
+  const void* A;       // bf16
+  long long a_batch_stride;  // elements (dense)
+  int lda;             // elements (dense)
+  // conv geometry (a_mode == 1): activation [B][T][H][W][C] bf16
+  int a_mode;          // 0 dense, 1 conv
+  int cT, cH, cW, cC;  // input dims (C multiple of 64)
+  int kt, kh, kw;      // 3,3,3 or 1,1,1
+  // ---- W operand -------------------------------------------------------------
+  const void* W;       // bf16 [N_rows][K]
+  int w_rows;          // rows present in memory (>= N)
+  // ---- epilogue ---------------------------------------------------------------
+  int mode;
+  void* out;
+  long long out_batch_stride;  // elements
+  int ldo;                     // elements
+  int out_row_offset;          // rows added to m (joint-sequence placement)
+  const float* bias;           // [N] (or [M] for ROWBIAS); may be null
+  const float* gate;           // RESID_GATE: gate[b * gate_batch_stride + n]
+  int gate_batch_stride;
+  const float* addend;         // F32_ADD: [rows][N] fp32, may be null
+  const int* row_map;          // F32_ADD: per-m row into addend (null -> m)
+  // QKV
+  const float* qk_norm_w;      // [2][64]: q weight then k weight
+  const float* rope_cs;        // [frames][32][2] (cos, sin)
+  const int* frame_id;         // [M]
+  int heads_dim;               // = 1536 (q|k|v block width)
+  // UNPATCH: out bf16 [B][C][1][2*gh][2*gw]
+  int up_gh, up_gw, up_C;
+  int out_f32;                 // UNPATCH: store fp32 instead of bf16
+  // CONV
+  int conv_store;              // ConvStore
+  int conv_drop_first;         // INTERLEAVE_T: drop output frame 0 (vae.py:408-409)
+  const void* residual;        // bf16, same layout as out (PLAIN store only), may be null
+  int out_C;                   // channels of the stored tensor (N, N/4 or N/2)
+};
+
+// Enqueue on `stream`.  Returns 0 or a negative error (see dv_last_error()).
+int launch_gemm(const GemmDesc& d, cudaStream_t stream);
+
+}  // namespace dv

@@ -1,0 +1,80 @@
+// deepv_b200 — launchers of the non-GEMM kernels (all enqueue on `stream`, no sync,
+// no allocation).  Every function returns 0 or a negative error code.
+#pragma once
+#include "common.cuh"
+
+namespace dv {
+
+// ---- attention (attention.cu) ------------------------------------------------------
+int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias, int B,
+                     int L, int Lpad, int H, cudaStream_t stream);
+
+// ---- MMDiT elementwise (elementwise.cu) -----------------------------------------------
+// out_bf16[b][l][:] = LN(x[b][l][:]) * (1 + scale[b][:]) + shift[b][:]   (eps inside sqrt)
+int launch_ln_modulate(const float* x, long long x_batch_stride, __nv_bfloat16* out,
+                       long long out_batch_stride, const float* shift, const float* scale,
+                       int mod_batch_stride, int B, int L, int D, float eps, cudaStream_t stream);
+
+// out[b][n] (+)= act_out( W[n][:] . act_in(in[b][:]) + bias[n] ),  W bf16 [N][K], B <= 4
+int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int in_stride,
+                float* out, int out_stride, int B, int N, int K, int silu_in, int accumulate,
+                cudaStream_t stream);
+
+// sinusoidal timestep features, cos first (mmdit.py:645-683 with flip_sin_to_cos, shift 0)
+int launch_timestep_features(const float* t, float* out, int B, cudaStream_t stream);
+
+// latent [B][C][T][H][W] (fp32 or bf16) -> patch rows [B][rows_total][Kpad] bf16 at row_offset,
+// k = c*4 + p1*2 + p2, zero padded to Kpad.  pool2 = 1 first averages 2x2 pixel blocks
+// (bilinear /2 of mmdit.py:990) before patchifying.
+int launch_patchify(const void* latent, int is_bf16, __nv_bfloat16* out, int rows_total,
+                    int row_offset, int Kpad, int B, int C, int T, int H, int W, int pool2,
+                    cudaStream_t stream);
+
+// fp32/bf16 -> bf16 copy (context embeddings staging)
+int launch_to_bf16(const void* in, int is_bf16, __nv_bfloat16* out, long long n,
+                   cudaStream_t stream);
+
+// base sincos table [S*S][D] (mmdit.py:590-642, grid coords / (S / base))
+int launch_pos_base(float* out, int S, int D, int base_size, cudaStream_t stream);
+// crop [top:top+oh, left:left+ow] of the base table, bilinear resize to (h, w) (align_corners
+// False, mmdit.py:864-871), write T copies to out rows [row_offset, row_offset + T*h*w)
+int launch_pos_clip(const float* base, int S, int D, float* out, int row_offset, int T, int h,
+                    int w, int oh, int ow, cudaStream_t stream);
+
+// key_bias[b][k] = 0 for live keys, -inf for dead context keys and k >= L
+int launch_key_bias(const float* ctx_mask, int Lc, float* key_bias, int B, int L, int Lpad,
+                    cudaStream_t stream);
+
+// ---- sampler step (sampler.cu) -------------------------------------------------------
+// CFG combine (pipeline.py:502-513) + Euler step (scheduler.py:278-286), rounding sequence of
+// the ATen bf16 path reproduced exactly when is_bf16 = 1; plain fp32 otherwise.
+int launch_cfg_euler(const void* noise_pred, int n_branch, const void* sample, void* out,
+                     long long numel, float w_text, float w_hist, double sigma, double sigma_next,
+                     int is_bf16, cudaStream_t stream);
+// stage transition (pipeline.py:453-465): nearest x2 upsample, alpha * x + beta * noise
+int launch_stage_renoise(const void* lat_lo, const void* noise, void* out, int planes, int h, int w,
+                         double alpha, double beta, int is_bf16, cudaStream_t stream);
+// correlated 2x2 block noise (pipeline.py:431-437): noise block = Lchol(4x4) @ z
+int launch_block_noise(const float* z, void* out, int planes, int h, int w, float gamma,
+                       int is_bf16, cudaStream_t stream);
+
+// ---- VAE elementwise (vae_kernels.cu) ---------------------------------------------------
+// per (b, frame, group) mean / rstd over channels-last activations [B][T][H][W][C]
+int launch_gn_stats(const __nv_bfloat16* x, float* stats /*[B*T][G][2]*/, int BT, int HW, int C,
+                    int G, float eps, cudaStream_t stream);
+// y = silu?( (x - mean) * rstd * gamma + beta )
+int launch_gn_apply(const __nv_bfloat16* x, const float* stats, const float* gamma,
+                    const float* beta, __nv_bfloat16* y, int BT, int HW, int C, int G, int silu,
+                    cudaStream_t stream);
+// row softmax over fp32/bf16 scores -> bf16 probabilities
+int launch_softmax_rows(const __nv_bfloat16* s, __nv_bfloat16* p, int rows, int cols, float scale,
+                        cudaStream_t stream);
+// NCDHW (fp32 / bf16) <-> channels-last bf16 with channel padding
+int launch_ncdhw_to_cl(const void* in, int is_bf16, __nv_bfloat16* out, int B, int C, int T, int H,
+                       int W, int Cpad, float scale0, float shift0, float scale1, float shift1,
+                       cudaStream_t stream);
+// decoded tile [T][H][W][Cs] bf16 -> fp32 staging planes + blends; see vae.cu
+int launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out, long long n,
+                    cudaStream_t stream);
+
+}  // namespace dv

@@ -1,0 +1,517 @@
+// deepv_b200 — MMDiT denoiser forward: host-side orchestration of the sm_100a kernels.
+//
+// Mirrors reference model/mmdit.py:1467-1530 (MMDiT.forward) for the runnable configuration
+// (sincos spatial pos-emb, temporal RoPE, temporal-causal joint attention, num_stages == 1):
+//   temb      time_text_embed                      mmdit.py:739-753   -> GEMV chain
+//   adaLN     all 2L+1 modulation linears at once  mmdit.py:548,495   -> one GEMV (temb is
+//             block independent, so they are hoisted out of the block loop)
+//   context   context_embedder (+ history tokens)  mmdit.py:1480-1485 -> tcgen05 GEMM
+//   patches   PatchEmbed3D + cropped/interp pos    mmdit.py:882-975   -> patchify + GEMM(+pos)
+//   blocks    JointTransformerBlock x L            mmdit.py:385-433   -> LN-mod, QKV GEMM with
+//             RMSNorm+RoPE epilogue, attention, out-proj/FF GEMMs with gate-residual epilogue
+//   head      norm_out + proj_out + unpatchify (last clip only, mmdit.py:1450,1526-1528)
+// The residual streams are kept in fp32; GEMM operands are bf16.
+#include <vector>
+
+#include "../../include/deepv_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace dv;
+
+struct dv_mmdit {
+  dv_mmdit_config cfg;
+  dv_mmdit_weights w;
+  std::vector<const void*> p_w_qkv_x, p_w_qkv_c, p_w_out_x, p_w_out_c, p_w_ff1_x, p_w_ff2_x,
+      p_w_ff1_c, p_w_ff2_c;
+  std::vector<const float*> p_b_qkv_x, p_b_qkv_c, p_qk_norm_x, p_qk_norm_c, p_b_out_x, p_b_out_c,
+      p_b_ff1_x, p_b_ff2_x, p_b_ff1_c, p_b_ff2_c;
+  float* pos_base = nullptr;  // [S*S][D]
+  float* rope_cs = nullptr;   // [kMaxFrames][32][2]
+  int D = 0;
+};
+
+static constexpr int kMaxFrames = 256;
+
+struct ClipInfo {
+  int t, h, w;       // latent
+  int gh, gw;        // token grid
+  int row0, rows;    // rows inside the video stream
+};
+
+struct dv_mmdit_plan {
+  dv_mmdit* m = nullptr;
+  int B = 0, text_len = 0, hist_tokens = 0, hist_h = 0, hist_w = 0, hist_ds = 1;
+  int Lc = 0, Lv = 0, L = 0, Lpad = 0, n_last = 0;
+  std::vector<ClipInfo> clips;
+  double flops = 0;
+  long long bytes = 0;
+  std::vector<void*> allocs;
+  // device buffers
+  int *frame_x = nullptr, *frame_c = nullptr, *kv_end = nullptr;
+  float *pos_x = nullptr, *pos_h = nullptr;
+  float *x = nullptr, *c = nullptr, *key_bias = nullptr;
+  float *tfeat = nullptr, *g1 = nullptr, *g3 = nullptr, *temb = nullptr, *mod = nullptr;
+  __nv_bfloat16 *xn = nullptr, *cn = nullptr, *qkv = nullptr, *attn = nullptr, *ffh = nullptr;
+  __nv_bfloat16 *patch_a = nullptr, *hist_a = nullptr, *enc_bf = nullptr, *xo = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(dv_mmdit_plan* p, T** out, long long n) {
+  void* ptr = nullptr;
+  const size_t bytes = static_cast<size_t>(n) * sizeof(T);
+  DV_CHECK_CUDA(cudaMalloc(&ptr, bytes ? bytes : 16));
+  DV_CHECK_CUDA(cudaMemset(ptr, 0, bytes ? bytes : 16));
+  p->allocs.push_back(ptr);
+  p->bytes += bytes;
+  *out = reinterpret_cast<T*>(ptr);
+  return 0;
+}
+
+template <typename T, typename S>
+void copy_ptrs(std::vector<T>& dst, S const* src, int n) {
+  dst.assign(src, src + n);
+}
+
+GemmDesc dense_desc(const void* A, long long a_bs, int lda, const void* W, int w_rows,
+                    const float* bias, int B, int M, int N, int K) {
+  GemmDesc d = {};
+  d.batch = B;
+  d.M = M;
+  d.N = N;
+  d.K = K;
+  d.A = A;
+  d.a_batch_stride = a_bs;
+  d.lda = lda;
+  d.a_mode = 0;
+  d.W = W;
+  d.w_rows = w_rows;
+  d.bias = bias;
+  return d;
+}
+
+}  // namespace
+
+extern "C" int dv_mmdit_create(const dv_mmdit_config* cfg, const dv_mmdit_weights* w,
+                               dv_mmdit** out) {
+  DV_REQUIRE(cfg && w && out, "dv_mmdit_create: null argument");
+  DV_REQUIRE(cfg->head_dim == 64, "dv_mmdit_create: head_dim %d != 64", cfg->head_dim);
+  DV_REQUIRE(cfg->patch_size == 2, "dv_mmdit_create: patch_size %d != 2", cfg->patch_size);
+  const int D = cfg->num_heads * cfg->head_dim;
+  DV_REQUIRE(D == 1536, "dv_mmdit_create: inner dim %d != 1536 (LN kernel is specialised)", D);
+  DV_REQUIRE(cfg->patch_k_pad % 64 == 0 && cfg->patch_k_pad >= cfg->in_channels * 4,
+             "dv_mmdit_create: patch_k_pad=%d", cfg->patch_k_pad);
+  DV_REQUIRE(cfg->joint_dim % 64 == 0 && cfg->pooled_dim % 8 == 0, "dv_mmdit_create: dims");
+  const int NL = cfg->num_layers;
+  const int expect_rows = (NL - 1) * 12 * D + 6 * D + 2 * D + 2 * D;
+  DV_REQUIRE(w->mod_rows == expect_rows, "dv_mmdit_create: mod_rows=%d, expected %d", w->mod_rows,
+             expect_rows);
+  dv_mmdit* m = new dv_mmdit();
+  m->cfg = *cfg;
+  m->w = *w;
+  m->D = D;
+  copy_ptrs(m->p_w_qkv_x, w->w_qkv_x, NL);
+  copy_ptrs(m->p_b_qkv_x, w->b_qkv_x, NL);
+  copy_ptrs(m->p_w_qkv_c, w->w_qkv_c, NL);
+  copy_ptrs(m->p_b_qkv_c, w->b_qkv_c, NL);
+  copy_ptrs(m->p_qk_norm_x, w->qk_norm_x, NL);
+  copy_ptrs(m->p_qk_norm_c, w->qk_norm_c, NL);
+  copy_ptrs(m->p_w_out_x, w->w_out_x, NL);
+  copy_ptrs(m->p_b_out_x, w->b_out_x, NL);
+  copy_ptrs(m->p_w_out_c, w->w_out_c, NL);
+  copy_ptrs(m->p_b_out_c, w->b_out_c, NL);
+  copy_ptrs(m->p_w_ff1_x, w->w_ff1_x, NL);
+  copy_ptrs(m->p_b_ff1_x, w->b_ff1_x, NL);
+  copy_ptrs(m->p_w_ff2_x, w->w_ff2_x, NL);
+  copy_ptrs(m->p_b_ff2_x, w->b_ff2_x, NL);
+  copy_ptrs(m->p_w_ff1_c, w->w_ff1_c, NL);
+  copy_ptrs(m->p_b_ff1_c, w->b_ff1_c, NL);
+  copy_ptrs(m->p_w_ff2_c, w->w_ff2_c, NL);
+  copy_ptrs(m->p_b_ff2_c, w->b_ff2_c, NL);
+
+  // base sincos table (PatchEmbed3D buffer, mmdit.py:820-824) and the temporal RoPE table
+  // (EmbedNDRoPE / rope(), mmdit.py:999-1028: fp64 angles, cast to fp32).
+  const int S = cfg->pos_embed_max;
+  cudaError_t e = cudaMalloc(&m->pos_base, static_cast<size_t>(S) * S * D * sizeof(float));
+  if (e != cudaSuccess) {
+    set_error("dv_mmdit_create: cudaMalloc pos table: %s", cudaGetErrorString(e));
+    delete m;
+    return DV_ERR_CUDA;
+  }
+  int rc = launch_pos_base(m->pos_base, S, D, cfg->pos_base_size, 0);
+  if (rc) {
+    delete m;
+    return rc;
+  }
+  std::vector<float> cs(static_cast<size_t>(kMaxFrames) * 64);
+  for (int f = 0; f < kMaxFrames; ++f)
+    for (int i = 0; i < 32; ++i) {
+      const double omega = 1.0 / pow(10000.0, static_cast<double>(2 * i) / 64.0);
+      const double a = static_cast<double>(f) * omega;
+      cs[(f * 32 + i) * 2 + 0] = static_cast<float>(cos(a));
+      cs[(f * 32 + i) * 2 + 1] = static_cast<float>(sin(a));
+    }
+  e = cudaMalloc(&m->rope_cs, cs.size() * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->rope_cs, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("dv_mmdit_create: rope table: %s", cudaGetErrorString(e));
+    delete m;
+    return DV_ERR_CUDA;
+  }
+  *out = m;
+  return DV_OK;
+}
+
+extern "C" void dv_mmdit_destroy(dv_mmdit* m) {
+  if (!m) return;
+  cudaFree(m->pos_base);
+  cudaFree(m->rope_cs);
+  delete m;
+}
+
+extern "C" int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const int* clip_thw,
+                                    int text_len, int has_history, int hist_h, int hist_w,
+                                    int hist_downsample, dv_mmdit_plan** out) {
+  DV_REQUIRE(m && clip_thw && out, "dv_mmdit_plan_create: null argument");
+  DV_REQUIRE(batch >= 1 && batch <= 4, "dv_mmdit_plan_create: batch %d not in [1,4]", batch);
+  DV_REQUIRE(n_clips >= 1, "dv_mmdit_plan_create: n_clips=%d", n_clips);
+  const int D = m->D;
+  const int S = m->cfg.pos_embed_max;
+  dv_mmdit_plan* p = new dv_mmdit_plan();
+  p->m = m;
+  p->B = batch;
+  p->text_len = text_len;
+  auto fail = [&](int rc) {
+    dv_mmdit_plan_destroy(p);
+    return rc;
+  };
+
+  int row = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    ClipInfo ci;
+    ci.t = clip_thw[3 * i];
+    ci.h = clip_thw[3 * i + 1];
+    ci.w = clip_thw[3 * i + 2];
+    if (ci.t < 1 || ci.h % 2 || ci.w % 2 || ci.h < 2 || ci.w < 2) {
+      set_error("dv_mmdit_plan_create: clip %d has invalid dims (%d,%d,%d)", i, ci.t, ci.h, ci.w);
+      return fail(DV_ERR_INVALID);
+    }
+    ci.gh = ci.h / 2;
+    ci.gw = ci.w / 2;
+    ci.row0 = row;
+    ci.rows = ci.t * ci.gh * ci.gw;
+    row += ci.rows;
+    p->clips.push_back(ci);
+  }
+  p->Lv = row;
+  const ClipInfo& last = p->clips.back();
+  p->n_last = last.rows;
+  if (has_history) {
+    p->hist_h = hist_h;
+    p->hist_w = hist_w;
+    p->hist_ds = hist_downsample;
+    if (hist_downsample != 2 || hist_h % 4 || hist_w % 4) {
+      set_error("dv_mmdit_plan_create: history %dx%d / %d unsupported (need ratio 2)", hist_h,
+                hist_w, hist_downsample);
+      return fail(DV_ERR_INVALID);
+    }
+    p->hist_tokens = (hist_h / 4) * (hist_w / 4);
+  }
+  p->Lc = p->hist_tokens + text_len;
+  p->L = p->Lc + p->Lv;
+  p->Lpad = (p->L + 127) / 128 * 128;
+  // every clip's positional crop is taken at the noisy clip's size (mmdit.py:960-962)
+  for (const ClipInfo& ci : p->clips) {
+    if (ci.gh > last.gh || ci.gw > last.gw || last.gh > S || last.gw > S) {
+      set_error("dv_mmdit_plan_create: clip grid %dx%d exceeds the noisy clip's %dx%d", ci.gh,
+                ci.gw, last.gh, last.gw);  // mmdit.py:851-852
+      return fail(DV_ERR_INVALID);
+    }
+  }
+
+  const int B = batch, Lv = p->Lv, Lc = p->Lc, L = p->L;
+  const int Kp = m->cfg.patch_k_pad;
+  int rc = 0;
+#define DV_A(ptr, n)                          \
+  if ((rc = dev_alloc(p, &(ptr), (n))) != 0) return fail(rc)
+  DV_A(p->frame_x, Lv);
+  DV_A(p->frame_c, Lc);
+  DV_A(p->kv_end, L);
+  DV_A(p->pos_x, static_cast<long long>(Lv) * D);
+  DV_A(p->pos_h, static_cast<long long>(p->hist_tokens ? p->hist_tokens : 1) * D);
+  DV_A(p->x, static_cast<long long>(B) * Lv * D);
+  DV_A(p->c, static_cast<long long>(B) * Lc * D);
+  DV_A(p->key_bias, static_cast<long long>(B) * p->Lpad);
+  DV_A(p->tfeat, B * 256);
+  DV_A(p->g1, B * D);
+  DV_A(p->g3, B * D);
+  DV_A(p->temb, B * D);
+  DV_A(p->mod, static_cast<long long>(B) * m->w.mod_rows);
+  DV_A(p->xn, static_cast<long long>(B) * Lv * D);
+  DV_A(p->cn, static_cast<long long>(B) * Lc * D);
+  DV_A(p->qkv, static_cast<long long>(B) * L * 3 * D);
+  DV_A(p->attn, static_cast<long long>(B) * L * D);
+  DV_A(p->ffh, static_cast<long long>(B) * (Lv > Lc ? Lv : Lc) * 4 * D);
+  DV_A(p->patch_a, static_cast<long long>(B) * Lv * Kp);
+  DV_A(p->hist_a, static_cast<long long>(B) * (p->hist_tokens ? p->hist_tokens : 1) * Kp);
+  DV_A(p->enc_bf, static_cast<long long>(B) * text_len * m->cfg.joint_dim);
+  DV_A(p->xo, static_cast<long long>(B) * p->n_last * D);
+#undef DV_A
+
+  // token -> frame ids (mmdit.py:1336-1356: cumulative over clips; context = 0) and the
+  // visible-key prefix of every query (frame(q) >= frame(k), mmdit.py:1430-1433)
+  std::vector<int> fx(Lv), kv(L);
+  std::vector<int> frame_end;  // tokens (joint index) with frame <= f
+  int fbase = 0;
+  for (const ClipInfo& ci : p->clips) {
+    for (int t = 0; t < ci.t; ++t) {
+      for (int r = 0; r < ci.gh * ci.gw; ++r) fx[ci.row0 + t * ci.gh * ci.gw + r] = fbase + t;
+      frame_end.push_back(Lc + ci.row0 + (t + 1) * ci.gh * ci.gw);
+    }
+    fbase += ci.t;
+  }
+  if (fbase > kMaxFrames) {
+    set_error("dv_mmdit_plan_create: %d frames > %d", fbase, kMaxFrames);
+    return fail(DV_ERR_INVALID);
+  }
+  for (int i = 0; i < Lc; ++i) kv[i] = frame_end[0];
+  for (int i = 0; i < Lv; ++i) kv[Lc + i] = frame_end[fx[i]];
+  cudaError_t e = cudaMemcpy(p->frame_x, fx.data(), Lv * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(p->kv_end, kv.data(), L * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("dv_mmdit_plan_create: upload: %s", cudaGetErrorString(e));
+    return fail(DV_ERR_CUDA);
+  }
+  // positional tables (mmdit.py:841-880): crop at the noisy clip's size, resize per clip
+  for (const ClipInfo& ci : p->clips) {
+    rc = launch_pos_clip(m->pos_base, S, D, p->pos_x, ci.row0, ci.t, ci.gh, ci.gw, last.gh, last.gw, 0);
+    if (rc) return fail(rc);
+  }
+  if (p->hist_tokens) {
+    // forward_history_v2 (mmdit.py:985-993): crop at the down-sampled history size, no resize
+    rc = launch_pos_clip(m->pos_base, S, D, p->pos_h, 0, 1, hist_h / 4, hist_w / 4, hist_h / 4,
+                         hist_w / 4, 0);
+    if (rc) return fail(rc);
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("dv_mmdit_plan_create: %s", cudaGetErrorString(e));
+    return fail(DV_ERR_CUDA);
+  }
+
+  // algorithmic FLOPs
+  {
+    const double d = D, NL = m->cfg.num_layers, Bd = B;
+    double lin = 2.0 * Bd * (Lv * 12.0 * d * d * NL + Lc * (12.0 * d * d * (NL - 1) + 3.0 * d * d));
+    lin += 2.0 * Bd * Lv * (m->cfg.in_channels * 4.0) * d + 2.0 * Bd * p->n_last * (m->cfg.in_channels * 4.0) * d;
+    lin += 2.0 * Bd * text_len * m->cfg.joint_dim * d;
+    lin += 2.0 * Bd * p->hist_tokens * (m->cfg.in_channels * 4.0) * d;
+    lin += 2.0 * Bd * d * m->w.mod_rows + 2.0 * Bd * (256.0 * d + d * d + m->cfg.pooled_dim * d + d * d);
+    double pairs = 0;
+    for (int i = 0; i < L; ++i) pairs += kv[i];
+    const double attn = 4.0 * d * NL * Bd * pairs;
+    p->flops = lin + attn;
+  }
+  *out = p;
+  return DV_OK;
+}
+
+extern "C" void dv_mmdit_plan_destroy(dv_mmdit_plan* p) {
+  if (!p) return;
+  for (void* a : p->allocs) cudaFree(a);
+  delete p;
+}
+
+extern "C" long long dv_mmdit_plan_workspace_bytes(const dv_mmdit_plan* p) { return p ? p->bytes : 0; }
+extern "C" double dv_mmdit_plan_flops(const dv_mmdit_plan* p) { return p ? p->flops : 0.0; }
+
+extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, int io_dtype,
+                                const void* enc_dev, int enc_dtype, const float* ctx_mask_dev,
+                                const float* pooled_dev, const float* timestep_dev,
+                                const void* history_dev, void* out_dev, int out_dtype,
+                                void* stream_v) {
+  DV_REQUIRE(p && clips_dev && enc_dev && ctx_mask_dev && pooled_dev && timestep_dev && out_dev,
+             "dv_mmdit_forward: null argument");
+  DV_REQUIRE((p->hist_tokens > 0) == (history_dev != nullptr),
+             "dv_mmdit_forward: history pointer does not match the plan (plan has %d history tokens)",
+             p->hist_tokens);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  dv_mmdit* m = p->m;
+  const dv_mmdit_weights& w = m->w;
+  const int B = p->B, D = m->D, Lv = p->Lv, Lc = p->Lc, L = p->L;
+  const int C = m->cfg.in_channels, Kp = m->cfg.patch_k_pad, NL = m->cfg.num_layers;
+  const int MR = w.mod_rows;
+  const int is_bf16 = io_dtype == DV_DTYPE_BF16;
+  int rc;
+#define DV_RUN(call) \
+  if ((rc = (call)) != 0) return rc
+
+  // ---- conditioning: temb and every adaLN modulation vector -------------------------
+  DV_RUN(launch_timestep_features(timestep_dev, p->tfeat, B, st));
+  DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_t1), w.b_t1, p->tfeat, 256, p->g1, D,
+                     B, D, 256, 0, 0, st));
+  DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_t2), w.b_t2, p->g1, D, p->temb, D, B,
+                     D, D, 1, 0, st));
+  DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_p1), w.b_p1, pooled_dev,
+                     m->cfg.pooled_dim, p->g3, D, B, D, m->cfg.pooled_dim, 0, 0, st));
+  DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_p2), w.b_p2, p->g3, D, p->temb, D, B,
+                     D, D, 1, 1, st));
+  DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_mod), w.b_mod, p->temb, D, p->mod, MR,
+                     B, MR, D, 1, 0, st));
+
+  // ---- context stream: [history tokens | text tokens] ---------------------------------
+  DV_RUN(launch_to_bf16(enc_dev, enc_dtype == DV_DTYPE_BF16, p->enc_bf,
+                        static_cast<long long>(B) * p->text_len * m->cfg.joint_dim, st));
+  {
+    GemmDesc d = dense_desc(p->enc_bf, static_cast<long long>(p->text_len) * m->cfg.joint_dim,
+                            m->cfg.joint_dim, w.w_ctx, D, w.b_ctx, B, p->text_len, D,
+                            m->cfg.joint_dim);
+    d.mode = EPI_F32_ADD;
+    d.out = p->c;
+    d.out_batch_stride = static_cast<long long>(Lc) * D;
+    d.ldo = D;
+    d.out_row_offset = p->hist_tokens;
+    DV_RUN(launch_gemm(d, st));
+  }
+  if (p->hist_tokens) {
+    DV_RUN(launch_patchify(history_dev, is_bf16, p->hist_a, p->hist_tokens, 0, Kp, B, C, 1,
+                           p->hist_h, p->hist_w, 1, st));
+    GemmDesc d = dense_desc(p->hist_a, static_cast<long long>(p->hist_tokens) * Kp, Kp,
+                            w.w_patch_hist, D, w.b_patch_hist, B, p->hist_tokens, D, Kp);
+    d.mode = EPI_F32_ADD;
+    d.out = p->c;
+    d.out_batch_stride = static_cast<long long>(Lc) * D;
+    d.ldo = D;
+    d.addend = p->pos_h;
+    DV_RUN(launch_gemm(d, st));
+  }
+  // ---- video stream: patch embed + positional table -------------------------------------
+  for (size_t i = 0; i < p->clips.size(); ++i) {
+    const ClipInfo& ci = p->clips[i];
+    DV_RUN(launch_patchify(clips_dev[i], is_bf16, p->patch_a, Lv, ci.row0, Kp, B, C, ci.t, ci.h,
+                           ci.w, 0, st));
+  }
+  {
+    GemmDesc d = dense_desc(p->patch_a, static_cast<long long>(Lv) * Kp, Kp, w.w_patch, D,
+                            w.b_patch, B, Lv, D, Kp);
+    d.mode = EPI_F32_ADD;
+    d.out = p->x;
+    d.out_batch_stride = static_cast<long long>(Lv) * D;
+    d.ldo = D;
+    d.addend = p->pos_x;
+    DV_RUN(launch_gemm(d, st));
+  }
+  DV_RUN(launch_key_bias(ctx_mask_dev, Lc, p->key_bias, B, L, p->Lpad, st));
+
+  const long long xs = static_cast<long long>(Lv) * D, cs = static_cast<long long>(Lc) * D;
+  const long long js = static_cast<long long>(L) * D;  // joint (attention output) batch stride
+  // ---- transformer blocks ------------------------------------------------------------------
+  for (int i = 0; i < NL; ++i) {
+    const bool last = (i == NL - 1);
+    const float* mx = p->mod + static_cast<long long>(i) * 12 * D;  // video modulation, 6 chunks
+    const float* mc = mx + 6 * D;                                   // context modulation
+    // norm1 / norm1_context: chunk order shift, scale, gate (msa), shift, scale, gate (mlp)
+    DV_RUN(launch_ln_modulate(p->x, xs, p->xn, xs, mx + 0 * D, mx + 1 * D, MR, B, Lv, D, 1e-6f, st));
+    if (!last) {
+      DV_RUN(launch_ln_modulate(p->c, cs, p->cn, cs, mc + 0 * D, mc + 1 * D, MR, B, Lc, D, 1e-6f, st));
+    } else {
+      // AdaLayerNormContinuous: chunk order scale, shift (mmdit.py:513)
+      DV_RUN(launch_ln_modulate(p->c, cs, p->cn, cs, mc + 1 * D, mc + 0 * D, MR, B, Lc, D, 1e-6f, st));
+    }
+    // fused q|k|v projection + per-head RMSNorm + temporal RoPE, written into the joint layout
+    for (int s = 0; s < 2; ++s) {
+      const bool vid = (s == 0);
+      GemmDesc d = dense_desc(vid ? p->xn : p->cn, vid ? xs : cs, D,
+                              vid ? m->p_w_qkv_x[i] : m->p_w_qkv_c[i], 3 * D,
+                              vid ? m->p_b_qkv_x[i] : m->p_b_qkv_c[i], B, vid ? Lv : Lc, 3 * D, D);
+      d.mode = EPI_QKV;
+      d.out = p->qkv;
+      d.out_batch_stride = static_cast<long long>(L) * 3 * D;
+      d.ldo = 3 * D;
+      d.out_row_offset = vid ? Lc : 0;
+      d.qk_norm_w = vid ? m->p_qk_norm_x[i] : m->p_qk_norm_c[i];
+      d.rope_cs = m->rope_cs;
+      d.frame_id = vid ? p->frame_x : p->frame_c;
+      d.heads_dim = D;
+      DV_RUN(launch_gemm(d, st));
+    }
+    DV_RUN(launch_attention(p->qkv, p->attn, p->kv_end, p->key_bias, B, L, p->Lpad,
+                            m->cfg.num_heads, st));
+    // x += gate_msa * to_out(attn)
+    {
+      GemmDesc d = dense_desc(p->attn + static_cast<long long>(Lc) * D, js, D, m->p_w_out_x[i], D,
+                              m->p_b_out_x[i], B, Lv, D, D);
+      d.mode = EPI_RESID_GATE;
+      d.out = p->x;
+      d.out_batch_stride = xs;
+      d.ldo = D;
+      d.gate = mx + 2 * D;
+      d.gate_batch_stride = MR;
+      DV_RUN(launch_gemm(d, st));
+    }
+    if (!last) {
+      GemmDesc d = dense_desc(p->attn, js, D, m->p_w_out_c[i], D, m->p_b_out_c[i], B, Lc, D, D);
+      d.mode = EPI_RESID_GATE;
+      d.out = p->c;
+      d.out_batch_stride = cs;
+      d.ldo = D;
+      d.gate = mc + 2 * D;
+      d.gate_batch_stride = MR;
+      DV_RUN(launch_gemm(d, st));
+    }
+    // feed-forward, both streams
+    for (int s = 0; s < 2; ++s) {
+      const bool vid = (s == 0);
+      if (!vid && last) break;
+      const float* mm = vid ? mx : mc;
+      float* res = vid ? p->x : p->c;
+      __nv_bfloat16* nrm = vid ? p->xn : p->cn;
+      const long long rs = vid ? xs : cs;
+      const int Ls = vid ? Lv : Lc;
+      DV_RUN(launch_ln_modulate(res, rs, nrm, rs, mm + 3 * D, mm + 4 * D, MR, B, Ls, D, 1e-6f, st));
+      GemmDesc d1 = dense_desc(nrm, rs, D, vid ? m->p_w_ff1_x[i] : m->p_w_ff1_c[i], 4 * D,
+                               vid ? m->p_b_ff1_x[i] : m->p_b_ff1_c[i], B, Ls, 4 * D, D);
+      d1.mode = EPI_GELU;
+      d1.out = p->ffh;
+      d1.out_batch_stride = static_cast<long long>(Ls) * 4 * D;
+      d1.ldo = 4 * D;
+      DV_RUN(launch_gemm(d1, st));
+      GemmDesc d2 = dense_desc(p->ffh, static_cast<long long>(Ls) * 4 * D, 4 * D,
+                               vid ? m->p_w_ff2_x[i] : m->p_w_ff2_c[i], D,
+                               vid ? m->p_b_ff2_x[i] : m->p_b_ff2_c[i], B, Ls, D, 4 * D);
+      d2.mode = EPI_RESID_GATE;
+      d2.out = res;
+      d2.out_batch_stride = rs;
+      d2.ldo = D;
+      d2.gate = mm + 5 * D;
+      d2.gate_batch_stride = MR;
+      DV_RUN(launch_gemm(d2, st));
+    }
+  }
+
+  // ---- head: norm_out (scale, shift) + proj_out + unpatchify, noisy clip only ---------------
+  {
+    const ClipInfo& lc = p->clips.back();
+    const float* mo = p->mod + static_cast<long long>(NL - 1) * 12 * D + 6 * D + 2 * D;
+    DV_RUN(launch_ln_modulate(p->x + static_cast<long long>(lc.row0) * D, xs, p->xo,
+                              static_cast<long long>(p->n_last) * D, mo + 1 * D, mo + 0 * D, MR, B,
+                              p->n_last, D, 1e-6f, st));
+    GemmDesc d = dense_desc(p->xo, static_cast<long long>(p->n_last) * D, D, w.w_proj_out, 4 * C,
+                            w.b_proj_out, B, p->n_last, 4 * C, D);
+    d.mode = EPI_UNPATCH;
+    d.out = out_dev;
+    d.out_batch_stride = static_cast<long long>(C) * lc.t * lc.h * lc.w;
+    d.up_gh = lc.gh;
+    d.up_gw = lc.gw;
+    d.up_C = C;
+    d.out_f32 = (out_dtype == DV_DTYPE_F32);
+    DV_REQUIRE(lc.t == 1, "dv_mmdit_forward: noisy clip must have one latent frame (t=%d)", lc.t);
+    DV_RUN(launch_gemm(d, st));
+  }
+#undef DV_RUN
+  return DV_OK;
+}

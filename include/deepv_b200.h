@@ -1,0 +1,195 @@
+/* deepv_b200 — C ABI of the B200-native DeepVerse denoise + decode hot path.
+ *
+ * The reference (lorenzocean/deepv) has no FFI: its seam is Python duck typing at three call
+ * sites fed by InferencePipeline._create_models (pipeline.py:203-223).  This header is the
+ * boundary a binding for those call sites talks to (INTEGRATION.md shows the ctypes stub):
+ *
+ *   dv_mmdit_*        replaces MMDiT.forward                      model/mmdit.py:1467-1530
+ *   dv_cfg_euler_step replaces the CFG combine + scheduler.step   pipeline.py:502-520,
+ *                                                                model/scheduler.py:230-294
+ *   dv_stage_renoise  replaces the pyramid stage transition       pipeline.py:452-465
+ *   dv_block_noise    replaces sample_block_noise                 pipeline.py:431-437
+ *   dv_vae_*          replaces CausalVideoVAE.decode (tiled)      model/vae.py:885-920,989-1014
+ *
+ * Conventions: plain pointers and sizes only; every pointer named *_dev is DEVICE memory owned
+ * by the caller and must stay alive until the stream has consumed it; calls enqueue work on
+ * `stream` (a cudaStream_t passed as void*) and never synchronise or allocate, except the
+ * *_create / *_plan_create calls, which allocate and may synchronise.  Every call returns 0 on
+ * success or a negative code; dv_last_error() returns a thread-local message.  Handles are not
+ * thread-safe: one per GPU / process.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with DV_ERR_CUDA.
+ */
+#ifndef DEEPV_B200_H_
+#define DEEPV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DV_OK 0
+#define DV_ERR_INVALID (-1)
+#define DV_ERR_CUDA (-2)
+
+#define DV_DTYPE_F32 0
+#define DV_DTYPE_BF16 1
+
+const char* dv_last_error(void);
+int dv_version(void);
+/* number of kernels launched by this library in this process since the last reset */
+long long dv_launch_count(void);
+void dv_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampler step  (bit-exact with the reference's ATen arithmetic)
+ * ------------------------------------------------------------------------------------------ */
+/* noise_pred_dev: [n_branch][numel] (uncond, text[, text+history]); sample/out: [numel].
+ * n_branch 1: no guidance; 2: u + w_text (t - u); 3: ... + w_hist (h - t).
+ * out = dtype( fp32(sample) + (sigma_next - sigma) * guided )                                */
+int dv_cfg_euler_step(const void* noise_pred_dev, int n_branch, const void* sample_dev,
+                      void* out_dev, long long numel, float w_text, float w_hist, double sigma,
+                      double sigma_next, int dtype, void* stream);
+/* lat_lo_dev: [planes][h][w]; noise_dev/out_dev: [planes][2h][2w];
+ * out = alpha * nearest_up2(lat_lo) + beta * noise                                            */
+int dv_stage_renoise(const void* lat_lo_dev, const void* noise_dev, void* out_dev, int planes,
+                     int h, int w, double alpha, double beta, int dtype, void* stream);
+/* z_dev: iid N(0,1) fp32 [planes][h/2][w/2][4]; out_dev: [planes][h][w] with
+ * cov(2x2 block) = (1+gamma) I - gamma 11^T                                                   */
+int dv_block_noise(const float* z_dev, void* out_dev, int planes, int h, int w, float gamma,
+                   int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks (exported for the parity tests and for other bindings)
+ * ------------------------------------------------------------------------------------------ */
+/* C[b][m][n] = epi( sum_k A[b][m][k] W[n][k] + bias[n] );  A, W, C bf16; K % 64 == 0, N % 32 == 0.
+ * epi: 0 identity, 1 gelu-tanh.                                                               */
+int dv_gemm_bf16(const void* A_dev, const void* W_dev, const float* bias_dev, void* C_dev,
+                 int batch, int M, int N, int K, int epi, void* stream);
+/* joint attention over fused qkv [B][L][3*H*64] bf16 -> out [B][L][H*64] bf16.
+ * kv_end_dev: int32 [L] (keys visible to each query = prefix length, non-decreasing);
+ * key_bias_dev: fp32 [B][Lpad], 0 for live keys, -inf for dead keys and k >= L; Lpad % 128 == 0 */
+int dv_attention(const void* qkv_dev, void* out_dev, const int* kv_end_dev,
+                 const float* key_bias_dev, int B, int L, int Lpad, int H, void* stream);
+/* channels-last causal conv3d (zero padded, stride 1): x [B][T][H][W][Cin] bf16,
+ * w [Cout_rows][kt*kh*kw*Cin] bf16 (tap-major, channel-minor), bias fp32 [>= Cout, padded to 32].
+ * store: 0 plain, 1 pixel-shuffle (rows ordered (p1,p2,c)), 2 frame-interleave (rows (p,c)).   */
+int dv_conv3d_cl(const void* x_dev, const void* w_dev, const float* bias_dev,
+                 const void* residual_dev, void* out_dev, int B, int T, int H, int W, int Cin,
+                 int Cout, int w_rows, int ksize, int store, int drop_first, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MMDiT denoiser
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dv_mmdit dv_mmdit;
+typedef struct dv_mmdit_plan dv_mmdit_plan;
+
+typedef struct {
+  int num_layers;        /* 24 */
+  int num_heads;         /* 24 */
+  int head_dim;          /* 64 */
+  int in_channels;       /* 38 */
+  int patch_size;        /* 2  */
+  int joint_dim;         /* 4096 (T5 width) */
+  int pooled_dim;        /* 2048 */
+  int pos_embed_max;     /* 192 */
+  int pos_base_size;     /* sample_size / patch_size = 64 */
+  int patch_k_pad;       /* in_channels * 4 rounded up to 64 = 192 */
+} dv_mmdit_config;
+
+/* All weights are DEVICE pointers owned by the caller; matrices bf16 row-major [out][in],
+ * vectors fp32.  Per-layer arrays have num_layers entries; *_c entries of the last layer that
+ * the reference does not have (context_pre_only block, mmdit.py:378-383) are NULL.            */
+typedef struct {
+  const void* const* w_qkv_x;  const float* const* b_qkv_x;   /* [3*D][D]: to_q | to_k | to_v      */
+  const void* const* w_qkv_c;  const float* const* b_qkv_c;   /* add_q_proj | add_k_proj | add_v_proj */
+  const float* const* qk_norm_x;                               /* [2][64]: norm_q.weight, norm_k.weight */
+  const float* const* qk_norm_c;                               /* norm_add_q, norm_add_k            */
+  const void* const* w_out_x;  const float* const* b_out_x;   /* to_out[0]                          */
+  const void* const* w_out_c;  const float* const* b_out_c;   /* to_add_out (NULL in last layer)    */
+  const void* const* w_ff1_x;  const float* const* b_ff1_x;   /* ff.net[0].proj      [4D][D]        */
+  const void* const* w_ff2_x;  const float* const* b_ff2_x;   /* ff.net[2]           [D][4D]        */
+  const void* const* w_ff1_c;  const float* const* b_ff1_c;   /* ff_context (NULL in last layer)    */
+  const void* const* w_ff2_c;  const float* const* b_ff2_c;
+  /* all adaLN linears concatenated along the output dim, in forward order:
+   * per layer: norm1.linear (6D) then norm1_context.linear (6D; last layer 2D), then
+   * norm_out.linear (2D).  rows = (L-1)*12D + 6D + 2D + 2D                                     */
+  const void* w_mod;  const float* b_mod;  int mod_rows;
+  const void* w_t1;   const float* b_t1;   /* time_text_embed.timestep_embedder.linear_1 [D][256] */
+  const void* w_t2;   const float* b_t2;   /* ...linear_2 [D][D]                                  */
+  const void* w_p1;   const float* b_p1;   /* time_text_embed.text_embedder.linear_1 [D][pooled]  */
+  const void* w_p2;   const float* b_p2;   /* ...linear_2 [D][D]                                  */
+  const void* w_ctx;  const float* b_ctx;  /* context_embedder [D][joint_dim]                     */
+  const void* w_patch;      const float* b_patch;       /* pos_embed.proj as [D][patch_k_pad]      */
+  const void* w_patch_hist; const float* b_patch_hist;  /* pos_embed.proj_history                  */
+  const void* w_proj_out;   const float* b_proj_out;    /* proj_out [4*C][D], bias padded to 32k   */
+} dv_mmdit_weights;
+
+int dv_mmdit_create(const dv_mmdit_config* cfg, const dv_mmdit_weights* w, dv_mmdit** out);
+void dv_mmdit_destroy(dv_mmdit* m);
+
+/* A plan fixes one token layout: batch, the clips of one sample (oldest
+ * first, the LAST one is the noisy clip and the only one returned), context length and the
+ * optional history frame.  clip_thw: n_clips x (t, h, w) in LATENT pixels.  Allocates all
+ * workspace the forward needs.                                                                 */
+int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const int* clip_thw, int text_len,
+                         int has_history, int hist_h, int hist_w, int hist_downsample,
+                         dv_mmdit_plan** out);
+void dv_mmdit_plan_destroy(dv_mmdit_plan* p);
+long long dv_mmdit_plan_workspace_bytes(const dv_mmdit_plan* p);
+/* algorithmic FLOPs of one forward with this plan (SURVEY.md §8d formula, dense attention pairs
+ * restricted to frame-causal ones), for roofline accounting                                   */
+double dv_mmdit_plan_flops(const dv_mmdit_plan* p);
+
+/* clips_dev[i]: [B][C][t_i][h_i][w_i] contiguous, dtype io_dtype.
+ * enc_dev: [B][text_len][joint_dim] (enc_dtype); ctx_mask_dev: fp32 [B][hist_tokens + text_len]
+ * (history mask first, then the text mask; non-zero = live); pooled_dev: fp32 [B][pooled_dim];
+ * timestep_dev: fp32 [B]; history_dev: [B][C][1][hist_h][hist_w] (io_dtype) or NULL.
+ * out_dev: [B][C][1][h][w] of the noisy clip, dtype out_dtype.                                 */
+int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, int io_dtype,
+                     const void* enc_dev, int enc_dtype, const float* ctx_mask_dev,
+                     const float* pooled_dev, const float* timestep_dev, const void* history_dev,
+                     void* out_dev, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Causal video VAE decoder
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dv_vae dv_vae;
+typedef struct dv_vae_plan dv_vae_plan;
+
+typedef struct {
+  int latent_channels;        /* 16 */
+  int out_channels;           /* 3  */
+  int block_channels[4];      /* decoder_block_out_channels, e.g. 128,256,512,512 */
+  int layers_per_block[4];    /* e.g. 3,3,3,3 */
+  int spatial_up[4];          /* per up block (in decoder order): 1,1,1,0 */
+  int temporal_up[4];         /* 1,1,1,0 */
+  int norm_groups;            /* 32 */
+} dv_vae_config;
+
+/* Weights are passed as a flat name-ordered table built by the host side (see
+ * deepv_b200/vae.py:pack_decoder_weights); conv weights bf16 [Cout_rows][taps*Cin_pad],
+ * biases / norm affine fp32.                                                                   */
+typedef struct {
+  const char* name;
+  const void* ptr;
+  long long numel;
+} dv_tensor_ref;
+
+int dv_vae_create(const dv_vae_config* cfg, const dv_tensor_ref* tensors, int n_tensors,
+                  dv_vae** out);
+void dv_vae_destroy(dv_vae* v);
+/* plan for decoding latents [1][16][T][h][w] with the reference's tiling (tile 32 latent px,
+ * stride 24, 64 px blends; vae.py:989-1014)                                                    */
+int dv_vae_plan_create(dv_vae* v, int T, int h, int w, int tile_latent, dv_vae_plan** out);
+void dv_vae_plan_destroy(dv_vae_plan* p);
+double dv_vae_plan_flops(const dv_vae_plan* p);
+/* z_dev: [1][16][T][h][w] (dtype), already un-normalised (pipeline.py:705-709);
+ * out_dev: [1][3][8(T-1)+1][8h][8w] (dtype)                                                    */
+int dv_vae_decode(dv_vae_plan* p, const void* z_dev, int z_dtype, void* out_dev, int out_dtype,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPV_B200_H_ */
