@@ -178,10 +178,11 @@ int launch_block_noise(const float* z, void* out, int planes, int h, int w, floa
       double s = a[i][j];
       for (int k = 0; k < j; ++k) s -= l[i][k] * l[j][k];
       if (i == j) {
-        DV_REQUIRE(s > 0.0, "block_noise: covariance not positive definite (gamma=%f)", gamma);
-        l[i][j] = sqrt(s);
+        // gamma = 1/3 makes the covariance exactly singular (last pivot 0): semi-definite is fine
+        DV_REQUIRE(s > -1e-6, "block_noise: covariance not positive semi-definite (gamma=%f)", gamma);
+        l[i][j] = s > 0.0 ? sqrt(s) : 0.0;
       } else {
-        l[i][j] = s / l[j][j];
+        l[i][j] = l[j][j] > 0.0 ? s / l[j][j] : 0.0;
       }
     }
   const long long total = static_cast<long long>(planes) * (h / 2) * (w / 2);
