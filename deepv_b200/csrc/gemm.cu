@@ -175,10 +175,25 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const TileCoord& t
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
         }
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out) +
-                             static_cast<long long>(tc.b) * d.out_batch_stride +
-                             static_cast<long long>(m + d.out_row_offset) * d.ldo + n;
-        store_bf16x32(out, v);
+        const long long off = static_cast<long long>(tc.b) * d.out_batch_stride +
+                              static_cast<long long>(m + d.out_row_offset) * d.ldo + n;
+        if (d.residual != nullptr) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(d.residual) + off);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t = __ldg(r4 + i);
+            v[8 * i + 0] += bf16_lo(t.x);
+            v[8 * i + 1] += bf16_hi(t.x);
+            v[8 * i + 2] += bf16_lo(t.y);
+            v[8 * i + 3] += bf16_hi(t.y);
+            v[8 * i + 4] += bf16_lo(t.z);
+            v[8 * i + 5] += bf16_hi(t.z);
+            v[8 * i + 6] += bf16_lo(t.w);
+            v[8 * i + 7] += bf16_hi(t.w);
+          }
+        }
+        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + off, v);
       } break;
       case EPI_BF16_ROWBIAS: {
         const float bm = d.bias ? __ldg(d.bias + m) : 0.f;
@@ -382,7 +397,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           } else {
             tma_load_3d(&a.tmA, &full_bar[stage], sa, kb * BK, tc.m_tile * BM, tc.b);
           }
-          tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
+          if (d.w_batch_stride != 0)
+            tma_load_3d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN, tc.b);
+          else
+            tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -527,9 +545,16 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
     int rc = make_tensor_map_bf16(&ka.tmA, d.A, 3, dims, strides, box, 1);
     if (rc) return rc;
   }
-  {
+  const uint64_t ldw_bytes = (uint64_t)(d.ldw > 0 ? d.ldw : K) * 2;
+  if (d.w_batch_stride != 0) {
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)d.w_rows, (uint64_t)d.batch};
+    uint64_t strides[2] = {ldw_bytes, (uint64_t)d.w_batch_stride * 2};
+    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    int rc = make_tensor_map_bf16(&ka.tmB, d.W, 3, dims, strides, box, 1);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)d.w_rows};
-    uint64_t strides[1] = {(uint64_t)K * 2};
+    uint64_t strides[1] = {ldw_bytes};
     uint32_t box[2] = {64, (uint32_t)bn};
     int rc = make_tensor_map_bf16(&ka.tmB, d.W, 2, dims, strides, box, 1);
     if (rc) return rc;

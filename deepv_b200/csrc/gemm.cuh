@@ -16,7 +16,7 @@
 namespace dv {
 
 enum EpiMode : int {
-  EPI_BF16 = 0,        // out_bf16 = acc + bias
+  EPI_BF16 = 0,        // out_bf16 = acc + bias (+ residual_bf16, same layout as out)
   EPI_GELU = 1,        // out_bf16 = gelu_tanh(acc + bias)            (mmdit.py:97)
   EPI_RESID_GATE = 2,  // x_f32 += gate[b][n] * (acc + bias)          (mmdit.py:409-410,416-418,424-431)
   EPI_F32_ADD = 3,     // out_f32 = acc + bias + addend[row_map[m]][n] (patch-embed + pos, mmdit.py:894-935)
@@ -46,6 +46,8 @@ struct GemmDesc {
   // ---- W operand -------------------------------------------------------------
   const void* W;       // bf16 [N_rows][K]
   int w_rows;          // rows present in memory (>= N)
+  long long w_batch_stride;  // elements; 0 = one W shared by every batch entry
+  int ldw;             // elements between W rows; 0 = K (dense)
   // ---- epilogue ---------------------------------------------------------------
   int mode;
   void* out;

@@ -59,22 +59,9 @@ int launch_block_noise(const float* z, void* out, int planes, int h, int w, floa
                        int is_bf16, cudaStream_t stream);
 
 // ---- VAE elementwise (vae_kernels.cu) ---------------------------------------------------
-// per (b, frame, group) mean / rstd over channels-last activations [B][T][H][W][C]
-int launch_gn_stats(const __nv_bfloat16* x, float* stats /*[B*T][G][2]*/, int BT, int HW, int C,
-                    int G, float eps, cudaStream_t stream);
-// y = silu?( (x - mean) * rstd * gamma + beta )
+// y = silu?( (x - mean) * rstd * gamma + beta ) over channels-last bf16 [frames][HW][C]
 int launch_gn_apply(const __nv_bfloat16* x, const float* stats, const float* gamma,
-                    const float* beta, __nv_bfloat16* y, int BT, int HW, int C, int G, int silu,
-                    cudaStream_t stream);
-// row softmax over fp32/bf16 scores -> bf16 probabilities
-int launch_softmax_rows(const __nv_bfloat16* s, __nv_bfloat16* p, int rows, int cols, float scale,
-                        cudaStream_t stream);
-// NCDHW (fp32 / bf16) <-> channels-last bf16 with channel padding
-int launch_ncdhw_to_cl(const void* in, int is_bf16, __nv_bfloat16* out, int B, int C, int T, int H,
-                       int W, int Cpad, float scale0, float shift0, float scale1, float shift1,
-                       cudaStream_t stream);
-// decoded tile [T][H][W][Cs] bf16 -> fp32 staging planes + blends; see vae.cu
-int launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out, long long n,
+                    const float* beta, __nv_bfloat16* y, int frames, int HW, int C, int G, int silu,
                     cudaStream_t stream);
 
 }  // namespace dv

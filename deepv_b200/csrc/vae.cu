@@ -1,0 +1,467 @@
+// deepv_b200 — causal video-VAE decode (latent -> RGB / disparity frames) on the sm_100a kernels.
+//
+// Mirrors reference model/vae.py CausalVideoVAE.decode as the pipeline calls it
+// (pipeline.py:713: temporal_chunk=True, window_size=1, tile_sample_min_size=256):
+//   tiled_decode  (vae.py:989-1014)  6 overlapping 32x32-latent tiles, sequential in-place blends
+//   chunk_decode  (vae.py:903-920)   temporal windows with a 2-frame conv cache
+//   decoder       (vae.py:731-751)   conv_in, mid (res, attn, res), 4 up blocks, GN+SiLU, conv_out
+// B200-first re-design: every tile is decoded in ONE pass over all latent frames (the causal
+// zero padding + cache of the windowed reference is mathematically the same contraction —
+// SURVEY.md App. E.2 — and gives 7x fewer, larger launches); activations are channels-last bf16 so
+// that each 3x3x3 conv is an implicit GEMM whose A tiles are 5-D TMA boxes with hardware zero
+// fill (gemm.cu); pixel-shuffle / frame-interleave are store-address maps in the conv epilogue;
+// the 6-tile geometry and the blend ORDER are kept exactly (per-tile GroupNorm statistics and
+// mid-block attention make tiling observable: 35.7 dB vs untiled).
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/deepv_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace dv;
+
+namespace dv {
+int launch_gn_stats(const __nv_bfloat16* x, double* acc, float* stats, int frames, int HW, int C,
+                    int G, float eps, cudaStream_t stream);
+int launch_softmax_rows(const float* s, __nv_bfloat16* p, long long rows, int cols, float scale,
+                        cudaStream_t stream);
+int launch_transpose(const __nv_bfloat16* in, int ld_in, __nv_bfloat16* out, int frames, int rows,
+                     int cols, cudaStream_t stream);
+int launch_latent_tile(const void* z, int is_bf16, __nv_bfloat16* out, int C, int T, int h, int w,
+                       int y0, int x0, int th, int tw, int Cpad, cudaStream_t stream);
+}  // namespace dv
+
+struct dv_vae {
+  dv_vae_config cfg;
+  std::map<std::string, const void*> t;
+  const void* get(const std::string& n) const {
+    auto it = t.find(n);
+    return it == t.end() ? nullptr : it->second;
+  }
+};
+
+struct TileOut {
+  __nv_bfloat16* px;  // [Tout][H][W][3]
+  int H, W;
+};
+
+struct dv_vae_plan {
+  dv_vae* v = nullptr;
+  int T = 0, h = 0, w = 0, tile = 0, Tout = 0;
+  int rows = 0, cols = 0;
+  std::vector<int> ys, xs;      // latent tile origins
+  std::vector<TileOut> tiles;   // rows * cols
+  __nv_bfloat16* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long buf_elems = 0;
+  __nv_bfloat16 *qk = nullptr, *vt = nullptr, *pr = nullptr;
+  float* sc = nullptr;
+  double* gn_acc = nullptr;
+  float* gn_stats = nullptr;
+  TileOut* tiles_dev = nullptr;
+  double flops = 0;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+struct BlendArgs {
+  const TileOut* tiles;
+  int rows, cols, Tout, Hout, Wout, limit, extent;
+};
+
+template <int DEPTH>
+__device__ float blended(const BlendArgs& a, int i, int j, int t, int y, int x, int c) {
+  const TileOut& tl = a.tiles[i * a.cols + j];
+  float v = __bfloat162float(tl.px[((static_cast<long long>(t) * tl.H + y) * tl.W + x) * 3 + c]);
+  if constexpr (DEPTH > 0) {
+    if (i > 0) {  // blend_v with the (already blended) tile above, vae.py:942-946
+      const TileOut& up = a.tiles[(i - 1) * a.cols + j];
+      const int e = min(min(up.H, tl.H), a.extent);
+      if (y < e) {
+        const float av = blended<DEPTH - 1>(a, i - 1, j, t, up.H - e + y, x, c);
+        const float wy = static_cast<float>(static_cast<double>(y) / e);
+        const float wn = static_cast<float>(1.0 - static_cast<double>(y) / e);
+        v = av * wn + v * wy;
+      }
+    }
+    if (j > 0) {  // blend_h with the (already blended) tile on the left, vae.py:948-952
+      const TileOut& lf = a.tiles[i * a.cols + j - 1];
+      const int e = min(min(lf.W, tl.W), a.extent);
+      if (x < e) {
+        const float av = blended<DEPTH - 1>(a, i, j - 1, t, y, lf.W - e + x, c);
+        const float wx = static_cast<float>(static_cast<double>(x) / e);
+        const float wn = static_cast<float>(1.0 - static_cast<double>(x) / e);
+        v = av * wn + v * wx;
+      }
+    }
+  }
+  return v;
+}
+
+template <typename T>
+__global__ void blend_kernel(BlendArgs a, T* __restrict__ out) {
+  // out: [3][Tout][Hout][Wout]; x fastest -> coalesced stores
+  const long long total = 3LL * a.Tout * a.Hout * a.Wout;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int X = idx % a.Wout;
+  long long r = idx / a.Wout;
+  const int Y = r % a.Hout;
+  r /= a.Hout;
+  const int t = r % a.Tout;
+  const int c = r / a.Tout;
+  const int i = min(Y / a.limit, a.rows - 1), j = min(X / a.limit, a.cols - 1);
+  // depth 3 covers every dependency chain of a row-major sweep (corner -> up -> up-left)
+  const float v = blended<3>(a, i, j, t, Y - i * a.limit, X - j * a.limit, c);
+  if constexpr (sizeof(T) == 2)
+    out[idx] = __float2bfloat16(v);
+  else
+    out[idx] = v;
+}
+
+template <typename T>
+int plan_alloc(dv_vae_plan* p, T** out, long long n) {
+  void* ptr = nullptr;
+  DV_CHECK_CUDA(cudaMalloc(&ptr, static_cast<size_t>(n) * sizeof(T)));
+  p->allocs.push_back(ptr);
+  *out = reinterpret_cast<T*>(ptr);
+  return 0;
+}
+
+struct Act {  // channels-last activation
+  __nv_bfloat16* p;
+  int T, H, W, C;
+  long long elems() const { return static_cast<long long>(T) * H * W * C; }
+};
+
+struct Runner {
+  dv_vae_plan* pl;
+  cudaStream_t st;
+  int rc = 0;
+  double flops = 0;
+  bool dry = false;  // count flops / buffer sizes only
+  long long max_elems = 0;
+
+  const void* W(const std::string& n) {
+    const void* p = pl->v->get(n);
+    if (!p && rc == 0) {
+      set_error("vae: missing tensor '%s'", n.c_str());
+      rc = DV_ERR_INVALID;
+    }
+    return p;
+  }
+  void note(const Act& a) { max_elems = a.elems() > max_elems ? a.elems() : max_elems; }
+
+  // causal conv (vae.py:225-252) as implicit GEMM
+  Act conv(const std::string& name, const Act& x, int cout, int ks, int store, int drop_first,
+           const __nv_bfloat16* residual, __nv_bfloat16* outbuf, int w_rows = -1) {
+    Act y;
+    y.p = outbuf;
+    y.T = x.T;
+    y.H = x.H;
+    y.W = x.W;
+    y.C = cout;
+    if (store == CONV_SHUFFLE_HW) {
+      y.H *= 2;
+      y.W *= 2;
+      y.C = cout / 4;
+    } else if (store == CONV_INTERLEAVE_T) {
+      y.T = 2 * x.T - (drop_first ? 1 : 0);
+      y.C = cout / 2;
+    }
+    note(y);
+    flops += 2.0 * x.T * x.H * x.W * cout * static_cast<double>(ks * ks * ks) * x.C;
+    if (dry || rc) return y;
+    GemmDesc d = {};
+    d.batch = 1;
+    d.N = cout;
+    d.A = x.p;
+    d.a_mode = 1;
+    d.cT = x.T;
+    d.cH = x.H;
+    d.cW = x.W;
+    d.cC = x.C;
+    d.kt = d.kh = d.kw = ks;
+    d.W = W(name + ".weight");
+    d.w_rows = w_rows > 0 ? w_rows : cout;
+    d.bias = reinterpret_cast<const float*>(W(name + ".bias"));
+    d.mode = EPI_CONV;
+    d.out = outbuf;
+    d.conv_store = store;
+    d.conv_drop_first = drop_first;
+    d.residual = residual;
+    d.out_C = y.C;
+    if (rc == 0) rc = launch_gemm(d, st);
+    return y;
+  }
+
+  // per-frame GroupNorm (+ SiLU), vae.py:161-167,298-304
+  Act gn(const std::string& name, const Act& x, bool act, __nv_bfloat16* outbuf) {
+    Act y = x;
+    y.p = outbuf;
+    if (dry || rc) return y;
+    const int G = pl->v->cfg.norm_groups;
+    rc = launch_gn_stats(x.p, pl->gn_acc, pl->gn_stats, x.T, x.H * x.W, x.C, G, 1e-6f, st);
+    if (rc == 0)
+      rc = launch_gn_apply(x.p, pl->gn_stats, reinterpret_cast<const float*>(W(name + ".weight")),
+                           reinterpret_cast<const float*>(W(name + ".bias")), outbuf, x.T, x.H * x.W,
+                           x.C, G, act ? 1 : 0, st);
+    return y;
+  }
+
+  // CausalResnetBlock3D (vae.py:293-310); x lives in buf[ix], result goes to buf[iout]
+  Act resnet(const std::string& name, const Act& x, int cout, int ia, int ib, int iout) {
+    __nv_bfloat16** B = pl->buf;
+    Act a = gn(name + ".norm1", x, true, B[ia]);
+    Act h = conv(name + ".conv1", a, cout, 3, CONV_PLAIN, 0, nullptr, B[ib]);
+    Act a2 = gn(name + ".norm2", h, true, B[ia]);
+    const __nv_bfloat16* res = x.p;
+    if (x.C != cout) {
+      Act sc = conv(name + ".conv_shortcut", x, cout, 1, CONV_PLAIN, 0, nullptr, B[ib]);
+      res = sc.p;  // conv1's output (in B[ib]) has been consumed by norm2 already
+    }
+    return conv(name + ".conv2", a2, cout, 3, CONV_PLAIN, 0, res, B[iout]);
+  }
+
+  // diffusers Attention of the mid block (vae.py:439-445,463-467): per frame, one head of width C
+  Act attention(const std::string& name, const Act& x, int ia, int iout) {
+    __nv_bfloat16** B = pl->buf;
+    const int C = x.C, pix = x.H * x.W, F = x.T;
+    Act xn = gn(name + ".group_norm", x, false, B[ia]);
+    flops += 2.0 * F * pix * C * C * 4 + 4.0 * F * pix * static_cast<double>(pix) * C;
+    Act y = x;
+    y.p = B[iout];
+    note(y);
+    if (dry || rc) return y;
+    auto dense = [&](const void* A, long long abs_, int lda, const void* Wp, int wrows, long long wbs,
+                     int ldw, const float* bias, int M, int N, int K, void* out, long long obs,
+                     int ldo, const void* residual, int mode) {
+      GemmDesc d = {};
+      d.batch = F;
+      d.M = M;
+      d.N = N;
+      d.K = K;
+      d.A = A;
+      d.a_batch_stride = abs_;
+      d.lda = lda;
+      d.W = Wp;
+      d.w_rows = wrows;
+      d.w_batch_stride = wbs;
+      d.ldw = ldw;
+      d.bias = bias;
+      d.mode = mode;
+      d.out = out;
+      d.out_batch_stride = obs;
+      d.ldo = ldo;
+      d.residual = residual;
+      if (rc == 0) rc = launch_gemm(d, st);
+    };
+    const long long pc = static_cast<long long>(pix) * C;
+    // q | k | v in one GEMM: [pix][3C]
+    dense(xn.p, pc, C, W(name + ".to_qkv.weight"), 3 * C, 0, 0,
+          reinterpret_cast<const float*>(W(name + ".to_qkv.bias")), pix, 3 * C, C, pl->qk, 3 * pc,
+          3 * C, nullptr, EPI_BF16);
+    // V^T [C][pix] per frame: the K-major B operand of P V
+    if (rc == 0) rc = launch_transpose(pl->qk + 2 * C, 3 * C, pl->vt, F, pix, C, st);
+    // S = Q K^T in fp32 (A = q columns, B = k columns of the same frame; rows are 3C apart)
+    dense(pl->qk, 3 * pc, 3 * C, pl->qk + C, pix, 3 * pc, 3 * C, nullptr, pix, pix, C, pl->sc,
+          static_cast<long long>(pix) * pix, pix, nullptr, EPI_F32_ADD);
+    if (rc == 0)
+      rc = launch_softmax_rows(pl->sc, pl->pr, static_cast<long long>(F) * pix, pix,
+                               1.0f / sqrtf(static_cast<float>(C)), st);
+    // O = P V
+    dense(pl->pr, static_cast<long long>(pix) * pix, pix, pl->vt, C, pc, 0, nullptr, pix, C, pix,
+          B[ia], pc, C, nullptr, EPI_BF16);
+    // out projection + residual
+    dense(B[ia], pc, C, W(name + ".to_out.0.weight"), C, 0, 0,
+          reinterpret_cast<const float*>(W(name + ".to_out.0.bias")), pix, C, C, y.p, pc, C, x.p,
+          EPI_BF16);
+    return y;
+  }
+};
+
+}  // namespace
+
+extern "C" int dv_vae_create(const dv_vae_config* cfg, const dv_tensor_ref* tensors, int n_tensors,
+                             dv_vae** out) {
+  DV_REQUIRE(cfg && tensors && out, "dv_vae_create: null argument");
+  DV_REQUIRE(cfg->norm_groups == 32, "dv_vae_create: norm_groups=%d (32 supported)", cfg->norm_groups);
+  dv_vae* v = new dv_vae();
+  v->cfg = *cfg;
+  for (int i = 0; i < n_tensors; ++i) v->t[tensors[i].name] = tensors[i].ptr;
+  *out = v;
+  return DV_OK;
+}
+
+extern "C" void dv_vae_destroy(dv_vae* v) { delete v; }
+
+static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, cudaStream_t st,
+                    bool dry, double* flops, long long* max_elems) {
+  const dv_vae_config& c = p->v->cfg;
+  Runner r;
+  r.pl = p;
+  r.st = st;
+  r.dry = dry;
+  const int y0 = p->ys[ti], x0 = p->xs[tj];
+  const int th = std::min(p->tile, p->h - y0), tw = std::min(p->tile, p->w - x0);
+  if (th % 8 || tw % 16) {
+    set_error("vae: latent tile %dx%d must be a multiple of 8x16", th, tw);
+    return DV_ERR_INVALID;
+  }
+  __nv_bfloat16** B = p->buf;
+  Act x{B[0], p->T, th, tw, 64};
+  r.note(x);
+  if (!dry) {
+    r.rc = launch_latent_tile(z, z_bf16, B[0], c.latent_channels, p->T, p->h, p->w, y0, x0, th, tw, 64, st);
+  }
+  const int top = c.block_channels[3];
+  // post_quant_conv (1x1x1, output padded to 64 channels so it can feed conv_in's TMA boxes)
+  x = r.conv("post_quant_conv.conv", x, 64, 1, CONV_PLAIN, 0, nullptr, B[1], 64);
+  x = r.conv("decoder.conv_in.conv", x, top, 3, CONV_PLAIN, 0, nullptr, B[0]);
+  // buffers: x in B[0]; scratch B[1], B[2]; result B[3] -> rotate
+  int cur = 0;
+  auto other = [&](int k) { return (cur + k) & 3; };
+  {
+    x = r.resnet("decoder.mid_block.resnets.0", x, top, other(1), other(2), other(3));
+    cur = other(3);
+    x = r.attention("decoder.mid_block.attentions.0", x, other(1), other(3));
+    cur = other(3);
+    x = r.resnet("decoder.mid_block.resnets.1", x, top, other(1), other(2), other(3));
+    cur = other(3);
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int co = c.block_channels[3 - i];
+    for (int j = 0; j < c.layers_per_block[i]; ++j) {
+      x = r.resnet("decoder.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), x, co,
+                   other(1), other(2), other(3));
+      cur = other(3);
+    }
+    if (c.spatial_up[i]) {
+      x = r.conv("decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv.conv", x, co * 4, 3,
+                 CONV_SHUFFLE_HW, 0, nullptr, B[other(1)]);
+      cur = other(1);
+    }
+    if (c.temporal_up[i]) {
+      x = r.conv("decoder.up_blocks." + std::to_string(i) + ".temporal_upsamplers.0.conv.conv", x,
+                 co * 2, 3, CONV_INTERLEAVE_T, 1, nullptr, B[other(1)]);
+      cur = other(1);
+    }
+  }
+  x = r.gn("decoder.conv_norm_out", x, true, B[other(1)]);
+  TileOut& to = p->tiles[ti * p->cols + tj];
+  Act y = r.conv("decoder.conv_out.conv", x, c.out_channels, 3, CONV_PLAIN, 0, nullptr, to.px, 16);
+  if (dry) {
+    to.H = y.H;
+    to.W = y.W;
+    p->Tout = y.T;
+  }
+  if (flops) *flops += r.flops;
+  if (max_elems && r.max_elems > *max_elems) *max_elems = r.max_elems;
+  return r.rc;
+}
+
+extern "C" int dv_vae_plan_create(dv_vae* v, int T, int h, int w, int tile_latent,
+                                  dv_vae_plan** out) {
+  DV_REQUIRE(v && out, "dv_vae_plan_create: null argument");
+  DV_REQUIRE(T >= 1 && h >= 8 && w >= 16 && tile_latent >= 8, "dv_vae_plan_create: T=%d h=%d w=%d", T,
+             h, w);
+  dv_vae_plan* p = new dv_vae_plan();
+  p->v = v;
+  p->T = T;
+  p->h = h;
+  p->w = w;
+  p->tile = tile_latent;
+  auto fail = [&](int rc) {
+    dv_vae_plan_destroy(p);
+    return rc;
+  };
+  // tile origins (vae.py:990-997): stride = 3/4 tile when the latent exceeds one tile
+  const bool tiled = (h > tile_latent) || (w > tile_latent);
+  const int stride = tiled ? (tile_latent * 3) / 4 : (h > w ? h : w);
+  for (int y = 0; y < h; y += stride) p->ys.push_back(y);
+  for (int x = 0; x < w; x += stride) p->xs.push_back(x);
+  if (!tiled) {
+    p->ys.assign(1, 0);
+    p->xs.assign(1, 0);
+    p->tile = h > w ? h : w;
+  }
+  p->rows = static_cast<int>(p->ys.size());
+  p->cols = static_cast<int>(p->xs.size());
+  p->tiles.resize(static_cast<size_t>(p->rows) * p->cols);
+  long long max_elems = 0;
+  for (int i = 0; i < p->rows; ++i)
+    for (int j = 0; j < p->cols; ++j) {
+      int rc = run_tile(p, nullptr, 0, i, j, 0, true, &p->flops, &max_elems);
+      if (rc) return fail(rc);
+    }
+  p->buf_elems = max_elems;
+  int rc = 0;
+  for (int k = 0; k < 4; ++k)
+    if ((rc = plan_alloc(p, &p->buf[k], max_elems)) != 0) return fail(rc);
+  const int top = v->cfg.block_channels[3];
+  const long long pix = static_cast<long long>(p->tile) * p->tile;
+  if ((rc = plan_alloc(p, &p->qk, static_cast<long long>(T) * pix * 3 * top)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->vt, static_cast<long long>(T) * pix * top)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->sc, static_cast<long long>(T) * pix * pix)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->pr, static_cast<long long>(T) * pix * pix)) != 0) return fail(rc);
+  const int max_frames = 8 * T + 8;
+  if ((rc = plan_alloc(p, &p->gn_acc, static_cast<long long>(max_frames) * 64 * 2)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->gn_stats, static_cast<long long>(max_frames) * 64 * 2)) != 0) return fail(rc);
+  cudaError_t e = cudaMemset(p->gn_acc, 0, static_cast<size_t>(max_frames) * 64 * 2 * sizeof(double));
+  for (auto& to : p->tiles) {
+    if ((rc = plan_alloc(p, &to.px, static_cast<long long>(p->Tout) * to.H * to.W * 3)) != 0)
+      return fail(rc);
+  }
+  if ((rc = plan_alloc(p, &p->tiles_dev, static_cast<long long>(p->tiles.size()))) != 0) return fail(rc);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->tiles_dev, p->tiles.data(), p->tiles.size() * sizeof(TileOut),
+                   cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("dv_vae_plan_create: %s", cudaGetErrorString(e));
+    return fail(DV_ERR_CUDA);
+  }
+  *out = p;
+  return DV_OK;
+}
+
+extern "C" void dv_vae_plan_destroy(dv_vae_plan* p) {
+  if (!p) return;
+  for (void* a : p->allocs) cudaFree(a);
+  delete p;
+}
+
+extern "C" double dv_vae_plan_flops(const dv_vae_plan* p) { return p ? p->flops : 0.0; }
+
+extern "C" int dv_vae_decode(dv_vae_plan* p, const void* z_dev, int z_dtype, void* out_dev,
+                             int out_dtype, void* stream) {
+  DV_REQUIRE(p && z_dev && out_dev, "dv_vae_decode: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < p->rows; ++i)
+    for (int j = 0; j < p->cols; ++j) {
+      int rc = run_tile(p, z_dev, z_dtype == DV_DTYPE_BF16, i, j, st, false, nullptr, nullptr);
+      if (rc) return rc;
+    }
+  BlendArgs a;
+  a.tiles = p->tiles_dev;
+  a.rows = p->rows;
+  a.cols = p->cols;
+  a.Tout = p->Tout;
+  const int scale = 8;
+  a.Hout = p->h * scale;
+  a.Wout = p->w * scale;
+  a.extent = (p->tile * scale) / 4;          // blend_extent = tile_sample_min_size * 0.25
+  a.limit = p->tile * scale - a.extent;      // row_limit
+  if (p->rows == 1 && p->cols == 1) a.limit = (a.Hout > a.Wout ? a.Hout : a.Wout) + 1;
+  const long long total = 3LL * a.Tout * a.Hout * a.Wout;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (out_dtype == DV_DTYPE_BF16)
+    blend_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a, reinterpret_cast<__nv_bfloat16*>(out_dev));
+  else
+    blend_kernel<float><<<blocks, 256, 0, st>>>(a, reinterpret_cast<float*>(out_dev));
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return DV_OK;
+}

@@ -1,0 +1,254 @@
+// deepv_b200 — HBM-bound kernels of the VAE decoder: per-frame GroupNorm (+SiLU), row
+// softmax for the mid-block attention, layout conversion and the tile blend.
+// Activations are channels-last bf16: [frames][H*W][C].
+#include "kernels.cuh"
+
+namespace dv {
+namespace {
+
+// ---------------------------------------------------------------------------------
+// GroupNorm statistics (reference CausalGroupNorm, vae.py:161-167: frames folded into the
+// batch, 32 groups, eps 1e-6).  Pass 1: per-CTA partial (sum, sumsq) per group in fp32,
+// merged with fp64 atomics; pass 2 (gn_finalize) turns them into (mean, rstd).
+// ---------------------------------------------------------------------------------
+constexpr int kGnThreads = 256;
+constexpr int kGnPixPerCta = 256;
+
+__global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                double* __restrict__ acc, int HW,
+                                                                int C, int G) {
+  // grid: (ceil(HW / kGnPixPerCta), frames).  Thread t owns the 8-channel vector (t % (C/8)) and
+  // strides over pixels, so every thread always accumulates into ONE group.
+  const int f = blockIdx.y;
+  const int vec_per_pix = C / 8;
+  const int cpg = C / G;  // channels per group: 4, 8 or 16
+  const int p0 = blockIdx.x * kGnPixPerCta;
+  const int p1 = min(p0 + kGnPixPerCta, HW);
+  const uint4* xf = reinterpret_cast<const uint4*>(x + static_cast<long long>(f) * HW * C);
+  __shared__ float s_sum[64], s_sq[64];
+  if (threadIdx.x < 64) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int v = threadIdx.x % vec_per_pix;           // requires blockDim % vec_per_pix == 0
+  const int pstep = kGnThreads / vec_per_pix;
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;      // cpg == 4 -> two groups per 8-vector
+  for (int p = p0 + threadIdx.x / vec_per_pix; p < p1; p += pstep) {
+    const uint4 t = __ldg(xf + static_cast<long long>(p) * vec_per_pix + v);
+    const float e[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y),
+                        bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s0 += e[i];
+      q0 += e[i] * e[i];
+    }
+#pragma unroll
+    for (int i = 4; i < 8; ++i) {
+      s1 += e[i];
+      q1 += e[i] * e[i];
+    }
+  }
+  if (cpg == 4) {
+    atomicAdd(&s_sum[(v * 8) / 4], s0);
+    atomicAdd(&s_sq[(v * 8) / 4], q0);
+    atomicAdd(&s_sum[(v * 8) / 4 + 1], s1);
+    atomicAdd(&s_sq[(v * 8) / 4 + 1], q1);
+  } else {
+    atomicAdd(&s_sum[(v * 8) / cpg], s0 + s1);
+    atomicAdd(&s_sq[(v * 8) / cpg], q0 + q1);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(&acc[(static_cast<long long>(f) * G + threadIdx.x) * 2 + 0],
+              static_cast<double>(s_sum[threadIdx.x]));
+    atomicAdd(&acc[(static_cast<long long>(f) * G + threadIdx.x) * 2 + 1],
+              static_cast<double>(s_sq[threadIdx.x]));
+  }
+}
+
+__global__ void gn_finalize_kernel(double* __restrict__ acc, float* __restrict__ stats, int n,
+                                   double inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = acc[2 * i] * inv_count;
+  double var = acc[2 * i + 1] * inv_count - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  stats[2 * i] = static_cast<float>(mean);
+  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  acc[2 * i] = 0.0;  // leave the accumulator clean for the next use
+  acc[2 * i + 1] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                       const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta,
+                                                       __nv_bfloat16* __restrict__ y, long long HWv,
+                                                       int C, int G, int do_silu, long long total) {
+  // one 8-channel vector per thread; total = frames * HW * C / 8
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vec_per_pix = C / 8;
+  const int v = i % vec_per_pix;
+  const long long f = i / HWv;  // HWv = HW * vec_per_pix
+  const int c0 = v * 8;
+  const int cpg = C / G;
+  const uint4 t = __ldg(reinterpret_cast<const uint4*>(x) + i);
+  float e[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y),
+                bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (c0 + k) / cpg;
+    const float2 ms = __ldg(reinterpret_cast<const float2*>(stats) + f * G + g);
+    float r = (e[k] - ms.x) * ms.y * gm[k] + bt[k];
+    e[k] = do_silu ? silu(r) : r;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(e[0], e[1]);
+  o.y = pack_bf16x2(e[2], e[3]);
+  o.z = pack_bf16x2(e[4], e[5]);
+  o.w = pack_bf16x2(e[6], e[7]);
+  reinterpret_cast<uint4*>(y)[i] = o;
+}
+
+// softmax over rows of fp32 scores (single 512-wide head of the mid block: diffusers
+// Attention at vae.py:439-445, scale = 1/sqrt(C)); one warp per row, in place allowed.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s,
+                                                           __nv_bfloat16* __restrict__ p,
+                                                           long long rows, int cols, float scale) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + row * cols;
+  __nv_bfloat16* pr = p + row * cols;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, sr[c] * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += __expf(sr[c] * scale - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  for (int c = lane; c < cols; c += 32)
+    pr[c] = __float2bfloat16(__expf(sr[c] * scale - m) * inv);
+}
+
+// [frames][rows][cols] -> [frames][cols][rows]  (V^T for the P V product)
+__global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, int ld_in,
+                                 __nv_bfloat16* __restrict__ out, int rows, int cols) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int f = blockIdx.z;
+  const __nv_bfloat16* src = in + static_cast<long long>(f) * rows * ld_in;
+  __nv_bfloat16* dst = out + static_cast<long long>(f) * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[static_cast<long long>(r) * ld_in + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[static_cast<long long>(c) * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float ldv(const T* p, long long i) {
+  if constexpr (sizeof(T) == 2)
+    return __bfloat162float(p[i]);
+  else
+    return p[i];
+}
+
+// latent tile: z [C][T][h][w] (batch 1) cropped at (y0, x0) -> [T][th][tw][Cpad] bf16
+template <typename T>
+__global__ void latent_tile_kernel(const T* __restrict__ z, __nv_bfloat16* __restrict__ out, int C,
+                                   int Tn, int h, int w, int y0, int x0, int th, int tw, int Cpad) {
+  const long long total = static_cast<long long>(Tn) * th * tw * Cpad;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = i % Cpad;
+  long long r = i / Cpad;
+  const int x = r % tw;
+  r /= tw;
+  const int y = r % th;
+  const int t = r / th;
+  float v = 0.f;
+  if (c < C) v = ldv(z, ((static_cast<long long>(c) * Tn + t) * h + (y0 + y)) * w + (x0 + x));
+  out[i] = __float2bfloat16(v);
+}
+
+}  // namespace
+
+int launch_gn_stats(const __nv_bfloat16* x, double* acc, float* stats, int frames, int HW, int C,
+                    int G, float eps, cudaStream_t stream) {
+  DV_REQUIRE(C % 8 == 0 && G <= 64 && C % G == 0, "gn_stats: C=%d G=%d", C, G);
+  const int cpg = C / G;
+  DV_REQUIRE(cpg == 4 || cpg % 8 == 0, "gn_stats: %d channels per group unsupported", cpg);
+  DV_REQUIRE(kGnThreads % (C / 8) == 0, "gn_stats: C=%d does not divide the CTA", C);
+  dim3 grid((HW + kGnPixPerCta - 1) / kGnPixPerCta, frames);
+  gn_partial_kernel<<<grid, kGnThreads, 0, stream>>>(x, acc, HW, C, G);
+  DV_CHECK_CUDA(cudaGetLastError());
+  const int n = frames * G;
+  gn_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(
+      acc, stats, n, 1.0 / (static_cast<double>(HW) * cpg), eps);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch(2);
+  return 0;
+}
+
+int launch_gn_apply(const __nv_bfloat16* x, const float* stats, const float* gamma,
+                    const float* beta, __nv_bfloat16* y, int frames, int HW, int C, int G, int silu_on,
+                    cudaStream_t stream) {
+  const long long total = static_cast<long long>(frames) * HW * C / 8;
+  const long long HWv = static_cast<long long>(HW) * (C / 8);
+  gn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      x, stats, gamma, beta, y, HWv, C, G, silu_on, total);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_softmax_rows(const float* s, __nv_bfloat16* p, long long rows, int cols, float scale,
+                        cudaStream_t stream) {
+  const long long threads = rows * 32;
+  softmax_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(s, p, rows,
+                                                                                       cols, scale);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_transpose(const __nv_bfloat16* in, int ld_in, __nv_bfloat16* out, int frames, int rows,
+                     int cols, cudaStream_t stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, frames);
+  transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, ld_in, out, rows, cols);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_latent_tile(const void* z, int is_bf16, __nv_bfloat16* out, int C, int T, int h, int w,
+                       int y0, int x0, int th, int tw, int Cpad, cudaStream_t stream) {
+  const long long total = static_cast<long long>(T) * th * tw * Cpad;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (is_bf16)
+    latent_tile_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(z), out, C, T, h, w, y0, x0, th, tw, Cpad);
+  else
+    latent_tile_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(z), out, C,
+                                                          T, h, w, y0, x0, th, tw, Cpad);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+}  // namespace dv

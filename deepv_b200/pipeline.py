@@ -1,0 +1,169 @@
+"""Rollout glue around the B200 denoiser / scheduler / VAE: the host side of the hot loop.
+
+Mirrors the call surface of reference `InferencePipeline` for the hot path only:
+  generate_one_unit   pipeline.py:439-524   stage x step loop, CFG, stage transition
+  decode_latent       pipeline.py:703-725   latent un-normalisation + tiled VAE decode
+  pyramid_conditions  pipeline.py:621-658   condition clip lists per stage (host glue)
+`prompt_type text|action` and `add_depth` (run.py:374-382) only select which prompt embeddings
+are fed and whether the disparity decode is saved; both branches run the same kernels here.
+The reference's control plane (CLI, image IO, pose feedback, text encoders) is out of scope
+ and can keep calling these methods unchanged — see INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check
+from .mmdit import B200MMDiT
+from .scheduler import B200Scheduler
+from .vae import B200VAE
+
+VAE_SHIFT, VAE_SCALE = 0.1490, 1 / 1.8415               # pipeline.py:194-195
+VAE_VIDEO_SHIFT, VAE_VIDEO_SCALE = -0.2343, 1 / 3.0986   # pipeline.py:196-197
+
+DEFAULT_CFG = dict(stages=[1, 2, 4], frame_per_unit=1, max_temporal_length=8, vae_downsample=8,
+                   raymap_dim=6, history_guidance_scale=6.0, history_downsample_ratio=2,
+                   num_inference_steps=5)  # run.py:16-50
+
+
+class B200Pipeline:
+    def __init__(self, dit: B200MMDiT, vae: Optional[B200VAE], scheduler: B200Scheduler,
+                 model_cfg: Optional[dict] = None, device="cuda", torch_dtype=torch.bfloat16,
+                 guidance_scale: float = 4.0, video_guidance_scale: float = 3.5):
+        self.model, self.vae, self.scheduler = dit, vae, scheduler
+        self.model_cfg = dict(DEFAULT_CFG, **(model_cfg or {}))
+        self.device = torch.device(device)
+        self.dtype = torch_dtype
+        self._guidance_scale = guidance_scale
+        self._video_guidance_scale = video_guidance_scale
+        self.lib = _lib.load()
+
+    @property
+    def do_classifier_free_guidance(self):
+        return self._guidance_scale > 0
+
+    # -- pipeline.py:431-437 on the device ------------------------------------------------------
+    def sample_block_noise(self, bs, ch, temp, height, width, generator=None, dtype=None):
+        """2x2-block correlated noise, cov (1+g) I - g 11^T; distribution-level equivalent of the
+        reference's per-block CPU MultivariateNormal loop."""
+        dtype = dtype or self.dtype
+        planes = bs * ch * temp
+        z = torch.randn((planes, height // 2, width // 2, 4), device=self.device, dtype=torch.float32,
+                        generator=generator)
+        out = torch.empty((bs, ch, temp, height, width), device=self.device, dtype=dtype)
+        check(self.lib.dv_block_noise(z.data_ptr(), out.data_ptr(), planes, height, width,
+                                      float(self.scheduler.config.gamma), _lib.dtype_code(dtype),
+                                      _lib.stream_ptr()), "dv_block_noise")
+        return out
+
+    # -- pipeline.py:439-524 ------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate_one_unit(self, latents, input_history, past_conditions, prompt_embeds,
+                          prompt_attention_mask, pooled_prompt_embeds, num_inference_steps,
+                          height=None, width=None, temp=1, device=None, dtype=None, generator=None,
+                          is_first_frame: bool = False, block_noise: Optional[Sequence[torch.Tensor]] = None,
+                          timestep_dtype=None):
+        stages = self.model_cfg["stages"]
+        n_branch = 3 if input_history is not None else (2 if self.do_classifier_free_guidance else 1)
+        w_text = self._guidance_scale if is_first_frame else self._video_guidance_scale
+        w_hist = self.model_cfg["history_guidance_scale"]
+        latents = latents.contiguous()
+        dt = latents.dtype
+        history = None
+        history_mask = None
+        if input_history is not None:
+            history = torch.cat([input_history] * 3).to(dt)
+            hlen = int((input_history.size(-1) / self.model_cfg["history_downsample_ratio"] / 2) *
+                       (input_history.size(-2) / self.model_cfg["history_downsample_ratio"] / 2))
+            b = input_history.size(0)
+            history_mask = torch.cat([torch.zeros(2 * b, hlen), torch.ones(b, hlen)]).to(self.device)
+        enc = prompt_embeds.to(self.device)
+        enc_mask = prompt_attention_mask.to(self.device)
+        pooled = pooled_prompt_embeds.to(self.device)
+        intermed = []
+        for i_s in range(len(stages)):
+            self.scheduler.set_timesteps(num_inference_steps[i_s], i_s, device=None)
+            timesteps = self.scheduler._timesteps_host
+            if i_s > 0:
+                b, c, t, h, w = latents.shape
+                ori = 1 - self.scheduler.ori_start_sigmas[i_s]
+                gamma = self.scheduler.config.gamma
+                alpha = 1 / (math.sqrt(1 + (1 / gamma)) * (1 - ori) + ori)
+                beta = alpha * (1 - ori) / math.sqrt(gamma)
+                if block_noise is not None:
+                    noise = block_noise[i_s - 1].to(device=self.device, dtype=dt).contiguous()
+                else:
+                    noise = self.sample_block_noise(b, c, t, 2 * h, 2 * w, generator, dt)
+                up = torch.empty((b, c, t, 2 * h, 2 * w), device=self.device, dtype=dt)
+                check(self.lib.dv_stage_renoise(latents.data_ptr(), noise.data_ptr(), up.data_ptr(),
+                                                b * c * t, h, w, alpha, beta, _lib.dtype_code(dt),
+                                                _lib.stream_ptr()), "dv_stage_renoise")
+                latents = up
+            for idx in range(len(timesteps)):
+                x_in = torch.cat([latents] * n_branch) if n_branch > 1 else latents
+                # pipeline.py:473 casts the timestep to the latent dtype; timestep_dtype=float32
+                # keeps it unrounded for comparisons against the fp32 oracle
+                tval = torch.tensor(float(timesteps[idx]), dtype=torch.float64)
+                tt = tval.to(timestep_dtype or dt).to(torch.float32)
+                tvec = tt.expand(x_in.shape[0]).to(self.device)
+                noise_pred = self.model(
+                    sample=[list(past_conditions[i_s]) + [x_in]], timestep_ratio=tvec,
+                    encoder_hidden_states=enc, encoder_attention_mask=enc_mask,
+                    pooled_projections=pooled, history=history,
+                    history_downsample_ratio=self.model_cfg["history_downsample_ratio"] if history is not None else None,
+                    history_mask=history_mask)[0]
+                latents = self.scheduler.cfg_step(noise_pred, latents, n_branch, w_text, w_hist)
+            intermed.append(latents)
+        return intermed
+
+    # -- pipeline.py:621-658 ------------------------------------------------------------------------
+    def pyramid_conditions(self, generated: torch.Tensor, unit_index: int, firstframe_mask: bool,
+                           n_branch: int) -> List[List[torch.Tensor]]:
+        """Condition clip lists per stage: last frame at the stage's resolution, older frames one
+        stage lower each, everything older than that at stage 0; oldest first."""
+        nst = len(self.model_cfg["stages"])
+        fpu = self.model_cfg["frame_per_unit"]
+        pyr = [generated]
+        x = generated
+        for _ in range(nst - 1):
+            b, c, t, h, w = x.shape
+            x2 = F.interpolate(x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w), size=(h // 2, w // 2),
+                               mode="bilinear")
+            x = x2.view(b, t, c, h // 2, w // 2).permute(0, 2, 1, 3, 4)
+            pyr.append(x)
+        pyr = list(reversed(pyr))
+        rep = (lambda z: torch.cat([z] * n_branch)) if n_branch > 1 else (lambda z: z)
+        out = []
+        for i_s in range(nst):
+            clips = [rep(pyr[i_s][:, :, -fpu:])]
+            cur_stage, ptx = i_s, 1
+            while ptx < unit_index - firstframe_mask:
+                cur_stage = max(cur_stage - 1, 0)
+                if cur_stage == 0:
+                    break
+                ptx += 1
+                clips.append(rep(pyr[cur_stage][:, :, -(ptx * fpu):-((ptx - 1) * fpu)]))
+            if cur_stage == 0 and ptx < unit_index - firstframe_mask:
+                clips.append(rep(pyr[0][:, :, int(firstframe_mask):-(ptx * fpu)]))
+            out.append(list(reversed(clips)))
+        return out
+
+    # -- pipeline.py:703-725 ------------------------------------------------------------------------
+    @torch.no_grad()
+    def decode_latent(self, latents: torch.Tensor, save_memory: bool = True, out_dtype=None):
+        latents = latents.clone()
+        if latents.shape[2] == 1:
+            latents = (latents / VAE_SCALE) + VAE_SHIFT
+        else:
+            latents[:, :, :1] = (latents[:, :, :1] / VAE_SCALE) + VAE_SHIFT
+            latents[:, :, 1:] = (latents[:, :, 1:] / VAE_VIDEO_SCALE) + VAE_VIDEO_SHIFT
+        if not save_memory:
+            raise _lib.DeepVError("decode_latent: only the save_memory=True (256 px tile) branch exists; "
+                                  "the reference's 512 px branch crashes (SURVEY.md App. E.2)")
+        return self.vae.decode(latents, temporal_chunk=True, window_size=1, tile_sample_min_size=256,
+                               out_dtype=out_dtype).sample

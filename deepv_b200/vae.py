@@ -1,0 +1,194 @@
+"""Host-side mirror of the reference VAE decode (`model/vae.py:CausalVideoVAE.decode`).
+
+`B200VAE` is what `InferencePipeline._create_models` returns in place of `CausalVideoVAE`
+for the decode half of the hot path: `.decode(z, temporal_chunk=True, window_size=1,
+tile_sample_min_size=256).sample` (pipeline.py:713), `.enable_tiling()`, `.eval()`, `.to()`,
+`.device`, `.dtype`.  `encode` is outside the hot path and is delegated to an
+optional reference encoder object supplied by the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import TensorRef, VAEConfig, check
+
+
+def pack_decoder_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Dict[str, torch.Tensor]:
+    """Re-layout the decoder state dict (names of oracle/weights.py == reference state_dict):
+    conv weights [Cout,Cin,kt,kh,kw] -> bf16 [Cout_rows][taps*Cin_pad] (tap-major, Cin padded to a
+    multiple of 64); pixel-shuffle convs get their rows permuted (c p1 p2)->(p1 p2 c), frame-
+    interleave convs (c p)->(p c) so that the GEMM epilogue stores contiguous channel runs
+    (vae.py:382,407); biases fp32 in the same order, padded to a multiple of 32."""
+    out: Dict[str, torch.Tensor] = {}
+
+    def pad_to(t, n, dim=0):
+        if t.shape[dim] >= n:
+            return t
+        pad = [0, 0] * (t.dim() - dim - 1) + [0, n - t.shape[dim]]
+        return F.pad(t, pad)
+
+    def conv(name, perm=None, rows=None):
+        w = sd[name + ".weight"].float()
+        b = sd[name + ".bias"].float()
+        co, ci = w.shape[0], w.shape[1]
+        if perm == "hw":      # rows (c, p1, p2) -> (p1, p2, c)
+            idx = torch.arange(co).view(co // 4, 4).t().reshape(-1)
+            w, b = w[idx], b[idx]
+        elif perm == "t":     # rows (c, p) -> (p, c)
+            idx = torch.arange(co).view(co // 2, 2).t().reshape(-1)
+            w, b = w[idx], b[idx]
+        cip = (ci + 63) // 64 * 64
+        w = pad_to(w.permute(0, 2, 3, 4, 1), cip, dim=4).reshape(co, -1)
+        if rows is not None:
+            w = pad_to(w, rows, dim=0)
+        b = pad_to(b, max(32, (b.shape[0] + 31) // 32 * 32, rows or 0))
+        out[name + ".weight"] = w.to(device=device, dtype=torch.bfloat16).contiguous()
+        out[name + ".bias"] = b.to(device=device, dtype=torch.float32).contiguous()
+
+    def vec(name):
+        out[name] = sd[name].to(device=device, dtype=torch.float32).contiguous()
+
+    chans = list(reversed(cfg["decoder_block_out_channels"]))
+    conv("post_quant_conv.conv", rows=64)
+    conv("decoder.conv_in.conv")
+    a = "decoder.mid_block.attentions.0."
+    vec(a + "group_norm.weight")
+    vec(a + "group_norm.bias")
+    out[a + "to_qkv.weight"] = torch.cat([sd[a + "to_q.weight"], sd[a + "to_k.weight"], sd[a + "to_v.weight"]]) \
+        .to(device=device, dtype=torch.bfloat16).contiguous()
+    out[a + "to_qkv.bias"] = torch.cat([sd[a + "to_q.bias"], sd[a + "to_k.bias"], sd[a + "to_v.bias"]]) \
+        .to(device=device, dtype=torch.float32).contiguous()
+    out[a + "to_out.0.weight"] = sd[a + "to_out.0.weight"].to(device=device, dtype=torch.bfloat16).contiguous()
+    vec(a + "to_out.0.bias")
+
+    def resnet(name):
+        for n in ("norm1", "norm2"):
+            vec(f"{name}.{n}.weight")
+            vec(f"{name}.{n}.bias")
+        conv(name + ".conv1.conv")
+        conv(name + ".conv2.conv")
+        if name + ".conv_shortcut.conv.weight" in sd:
+            conv(name + ".conv_shortcut.conv")
+
+    resnet("decoder.mid_block.resnets.0")
+    resnet("decoder.mid_block.resnets.1")
+    for i in range(len(chans)):
+        for j in range(cfg["decoder_layers_per_block"][i]):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}")
+        if cfg["decoder_spatial_up_sample"][i]:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv.conv", perm="hw")
+        if cfg["decoder_temporal_up_sample"][i]:
+            conv(f"decoder.up_blocks.{i}.temporal_upsamplers.0.conv.conv", perm="t")
+    vec("decoder.conv_norm_out.weight")
+    vec("decoder.conv_norm_out.bias")
+    conv("decoder.conv_out.conv", rows=16)
+    return out
+
+
+class B200VAE:
+    """Drop-in for the decode side of reference `CausalVideoVAE`."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], config: dict, device="cuda",
+                 dtype=torch.bfloat16, reference_encoder=None):
+        self.lib = _lib.load()
+        self.config = dict(config)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.DeepVError("B200VAE needs a CUDA device (sm_100a); no CPU fallback")
+        self.dtype = dtype
+        self.use_tiling = False
+        self.reference_encoder = reference_encoder
+        self._packed = pack_decoder_weights(state_dict, config, self.device)
+        self._names = [n.encode() for n in self._packed]
+        refs = (TensorRef * len(self._packed))()
+        for i, (n, t) in enumerate(self._packed.items()):
+            refs[i] = TensorRef(self._names[i], t.data_ptr(), t.numel())
+        ch = config["decoder_block_out_channels"]
+        c = VAEConfig()
+        c.latent_channels = config["decoder_in_channels"]
+        c.out_channels = 3
+        for i in range(4):
+            c.block_channels[i] = ch[i]
+            c.layers_per_block[i] = config["decoder_layers_per_block"][i]
+            c.spatial_up[i] = int(config["decoder_spatial_up_sample"][i])
+            c.temporal_up[i] = int(config["decoder_temporal_up_sample"][i])
+        c.norm_groups = config.get("decoder_norm_num_groups", 32)
+        self._handle = C.c_void_p()
+        check(self.lib.dv_vae_create(C.byref(c), refs, len(self._packed), C.byref(self._handle)),
+              "dv_vae_create")
+        self._plans: Dict[tuple, int] = {}
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def enable_tiling(self, use_tiling: bool = True):
+        self.use_tiling = use_tiling
+
+    def _plan(self, T, h, w, tile):
+        key = (T, h, w, tile)
+        p = self._plans.get(key)
+        if p is None:
+            hdl = C.c_void_p()
+            check(self.lib.dv_vae_plan_create(self._handle, T, h, w, tile, C.byref(hdl)),
+                  "dv_vae_plan_create")
+            p = hdl.value
+            self._plans[key] = p
+        return p
+
+    def plan_flops(self, T, h, w, tile=32) -> float:
+        return self.lib.dv_vae_plan_flops(self._plan(T, h, w, tile))
+
+    def decode(self, z: torch.Tensor, return_dict: bool = True, is_init_image=True,
+               temporal_chunk=False, window_size=2, tile_sample_min_size=256, out_dtype=None):
+        """Reference signature vae.py:885-886.  temporal_chunk / window_size do not change the
+        result and are accepted for call compatibility."""
+        _lib.require_cuda(z)
+        if z.shape[0] != 1:
+            outs = [self.decode(z[i:i + 1], True, is_init_image, temporal_chunk, window_size,
+                                tile_sample_min_size, out_dtype).sample for i in range(z.shape[0])]
+            return SimpleNamespace(sample=torch.cat(outs, dim=0))
+        if z.dtype not in (torch.float32, torch.bfloat16):
+            z = z.float()
+        z = z.contiguous()
+        _, _, T, h, w = z.shape
+        tile = int(tile_sample_min_size / 8)
+        if not self.use_tiling:
+            tile = max(h, w)
+        plan = self._plan(T, h, w, tile)
+        od = out_dtype or z.dtype
+        out = torch.empty((1, 3, 8 * (T - 1) + 1, 8 * h, 8 * w), device=z.device, dtype=od)
+        check(self.lib.dv_vae_decode(plan, z.data_ptr(), _lib.dtype_code(z.dtype), out.data_ptr(),
+                                     _lib.dtype_code(od), _lib.stream_ptr()), "dv_vae_decode")
+        self._last = z
+        if not return_dict:
+            return (out,)
+        return SimpleNamespace(sample=out)
+
+    def encode(self, x, *a, **k):
+        if self.reference_encoder is None:
+            raise _lib.DeepVError("B200VAE.encode: the encoder is outside the hot path (SURVEY.md §8 "
+                                  "f1); pass reference_encoder= to delegate")
+        return self.reference_encoder.encode(x, *a, **k)
+
+    def close(self):
+        for p in self._plans.values():
+            self.lib.dv_vae_plan_destroy(p)
+        self._plans.clear()
+        if self._handle:
+            self.lib.dv_vae_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,242 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the CPU oracle and the golden
+vectors of the real reference.  Tolerances follow BASELINE.json north_star:
+  * scheduler / CFG / stage transition / indexing: bit-exact
+  * denoiser forward: max|a-b| / max|ref| <= 2e-2 (bf16 operands vs fp32 reference)
+  * decoded frames: PSNR >= 40 dB over [-1, 1]
+"""
+import math
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import mmdit_ref, scheduler_ref, vae_ref, weights
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+DENOISER_TOL = 2e-2
+PSNR_FLOOR_DB = 40.0
+
+
+def rel_max(a, b):
+    return ((a.float().cpu() - b.float().cpu()).abs().max() / b.float().abs().max()).item()
+
+
+def psnr(a, b, peak=2.0):
+    mse = ((a.float().cpu() - b.float().cpu()) ** 2).mean().item()
+    return 10 * math.log10(peak * peak / max(mse, 1e-20))
+
+
+@pytest.fixture(scope="module")
+def dit2():
+    from deepv_b200.mmdit import B200MMDiT
+    cfg, W = weights.mmdit_weights(dict(num_layers=2), seed=1)
+    return cfg, W, B200MMDiT(W, cfg, out_dtype=torch.float32)
+
+
+def _run_case(model, case, dtype=torch.float32):
+    inp = cases.mmdit_inputs(case)
+    dev = "cuda"
+    y = model(sample=[[c.to(dev, dtype) for c in inp["clips"]]], timestep_ratio=inp["t"].to(dev),
+              encoder_hidden_states=inp["enc"].to(dev), encoder_attention_mask=inp["mask"].to(dev),
+              pooled_projections=inp["pooled"].to(dev),
+              history=inp["hist"].to(dev, dtype) if inp["hist"] is not None else None,
+              history_mask=inp["hmask"].to(dev) if inp["hmask"] is not None else None,
+              history_downsample_ratio=2 if inp["hist"] is not None else None)[0]
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("name", ["two_block_b2", "two_block_b3_hist"])
+def test_mmdit_vs_reference_golden(dit2, name):
+    cfg, W, model = dit2
+    gold = torch.load(G / "mmdit_golden.pt")[name]
+    y = _run_case(model, cases.MMDIT_CASES[name])
+    assert y.shape == gold.shape
+    assert torch.isfinite(y).all()
+    err = rel_max(y, gold)
+    print(f"{name}: max|a-b|/max|ref| = {err:.3e}")
+    assert err <= DENOISER_TOL
+
+
+def test_mmdit_three_block_mixed_golden():
+    from deepv_b200.mmdit import B200MMDiT
+    case = cases.MMDIT_CASES["three_block_mixed"]
+    cfg, W = weights.mmdit_weights(case["cfg"], seed=case["wseed"])
+    model = B200MMDiT(W, cfg, out_dtype=torch.float32)
+    gold = torch.load(G / "mmdit_golden.pt")["three_block_mixed"]
+    err = rel_max(_run_case(model, case), gold)
+    print(f"three_block_mixed: {err:.3e}")
+    assert err <= DENOISER_TOL
+
+
+def test_mmdit_bf16_io_and_padding_invariance(dit2):
+    """bf16 latents in / bf16 out; padded text tokens must not influence the output
+    (SURVEY.md §4 invariance: dead tokens never reach live ones)."""
+    cfg, W, model = dit2
+    case = cases.MMDIT_CASES["two_block_b2"]
+    inp = cases.mmdit_inputs(case)
+    dev = "cuda"
+
+    def run(enc):
+        return model(sample=[[c.to(dev, torch.bfloat16) for c in inp["clips"]]],
+                     timestep_ratio=inp["t"].to(dev), encoder_hidden_states=enc.to(dev),
+                     encoder_attention_mask=inp["mask"].to(dev),
+                     pooled_projections=inp["pooled"].to(dev))[0]
+    y1 = run(inp["enc"])
+    enc2 = inp["enc"].clone()
+    enc2[0, 1:] = 7.0   # row 0 has one live token; scribble over the padded ones
+    enc2[1, 12:] = -3.0
+    y2 = run(enc2)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    gold = torch.load(G / "mmdit_golden.pt")["two_block_b2"]
+    assert rel_max(y1, gold) <= DENOISER_TOL
+
+
+def test_mmdit_full_depth_vs_oracle():
+    """24 blocks (the real depth), first-unit stage-1 layout, against the fp32 oracle."""
+    from deepv_b200.mmdit import B200MMDiT
+    cfg, W = weights.mmdit_weights(None, seed=1)
+    model = B200MMDiT(W, cfg, out_dtype=torch.float32)
+    case = dict(clips=[(1, 24, 32), (1, 24, 32)], B=2, hist=None, lens=[1, 12], t=654.5895004272461,
+                seed=41)
+    inp = cases.mmdit_inputs(case)
+    with torch.no_grad():
+        ref = mmdit_ref.mmdit_forward(W, cfg, inp["clips"], inp["t"], inp["enc"], inp["mask"], inp["pooled"])
+    y = _run_case(model, case)
+    err = rel_max(y, ref)
+    print(f"full depth: max|a-b|/max|ref| = {err:.3e} (ref absmax {ref.abs().max():.3f})")
+    assert err <= DENOISER_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("nb", [1, 2, 3])
+def test_cfg_euler_bit_exact(dtype, nb):
+    from deepv_b200.scheduler import B200Scheduler
+    s = B200Scheduler(**cases.SCHEDULER_KW)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 38, 1, 48, 64, generator=g).to(dtype)
+    pred = torch.randn(nb, 38, 1, 48, 64, generator=g).to(dtype)
+    tb = scheduler_ref.pyramid_tables(**cases.SCHEDULER_KW)
+    _, sig = scheduler_ref.stage_schedule(tb, 5, 1)
+    s.set_timesteps(5, 1)
+    cur_ref, cur = x, x.cuda()
+    for k in range(5):
+        guided = scheduler_ref.cfg_combine(pred, 3.5, 6.0)
+        cur_ref = scheduler_ref.euler_step(cur_ref, guided, float(sig[k]), float(sig[k + 1]))
+        cur = s.cfg_step(pred.cuda(), cur, nb, 3.5, 6.0)
+        assert torch.equal(cur.cpu(), cur_ref), f"step {k}"
+
+
+def test_scheduler_step_matches_reference_golden():
+    from deepv_b200.scheduler import B200Scheduler
+    for dtype in (torch.bfloat16, torch.float32):
+        gold = torch.load(G / "scheduler_step_golden.pt")[str(dtype)]
+        x, v = cases.step_inputs(dtype)
+        s = B200Scheduler(**cases.SCHEDULER_KW)
+        s.set_timesteps(5, 0, device="cuda")
+        cur = x.cuda()
+        for k in range(5):
+            cur = s.step(model_output=v.cuda(), timestep=s.timesteps[k], sample=cur).prev_sample
+            assert torch.equal(cur.cpu(), gold[k])
+
+
+def test_stage_renoise_bit_exact_and_block_noise_cov(lib):
+    from deepv_b200 import _lib
+    g = torch.Generator().manual_seed(6)
+    for dtype in (torch.bfloat16, torch.float32):
+        lo = torch.randn(38, 12, 16, generator=g).to(dtype)
+        nz = torch.randn(38, 24, 32, generator=g).to(dtype)
+        a, b = scheduler_ref.renoise_coefficients(0.6669999957084656, 0.3333)
+        out = torch.empty(38, 24, 32, device="cuda", dtype=dtype)
+        lo_d, nz_d = lo.cuda(), nz.cuda()
+        _lib.check(lib.dv_stage_renoise(lo_d.data_ptr(), nz_d.data_ptr(), out.data_ptr(), 38, 12, 16, a, b,
+                                        _lib.dtype_code(dtype), None))
+        torch.cuda.synchronize()
+        up = torch.nn.functional.interpolate(lo[None], size=(24, 32), mode="nearest")[0]
+        assert torch.equal(out.cpu(), a * up + b * nz)
+    # distribution-level parity of the block noise (pipeline.py:431-437)
+    z = torch.randn(400000, 4, device="cuda")
+    out = torch.empty(100, 80, 200, device="cuda")
+    _lib.check(lib.dv_block_noise(z.data_ptr(), out.data_ptr(), 100, 80, 200, 0.3333, 0, None))
+    blk = out.view(100, 40, 2, 100, 2).permute(0, 1, 3, 2, 4).reshape(-1, 4).double()
+    cov = (blk.t() @ blk / blk.shape[0]).cpu()
+    assert (cov - scheduler_ref.block_noise_cov(0.3333).double()).abs().max() < 0.02
+
+
+# ---------------------------------------------------------------------------------------------
+def _vae(cfg_over, seed):
+    from deepv_b200.vae import B200VAE
+    cfg, W = weights.vae_weights(cfg_over, seed=seed)
+    v = B200VAE(W, cfg, dtype=torch.float32)
+    v.enable_tiling()
+    return cfg, W, v
+
+
+def test_vae_tiled_decode_vs_oracle():
+    over = dict(decoder_block_out_channels=(128, 128, 128, 128), encoder_block_out_channels=(128, 128, 128, 128),
+                decoder_layers_per_block=(1, 1, 1, 1))
+    cfg, W, v = _vae(over, 7)
+    z = torch.randn(1, 16, 2, 40, 64, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        ref = vae_ref.tiled_decode(W, cfg, z, 256, 1, True)
+    y = v.decode(z.cuda(), temporal_chunk=True, window_size=1, tile_sample_min_size=256).sample
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape == (1, 3, 9, 320, 512)
+    p = psnr(y, ref)
+    print(f"vae tiled: PSNR {p:.1f} dB, max abs {(y.cpu() - ref).abs().max():.3e}, ref absmax {ref.abs().max():.2f}")
+    assert p >= PSNR_FLOOR_DB
+    # seams: the blended bands must match as well as the interior
+    band = psnr(y[..., 180:260, :], ref[..., 180:260, :])
+    assert band >= PSNR_FLOOR_DB
+
+
+def test_vae_untiled_three_frames_vs_oracle():
+    over = dict(decoder_block_out_channels=(128, 128, 128, 128), encoder_block_out_channels=(128, 128, 128, 128),
+                decoder_layers_per_block=(1, 1, 1, 1))
+    cfg, W, v = _vae(over, 9)
+    z = torch.randn(1, 16, 3, 16, 32, generator=torch.Generator().manual_seed(10))
+    with torch.no_grad():
+        ref = vae_ref.tiled_decode(W, cfg, z, 256, 1, True)
+    y = v.decode(z.cuda(), temporal_chunk=True, window_size=1, tile_sample_min_size=256).sample
+    assert y.shape == ref.shape == (1, 3, 17, 128, 256)
+    p = psnr(y, ref)
+    print(f"vae untiled: PSNR {p:.1f} dB")
+    assert p >= PSNR_FLOOR_DB
+
+
+# ---------------------------------------------------------------------------------------------
+def test_generate_one_unit_vs_oracle(dit2):
+    """3 stages x 2 steps through the public pipeline API with injected block noise."""
+    from deepv_b200.pipeline import B200Pipeline
+    from deepv_b200.scheduler import B200Scheduler
+    cfg, W, model = dit2
+    pipe = B200Pipeline(model, None, B200Scheduler(**cases.SCHEDULER_KW), torch_dtype=torch.float32)
+    g = torch.Generator().manual_seed(12)
+    lat = torch.randn(1, 38, 1, 8, 8, generator=g)
+    conds = [[torch.randn(2, 38, 1, 8 * 2 ** i, 8 * 2 ** i, generator=g)] for i in range(3)]
+    noise = [torch.randn(1, 38, 1, 16, 16, generator=g), torch.randn(1, 38, 1, 32, 32, generator=g)]
+    enc = torch.randn(2, 77, 4096, generator=g)
+    pooled = torch.randn(2, 2048, generator=g)
+    mask = torch.zeros(2, 77, dtype=torch.long)
+    mask[0, :1] = 1
+    mask[1, :12] = 1
+    tb = scheduler_ref.pyramid_tables(**cases.SCHEDULER_KW)
+
+    def model_fn(clips, tt):
+        return mmdit_ref.mmdit_forward(W, cfg, clips, tt.float(), enc, mask, pooled)
+
+    with torch.no_grad():
+        ref = scheduler_ref.generate_one_unit(model_fn, tb, lat, conds, noise, 2, [2, 2, 2], 3.5, 6.0,
+                                              timestep_dtype=torch.float32)
+    out = pipe.generate_one_unit(lat.cuda(), None, [[c.cuda() for c in cl] for cl in conds], enc, mask, pooled,
+                                 [2, 2, 2], block_noise=noise, timestep_dtype=torch.float32)
+    torch.cuda.synchronize()
+    for i in range(3):
+        e = rel_max(out[i], ref[i])
+        print(f"unit stage {i}: latent max|a-b|/max|ref| = {e:.3e}")
+        assert out[i].shape == ref[i].shape
+        assert e <= 3e-2  # ~2% latent drift per unit for bf16 vs fp32
