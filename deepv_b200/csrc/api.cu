@@ -14,6 +14,14 @@ extern "C" int dv_version(void) { return 100; }
 extern "C" long long dv_launch_count(void) { return launch_count(); }
 extern "C" void dv_launch_count_reset(void) { launch_count_reset(); }
 
+extern "C" void dv_profile_enable(int on) { prof_enable(on != 0); }
+extern "C" void dv_profile_reset(void) { prof_reset(); }
+extern "C" int dv_profile_summary(int kind, long long* count, double* ms, double* flops,
+                                  double* bytes) {
+  DV_REQUIRE(count && ms && flops && bytes, "dv_profile_summary: null pointer");
+  return prof_summary(kind, count, ms, flops, bytes);
+}
+
 extern "C" int dv_cfg_euler_step(const void* noise_pred_dev, int n_branch, const void* sample_dev,
                                  void* out_dev, long long numel, float w_text, float w_hist,
                                  double sigma, double sigma_next, int dtype, void* stream) {

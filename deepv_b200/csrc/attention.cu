@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 }  // namespace
 
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias, int B,
-                     int L, int Lpad, int H, cudaStream_t stream) {
+                     int L, int Lpad, int H, cudaStream_t stream, double flops) {
   DV_REQUIRE(Lpad % 128 == 0 && Lpad >= L, "attention: Lpad=%d must be a multiple of 128 >= L=%d",
              Lpad, L);
   DV_REQUIRE(B > 0 && L > 0 && H > 0, "attention: empty problem B=%d L=%d H=%d", B, L, H);
@@ -300,7 +300,9 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
     attr_set = true;
   }
   dim3 grid((L + kQ - 1) / kQ, H, B);
+  const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream);
   attn_kernel<<<grid, kAttnThreads, kSmemBytes, stream>>>(a);
+  prof_end(pid, stream);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace dv {
 
@@ -21,6 +22,81 @@ const char* last_error() { return g_err; }
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 void launch_count_reset() { g_launches.store(0, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------
+// Optional per-launch profiler: CUDA event pairs on the launching stream around every kernel
+// of a class, with the algorithmic FLOPs / bytes of that launch.  Off by default (zero cost);
+// bench.py switches it on for one step to get roofline.achieved of the dominant kernel.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int kind;
+  double flops, bytes;
+};
+constexpr int kProfMax = 1 << 16;
+bool g_prof_on = false;
+std::vector<ProfRec>* g_prof = nullptr;
+std::vector<cudaEvent_t>* g_prof_pool = nullptr;
+cudaEvent_t prof_event() {
+  if (g_prof_pool && !g_prof_pool->empty()) {
+    cudaEvent_t e = g_prof_pool->back();
+    g_prof_pool->pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void prof_enable(bool on) {
+  if (!g_prof) g_prof = new std::vector<ProfRec>();
+  if (!g_prof_pool) g_prof_pool = new std::vector<cudaEvent_t>();
+  g_prof_on = on;
+}
+void prof_reset() {
+  if (!g_prof) return;
+  for (auto& r : *g_prof) {
+    g_prof_pool->push_back(r.e0);
+    g_prof_pool->push_back(r.e1);
+  }
+  g_prof->clear();
+}
+int prof_begin(int kind, double flops, double bytes, cudaStream_t st) {
+  if (!g_prof_on || static_cast<int>(g_prof->size()) >= kProfMax) return -1;
+  ProfRec r;
+  r.e0 = prof_event();
+  r.e1 = prof_event();
+  r.kind = kind;
+  r.flops = flops;
+  r.bytes = bytes;
+  cudaEventRecord(r.e0, st);
+  g_prof->push_back(r);
+  return static_cast<int>(g_prof->size()) - 1;
+}
+void prof_end(int id, cudaStream_t st) {
+  if (id >= 0) cudaEventRecord((*g_prof)[id].e1, st);
+}
+// caller must have synchronised the stream(s)
+int prof_summary(int kind, long long* count, double* ms, double* flops, double* bytes) {
+  *count = 0;
+  *ms = *flops = *bytes = 0;
+  if (!g_prof) return 0;
+  for (auto& r : *g_prof) {
+    if (r.kind != kind) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) {
+      set_error("prof_summary: events not complete (synchronise first)");
+      return -2;
+    }
+    *count += 1;
+    *ms += t;
+    *flops += r.flops;
+    *bytes += r.bytes;
+  }
+  return 0;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

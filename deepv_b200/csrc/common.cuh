@@ -22,6 +22,13 @@ const char* last_error();
 void note_launch(int n = 1);
 long long launch_count();
 void launch_count_reset();
+// per-launch event profiler (kinds: 0 dense GEMM, 1 conv implicit GEMM, 2 attention, 3 other)
+enum ProfKind : int { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_OTHER = 3 };
+void prof_enable(bool on);
+void prof_reset();
+int prof_begin(int kind, double flops, double bytes, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+int prof_summary(int kind, long long* count, double* ms, double* flops, double* bytes);
 #define DV_CHECK_CUDA(expr)                                                        \
   do {                                                                             \
     cudaError_t _e = (expr);                                                       \

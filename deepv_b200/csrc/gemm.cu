@@ -560,14 +560,24 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
     if (rc) return rc;
   }
 
+  const double rows = static_cast<double>(ka.m_tiles ? (d.a_mode == 1 ? (double)d.cT * d.cH * d.cW : d.M) : 0) * d.batch;
+  const int pid = prof_begin(d.a_mode == 1 ? PROF_CONV : PROF_GEMM, 2.0 * rows * d.N * K,
+                             2.0 * (rows * K / (d.a_mode == 1 ? d.kt * d.kh * d.kw : 1) + (double)d.N * K + rows * d.N),
+                             stream);
+  int rc;
   switch (bn) {
     case 256:
-      return launch_bn<256>(ka, stream);
+      rc = launch_bn<256>(ka, stream);
+      break;
     case 128:
-      return launch_bn<128>(ka, stream);
+      rc = launch_bn<128>(ka, stream);
+      break;
     default:
-      return launch_bn<64>(ka, stream);
+      rc = launch_bn<64>(ka, stream);
+      break;
   }
+  prof_end(pid, stream);
+  return rc;
 }
 
 }  // namespace dv

@@ -7,7 +7,7 @@ namespace dv {
 
 // ---- attention (attention.cu) ------------------------------------------------------
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias, int B,
-                     int L, int Lpad, int H, cudaStream_t stream);
+                     int L, int Lpad, int H, cudaStream_t stream, double flops = 0.0);
 
 // ---- MMDiT elementwise (elementwise.cu) -----------------------------------------------
 // out_bf16[b][l][:] = LN(x[b][l][:]) * (1 + scale[b][:]) + shift[b][:]   (eps inside sqrt)

@@ -44,7 +44,7 @@ struct dv_mmdit_plan {
   int B = 0, text_len = 0, hist_tokens = 0, hist_h = 0, hist_w = 0, hist_ds = 1;
   int Lc = 0, Lv = 0, L = 0, Lpad = 0, n_last = 0;
   std::vector<ClipInfo> clips;
-  double flops = 0;
+  double flops = 0, attn_flops_layer = 0;
   long long bytes = 0;
   std::vector<void*> allocs;
   // device buffers
@@ -315,6 +315,7 @@ extern "C" int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const i
     for (int i = 0; i < L; ++i) pairs += kv[i];
     const double attn = 4.0 * d * NL * Bd * pairs;
     p->flops = lin + attn;
+    p->attn_flops_layer = 4.0 * d * Bd * pairs;
   }
   *out = p;
   return DV_OK;
@@ -440,7 +441,7 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
       DV_RUN(launch_gemm(d, st));
     }
     DV_RUN(launch_attention(p->qkv, p->attn, p->kv_end, p->key_bias, B, L, p->Lpad,
-                            m->cfg.num_heads, st));
+                            m->cfg.num_heads, st, p->attn_flops_layer));
     // x += gate_msa * to_out(attn)
     {
       GemmDesc d = dense_desc(p->attn + static_cast<long long>(Lc) * D, js, D, m->p_w_out_x[i], D,

@@ -216,14 +216,14 @@ struct Runner {
   Act resnet(const std::string& name, const Act& x, int cout, int ia, int ib, int iout) {
     __nv_bfloat16** B = pl->buf;
     Act a = gn(name + ".norm1", x, true, B[ia]);
-    Act h = conv(name + ".conv1", a, cout, 3, CONV_PLAIN, 0, nullptr, B[ib]);
+    Act h = conv(name + ".conv1.conv", a, cout, 3, CONV_PLAIN, 0, nullptr, B[ib]);
     Act a2 = gn(name + ".norm2", h, true, B[ia]);
     const __nv_bfloat16* res = x.p;
     if (x.C != cout) {
-      Act sc = conv(name + ".conv_shortcut", x, cout, 1, CONV_PLAIN, 0, nullptr, B[ib]);
+      Act sc = conv(name + ".conv_shortcut.conv", x, cout, 1, CONV_PLAIN, 0, nullptr, B[ib]);
       res = sc.p;  // conv1's output (in B[ib]) has been consumed by norm2 already
     }
-    return conv(name + ".conv2", a2, cout, 3, CONV_PLAIN, 0, res, B[iout]);
+    return conv(name + ".conv2.conv", a2, cout, 3, CONV_PLAIN, 0, res, B[iout]);
   }
 
   // diffusers Attention of the mid block (vae.py:439-445,463-467): per frame, one head of width C

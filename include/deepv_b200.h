@@ -40,6 +40,13 @@ int dv_version(void);
 /* number of kernels launched by this library in this process since the last reset */
 long long dv_launch_count(void);
 void dv_launch_count_reset(void);
+/* Per-launch CUDA-event profiler (off by default).  kind: 0 dense tcgen05 GEMM, 1 implicit-GEMM
+ * conv3d, 2 attention, 3 other.  dv_profile_summary sums launches, device milliseconds and the
+ * algorithmic FLOPs / bytes of every launch of that kind since the last reset; synchronise the
+ * stream first.                                                                               */
+void dv_profile_enable(int on);
+void dv_profile_reset(void);
+int dv_profile_summary(int kind, long long* count, double* ms, double* flops, double* bytes);
 
 /* ------------------------------------------------------------------------------------------
  * Sampler step  (bit-exact with the reference's ATen arithmetic)
