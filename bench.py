@@ -316,16 +316,25 @@ def run_ours(args):
             ud.append(e)
         return ud, [t.to(dev, non_blocking=True) for t in dec]
 
+    from deepv_b200.parallel import Shard
+    shard = Shard.current()
+
     def step(units, dec, fetch):
         outs = []
         for d in units:
+            # one rollout sharded over the ranks: CFG branches on different GPUs when there are enough
+            # ranks (all-gather of the branch predictions per step), else the whole CFG batch locally
+            sh = shard if (shard.active and shard.world >= d["n_branch"]) else None
             lat = pipe.generate_one_unit(d["latents"], d["history"], d["cond_tensors"], d["enc"], d["mask"],
-                                         d["pooled"], STEPS_PER_STAGE, block_noise=d["block_noise"])
+                                         d["pooled"], STEPS_PER_STAGE, block_noise=d["block_noise"], shard=sh)
             outs.append(lat[-1])
         # the rollout decodes the first 16 (RGB) and next 16 (disparity) latent channels of all units
         # (pipeline.py:686-696); synthetic latents of that shape keep the decode at [1,16,lat_T,48,64]
-        img = pipe.decode_latent(dec[0])
-        dsp = pipe.decode_latent(dec[1])
+        if shard.active:
+            img, dsp = pipe.decode_latents_sharded([dec[0], dec[1]], shard)  # tiles x modalities over ranks
+        else:
+            img = pipe.decode_latent(dec[0])
+            dsp = pipe.decode_latent(dec[1])
         if fetch:
             return img.to("cpu", non_blocking=True), dsp.to("cpu", non_blocking=True)
         return img, dsp

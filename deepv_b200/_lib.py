@@ -88,6 +88,11 @@ SIGNATURES = {
     "dv_vae_plan_destroy": (None, [_vp]),
     "dv_vae_plan_flops": (_d, [_vp]),
     "dv_vae_decode": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "dv_vae_plan_geometry": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "dv_vae_plan_tile_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "dv_vae_plan_bind_tile": (_i, [_vp, _i, _vp]),
+    "dv_vae_decode_tiles": (_i, [_vp, _vp, _i, C.c_ulonglong, _vp]),
+    "dv_vae_blend": (_i, [_vp, _vp, _i, _vp]),
 }
 
 

@@ -71,7 +71,8 @@ extern "C" int dv_attention(const void* qkv_dev, void* out_dev, const int* kv_en
                             const float* key_bias_dev, int B, int L, int Lpad, int H,
                             void* stream) {
   DV_REQUIRE(qkv_dev && out_dev && kv_end_dev && key_bias_dev, "dv_attention: null pointer");
-  return launch_attention(qkv_dev, out_dev, kv_end_dev, key_bias_dev, B, L, Lpad, H, S(stream));
+  return launch_attention(qkv_dev, out_dev, kv_end_dev, key_bias_dev, nullptr, B, L, Lpad, H,
+                          S(stream));
 }
 
 extern "C" int dv_conv3d_cl(const void* x_dev, const void* w_dev, const float* bias_dev,

@@ -236,18 +236,23 @@ __global__ void pos_clip_kernel(const float* __restrict__ base, int S, int D,
     out[(static_cast<long long>(row_offset) + static_cast<long long>(t) * h * w + p) * D + ch] = val;
 }
 
-__global__ void key_bias_kernel(const float* __restrict__ ctx_mask, int Lc,
-                                float* __restrict__ key_bias, int B, int L, int Lpad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * Lpad) return;
-  const int b = i / Lpad, k = i - b * Lpad;
+// one CTA of 128 threads per (sample, 128-key tile): key_bias plus a per-tile "holds a dead key"
+// flag that lets the attention kernel skip all masking work on fully-live tiles
+__global__ void __launch_bounds__(128) key_bias_kernel(const float* __restrict__ ctx_mask, int Lc,
+                                                       float* __restrict__ key_bias,
+                                                       int* __restrict__ tile_dead, int L,
+                                                       int Lpad) {
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int k = tile * 128 + threadIdx.x;
   float v = 0.f;
   if (k >= L) {
     v = -INFINITY;
   } else if (k < Lc) {
     v = (ctx_mask[b * Lc + k] != 0.f) ? 0.f : -INFINITY;
   }
-  key_bias[i] = v;
+  key_bias[static_cast<long long>(b) * Lpad + k] = v;
+  const int any = __syncthreads_or(v != 0.f);
+  if (tile_dead != nullptr && threadIdx.x == 0) tile_dead[b * (Lpad / 128) + tile] = any;
 }
 
 }  // namespace
@@ -365,9 +370,10 @@ int launch_pos_clip(const float* base, int S, int D, float* out, int row_offset,
   return 0;
 }
 
-int launch_key_bias(const float* ctx_mask, int Lc, float* key_bias, int B, int L, int Lpad,
-                    cudaStream_t stream) {
-  key_bias_kernel<<<(B * Lpad + 255) / 256, 256, 0, stream>>>(ctx_mask, Lc, key_bias, B, L, Lpad);
+int launch_key_bias(const float* ctx_mask, int Lc, float* key_bias, int* tile_dead, int B, int L,
+                    int Lpad, cudaStream_t stream) {
+  DV_REQUIRE(Lpad % 128 == 0, "key_bias: Lpad=%d must be a multiple of 128", Lpad);
+  key_bias_kernel<<<dim3(Lpad / 128, B), 128, 0, stream>>>(ctx_mask, Lc, key_bias, tile_dead, L, Lpad);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;

@@ -34,20 +34,25 @@ struct KArgs {
   alignas(64) CUtensorMap tmB;
   GemmDesc d;
   int m_tiles, n_tiles, k_blocks, total_tiles;
-  int tiles_w, tiles_h;  // conv: M-tile grid inside one frame
-  int c_blocks;          // conv: Cin / 64
+  int splits, kb_per_split;  // split-K (gate-residual epilogue only: fp32 atomics into x)
+  int tiles_w, tiles_h;      // conv: M-tile grid inside one frame
+  int c_blocks;              // conv: Cin / 64
 };
 
 struct TileCoord {
-  int b, m_tile, n_tile;
+  int b, m_tile, n_tile, split, kb0, kb1;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const KArgs& a, int tile) {
   TileCoord tc;
   tc.n_tile = tile % a.n_tiles;
   int rest = tile / a.n_tiles;
+  tc.split = rest % a.splits;
+  rest /= a.splits;
   tc.m_tile = rest % a.m_tiles;
   tc.b = rest / a.m_tiles;
+  tc.kb0 = tc.split * a.kb_per_split;
+  tc.kb1 = min(tc.kb0 + a.kb_per_split, a.k_blocks);
   return tc;
 }
 
@@ -205,12 +210,24 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const TileCoord& t
         store_bf16x32(out, v);
       } break;
       case EPI_RESID_GATE: {
-        load_bias32(d.bias, n, v);
+        if (tc.split == 0) load_bias32(d.bias, n, v);
         float* x = reinterpret_cast<float*>(d.out) +
                    static_cast<long long>(tc.b) * d.out_batch_stride +
                    static_cast<long long>(m + d.out_row_offset) * d.ldo + n;
         const float4* g4 =
             reinterpret_cast<const float4*>(d.gate + tc.b * d.gate_batch_stride + n);
+        if (a.splits > 1) {
+          // split-K partial sums: x += gate * partial, merged with fp32 reductions in L2
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 g = __ldg(g4 + i);
+            atomicAdd(x + 4 * i + 0, g.x * v[4 * i + 0]);
+            atomicAdd(x + 4 * i + 1, g.y * v[4 * i + 1]);
+            atomicAdd(x + 4 * i + 2, g.z * v[4 * i + 2]);
+            atomicAdd(x + 4 * i + 3, g.w * v[4 * i + 3]);
+          }
+          break;
+        }
         float4* x4 = reinterpret_cast<float4*>(x);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           h0 = (r / a.tiles_w) * 8;
           w0 = (r % a.tiles_w) * 16;
         }
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
@@ -421,7 +438,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * BN;
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
+        const TileCoord tc = decode_tile(a, tile);
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
@@ -431,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 slice inside the 128 B swizzle row (address field is >>4)
-            umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, ((kb - tc.kb0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
@@ -511,21 +529,51 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   }
   ka.k_blocks = K / BK;
 
-  int bn;
+  // ---- tile width and split-K from a small cost model --------------------------------------
+  // A CTA streams (128 + BN) x K_split x 2 bytes through its SM's L2 port (~80 GB/s per SM, ~10
+  // TB/s aggregate) and spends 128 x BN x K_split / 4096 tensor cycles; small-M problems are
+  // port-bound unless the reduction is split across more SMs (only the gate-residual epilogue
+  // can merge partial sums: fp32 atomics into the residual stream).
   const long long mt_total = static_cast<long long>(ka.m_tiles) * d.batch;
-  if (d.N <= 64) {
-    bn = 64;
-  } else if (d.N % 256 == 0 && mt_total * (d.N / 256) >= sm_count()) {
-    bn = 256;
-  } else if (d.N % 128 == 0 && mt_total * (d.N / 128) >= sm_count() / 2) {
-    bn = 128;
-  } else {
-    bn = 64;
+  const int nsm = sm_count();
+  int bn = 64, splits = 1;
+  {
+    double best = 1e30;
+    const int cand_bn[3] = {256, 128, 64};
+    const int cand_s[6] = {1, 2, 3, 4, 6, 8};
+    for (int bi = 0; bi < 3; ++bi) {
+      const int b_ = cand_bn[bi];
+      if (b_ > 64 && (d.N % b_ != 0)) continue;
+      const long long tiles = mt_total * ((d.N + b_ - 1) / b_);
+      for (int si = 0; si < 6; ++si) {
+        const int s_ = cand_s[si];
+        if (s_ > 1 && (d.mode != EPI_RESID_GATE || ka.k_blocks / s_ < 4)) break;
+        const int kbs = (ka.k_blocks + s_ - 1) / s_;
+        const long long ctas = tiles * s_;
+        const double waves = static_cast<double>((ctas + nsm - 1) / nsm);
+        const double cta_bytes = (128.0 + b_) * kbs * 64 * 2;
+        const double t_port = waves * cta_bytes / 80e9;
+        const double t_l2 = ctas * cta_bytes / 10e12;
+        const double t_mma = waves * (128.0 * b_ * kbs * 64 / 4096.0) / 1.8e9;
+        const double t_epi = waves * (s_ > 1 ? 3.0e-6 : 1.0e-6) * (b_ / 64.0) * 0.5;
+        double t = t_port > t_l2 ? t_port : t_l2;
+        t = t > t_mma ? t : t_mma;
+        t += t_epi + 2.0e-6;
+        if (t < best) {
+          best = t;
+          bn = b_;
+          splits = s_;
+        }
+      }
+    }
   }
   DV_REQUIRE(d.mode == EPI_UNPATCH || d.mode == EPI_CONV || d.N % 32 == 0,
              "gemm: N=%d must be a multiple of 32 for epilogue mode %d", d.N, d.mode);
   ka.n_tiles = (d.N + bn - 1) / bn;
-  ka.total_tiles = static_cast<int>(mt_total) * ka.n_tiles;
+  ka.kb_per_split = (ka.k_blocks + splits - 1) / splits;
+  splits = (ka.k_blocks + ka.kb_per_split - 1) / ka.kb_per_split;  // no empty split
+  ka.splits = splits;
+  ka.total_tiles = static_cast<int>(mt_total) * ka.n_tiles * splits;
 
   // ---- tensor maps ------------------------------------------------------------
   if (d.a_mode == 1) {

@@ -6,8 +6,10 @@
 namespace dv {
 
 // ---- attention (attention.cu) ------------------------------------------------------
-int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias, int B,
-                     int L, int Lpad, int H, cudaStream_t stream, double flops = 0.0);
+// tile_dead: [B][Lpad/128] "tile holds a dead key" flags from launch_key_bias, or nullptr
+int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
+                     const int* tile_dead, int B, int L, int Lpad, int H, cudaStream_t stream,
+                     double flops = 0.0);
 
 // ---- MMDiT elementwise (elementwise.cu) -----------------------------------------------
 // out_bf16[b][l][:] = LN(x[b][l][:]) * (1 + scale[b][:]) + shift[b][:]   (eps inside sqrt)
@@ -42,8 +44,9 @@ int launch_pos_clip(const float* base, int S, int D, float* out, int row_offset,
                     int w, int oh, int ow, cudaStream_t stream);
 
 // key_bias[b][k] = 0 for live keys, -inf for dead context keys and k >= L
-int launch_key_bias(const float* ctx_mask, int Lc, float* key_bias, int B, int L, int Lpad,
-                    cudaStream_t stream);
+// (+ tile_dead[b][tile] = 1 when the 128-key tile holds any masked key; may be nullptr)
+int launch_key_bias(const float* ctx_mask, int Lc, float* key_bias, int* tile_dead, int B, int L,
+                    int Lpad, cudaStream_t stream);
 
 // ---- sampler step (sampler.cu) -------------------------------------------------------
 // CFG combine (pipeline.py:502-513) + Euler step (scheduler.py:278-286), rounding sequence of

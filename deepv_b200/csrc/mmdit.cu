@@ -48,7 +48,7 @@ struct dv_mmdit_plan {
   long long bytes = 0;
   std::vector<void*> allocs;
   // device buffers
-  int *frame_x = nullptr, *frame_c = nullptr, *kv_end = nullptr;
+  int *frame_x = nullptr, *frame_c = nullptr, *kv_end = nullptr, *tile_dead = nullptr;
   float *pos_x = nullptr, *pos_h = nullptr;
   float *x = nullptr, *c = nullptr, *key_bias = nullptr;
   float *tfeat = nullptr, *g1 = nullptr, *g3 = nullptr, *temb = nullptr, *mod = nullptr;
@@ -246,6 +246,7 @@ extern "C" int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const i
   DV_A(p->x, static_cast<long long>(B) * Lv * D);
   DV_A(p->c, static_cast<long long>(B) * Lc * D);
   DV_A(p->key_bias, static_cast<long long>(B) * p->Lpad);
+  DV_A(p->tile_dead, static_cast<long long>(B) * (p->Lpad / 128));
   DV_A(p->tfeat, B * 256);
   DV_A(p->g1, B * D);
   DV_A(p->g3, B * D);
@@ -406,7 +407,7 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
     d.addend = p->pos_x;
     DV_RUN(launch_gemm(d, st));
   }
-  DV_RUN(launch_key_bias(ctx_mask_dev, Lc, p->key_bias, B, L, p->Lpad, st));
+  DV_RUN(launch_key_bias(ctx_mask_dev, Lc, p->key_bias, p->tile_dead, B, L, p->Lpad, st));
 
   const long long xs = static_cast<long long>(Lv) * D, cs = static_cast<long long>(Lc) * D;
   const long long js = static_cast<long long>(L) * D;  // joint (attention output) batch stride
@@ -440,7 +441,7 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
       d.heads_dim = D;
       DV_RUN(launch_gemm(d, st));
     }
-    DV_RUN(launch_attention(p->qkv, p->attn, p->kv_end, p->key_bias, B, L, p->Lpad,
+    DV_RUN(launch_attention(p->qkv, p->attn, p->kv_end, p->key_bias, p->tile_dead, B, L, p->Lpad,
                             m->cfg.num_heads, st, p->attn_flops_layer));
     // x += gate_msa * to_out(attn)
     {

@@ -435,15 +435,57 @@ extern "C" void dv_vae_plan_destroy(dv_vae_plan* p) {
 
 extern "C" double dv_vae_plan_flops(const dv_vae_plan* p) { return p ? p->flops : 0.0; }
 
-extern "C" int dv_vae_decode(dv_vae_plan* p, const void* z_dev, int z_dtype, void* out_dev,
-                             int out_dtype, void* stream) {
-  DV_REQUIRE(p && z_dev && out_dev, "dv_vae_decode: null argument");
+extern "C" int dv_vae_plan_geometry(const dv_vae_plan* p, int* rows, int* cols, int* t_out) {
+  DV_REQUIRE(p && rows && cols && t_out, "dv_vae_plan_geometry: null argument");
+  *rows = p->rows;
+  *cols = p->cols;
+  *t_out = p->Tout;
+  return DV_OK;
+}
+
+extern "C" int dv_vae_plan_tile_info(const dv_vae_plan* p, int tile, int* H, int* W) {
+  DV_REQUIRE(p && H && W && tile >= 0 && tile < p->rows * p->cols, "dv_vae_plan_tile_info: bad tile %d",
+             tile);
+  *H = p->tiles[tile].H;
+  *W = p->tiles[tile].W;
+  return DV_OK;
+}
+
+// Use a caller-owned buffer ([Tout][H][W][3] bf16) for one decoded tile, so that the host can
+// exchange tiles between ranks (NCCL broadcast / all_gather) before the blend.
+extern "C" int dv_vae_plan_bind_tile(dv_vae_plan* p, int tile, void* buf_dev) {
+  DV_REQUIRE(p && buf_dev && tile >= 0 && tile < p->rows * p->cols, "dv_vae_plan_bind_tile: bad tile %d",
+             tile);
+  p->tiles[tile].px = reinterpret_cast<__nv_bfloat16*>(buf_dev);
+  DV_CHECK_CUDA(cudaMemcpy(p->tiles_dev, p->tiles.data(), p->tiles.size() * sizeof(TileOut),
+                           cudaMemcpyHostToDevice));
+  return DV_OK;
+}
+
+extern "C" int dv_vae_decode_tiles(dv_vae_plan* p, const void* z_dev, int z_dtype,
+                                   unsigned long long tile_mask, void* stream) {
+  DV_REQUIRE(p && z_dev, "dv_vae_decode_tiles: null argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   for (int i = 0; i < p->rows; ++i)
     for (int j = 0; j < p->cols; ++j) {
+      if (!((tile_mask >> (i * p->cols + j)) & 1ull)) continue;
       int rc = run_tile(p, z_dev, z_dtype == DV_DTYPE_BF16, i, j, st, false, nullptr, nullptr);
       if (rc) return rc;
     }
+  return DV_OK;
+}
+
+extern "C" int dv_vae_decode(dv_vae_plan* p, const void* z_dev, int z_dtype, void* out_dev,
+                             int out_dtype, void* stream) {
+  DV_REQUIRE(p && z_dev && out_dev, "dv_vae_decode: null argument");
+  int rc = dv_vae_decode_tiles(p, z_dev, z_dtype, ~0ull, stream);
+  if (rc) return rc;
+  return dv_vae_blend(p, out_dev, out_dtype, stream);
+}
+
+extern "C" int dv_vae_blend(dv_vae_plan* p, void* out_dev, int out_dtype, void* stream) {
+  DV_REQUIRE(p && out_dev, "dv_vae_blend: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   BlendArgs a;
   a.tiles = p->tiles_dev;
   a.rows = p->rows;

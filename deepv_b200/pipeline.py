@@ -67,7 +67,9 @@ class B200Pipeline:
                           prompt_attention_mask, pooled_prompt_embeds, num_inference_steps,
                           height=None, width=None, temp=1, device=None, dtype=None, generator=None,
                           is_first_frame: bool = False, block_noise: Optional[Sequence[torch.Tensor]] = None,
-                          timestep_dtype=None):
+                          timestep_dtype=None, shard=None):
+        """`shard` (parallel.Shard): run only this rank's CFG branch (batch 1) and all-gather the
+        branch predictions before the fused CFG + Euler step."""
         stages = self.model_cfg["stages"]
         n_branch = 3 if input_history is not None else (2 if self.do_classifier_free_guidance else 1)
         w_text = self._guidance_scale if is_first_frame else self._video_guidance_scale
@@ -85,6 +87,16 @@ class B200Pipeline:
         enc = prompt_embeds.to(self.device)
         enc_mask = prompt_attention_mask.to(self.device)
         pooled = pooled_prompt_embeds.to(self.device)
+        sharded = shard is not None and shard.active and n_branch > 1
+        if sharded:
+            if latents.shape[0] != 1:
+                raise _lib.DeepVError("CFG-branch sharding expects one sample per rollout")
+            mb = shard.my_branch(n_branch)
+            enc, enc_mask, pooled = enc[mb:mb + 1], enc_mask[mb:mb + 1], pooled[mb:mb + 1]
+            past_conditions = [[c[mb:mb + 1] for c in st] for st in past_conditions]
+            if history is not None:
+                history, history_mask = history[mb:mb + 1], history_mask[mb:mb + 1]
+        n_local = 1 if sharded else n_branch
         intermed = []
         for i_s in range(len(stages)):
             self.scheduler.set_timesteps(num_inference_steps[i_s], i_s, device=None)
@@ -105,7 +117,7 @@ class B200Pipeline:
                                                 _lib.stream_ptr()), "dv_stage_renoise")
                 latents = up
             for idx in range(len(timesteps)):
-                x_in = torch.cat([latents] * n_branch) if n_branch > 1 else latents
+                x_in = torch.cat([latents] * n_local) if n_local > 1 else latents
                 # pipeline.py:473 casts the timestep to the latent dtype; timestep_dtype=float32
                 # keeps it unrounded for comparisons against the fp32 oracle
                 tval = torch.tensor(float(timesteps[idx]), dtype=torch.float64)
@@ -117,6 +129,8 @@ class B200Pipeline:
                     pooled_projections=pooled, history=history,
                     history_downsample_ratio=self.model_cfg["history_downsample_ratio"] if history is not None else None,
                     history_mask=history_mask)[0]
+                if sharded:
+                    noise_pred = shard.gather_branches(noise_pred, n_branch)
                 latents = self.scheduler.cfg_step(noise_pred, latents, n_branch, w_text, w_hist)
             intermed.append(latents)
         return intermed
@@ -154,14 +168,25 @@ class B200Pipeline:
         return out
 
     # -- pipeline.py:703-725 ------------------------------------------------------------------------
-    @torch.no_grad()
-    def decode_latent(self, latents: torch.Tensor, save_memory: bool = True, out_dtype=None):
+    @staticmethod
+    def _unnormalise(latents: torch.Tensor) -> torch.Tensor:
         latents = latents.clone()
         if latents.shape[2] == 1:
-            latents = (latents / VAE_SCALE) + VAE_SHIFT
-        else:
-            latents[:, :, :1] = (latents[:, :, :1] / VAE_SCALE) + VAE_SHIFT
-            latents[:, :, 1:] = (latents[:, :, 1:] / VAE_VIDEO_SCALE) + VAE_VIDEO_SHIFT
+            return (latents / VAE_SCALE) + VAE_SHIFT
+        latents[:, :, :1] = (latents[:, :, :1] / VAE_SCALE) + VAE_SHIFT
+        latents[:, :, 1:] = (latents[:, :, 1:] / VAE_VIDEO_SCALE) + VAE_VIDEO_SHIFT
+        return latents
+
+    @torch.no_grad()
+    def decode_latents_sharded(self, latent_list, shard, out_dtype=None):
+        """pipeline.py:695-696 (image + disparity decodes) with the tiles x modalities dealt over
+        the ranks of `shard`; returns one video per entry of latent_list on every rank."""
+        zs = [self._unnormalise(z) for z in latent_list]
+        return self.vae.decode_many(zs, shard, tile_sample_min_size=256, out_dtype=out_dtype)
+
+    @torch.no_grad()
+    def decode_latent(self, latents: torch.Tensor, save_memory: bool = True, out_dtype=None):
+        latents = self._unnormalise(latents)
         if not save_memory:
             raise _lib.DeepVError("decode_latent: only the save_memory=True (256 px tile) branch exists; "
                                   "the reference's 512 px branch crashes (SURVEY.md App. E.2)")

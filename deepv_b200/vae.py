@@ -173,6 +173,56 @@ class B200VAE:
             return (out,)
         return SimpleNamespace(sample=out)
 
+    # ---- multi-GPU: tiles x modalities dealt over the ranks (parallel.Shard) -----------------
+    def _sharded_plan(self, T, h, w, tile, slot):
+        """A plan per modality slot whose tile outputs live in torch buffers (so that
+        torch.distributed can broadcast them)."""
+        key = (T, h, w, tile, "shard", slot)
+        ent = self._plans.get(key)
+        if ent is None:
+            hdl = C.c_void_p()
+            check(self.lib.dv_vae_plan_create(self._handle, T, h, w, tile, C.byref(hdl)), "dv_vae_plan_create")
+            rows, cols, tout = C.c_int(), C.c_int(), C.c_int()
+            check(self.lib.dv_vae_plan_geometry(hdl, C.byref(rows), C.byref(cols), C.byref(tout)))
+            bufs = []
+            for i in range(rows.value * cols.value):
+                H, W = C.c_int(), C.c_int()
+                check(self.lib.dv_vae_plan_tile_info(hdl, i, C.byref(H), C.byref(W)))
+                b = torch.empty((tout.value, H.value, W.value, 3), device=self.device, dtype=torch.bfloat16)
+                check(self.lib.dv_vae_plan_bind_tile(hdl, i, b.data_ptr()), "dv_vae_plan_bind_tile")
+                bufs.append(b)
+            self._plans[key] = hdl.value
+            self._shard_bufs = getattr(self, "_shard_bufs", {})
+            self._shard_bufs[key] = bufs
+        return self._plans[key], self._shard_bufs[key]
+
+    def decode_many(self, zs, shard, tile_sample_min_size=256, out_dtype=None):
+        """Decode several latent videos [1,16,T,h,w] of the same shape (rgb, disparity, ...) with
+        the (modality, tile) work items dealt over the ranks of `shard`; every rank returns all
+        decoded videos."""
+        from .parallel import decode_items
+        zs = [z.contiguous() if z.dtype in (torch.float32, torch.bfloat16) else z.float().contiguous() for z in zs]
+        _lib.require_cuda(*zs)
+        _, _, T, h, w = zs[0].shape
+        tile = int(tile_sample_min_size / 8) if self.use_tiling else max(h, w)
+        plans = [self._sharded_plan(T, h, w, tile, m) for m in range(len(zs))]
+        n_tiles = len(plans[0][1])
+        items = decode_items(len(zs), n_tiles)
+        for i in shard.my_items(len(items)):
+            m, t = items[i]
+            check(self.lib.dv_vae_decode_tiles(plans[m][0], zs[m].data_ptr(), _lib.dtype_code(zs[m].dtype),
+                                               1 << t, _lib.stream_ptr()), "dv_vae_decode_tiles")
+        shard.exchange_tiles([plans[m][1][t] for (m, t) in items])
+        outs = []
+        for m, z in enumerate(zs):
+            od = out_dtype or z.dtype
+            out = torch.empty((1, 3, 8 * (T - 1) + 1, 8 * h, 8 * w), device=z.device, dtype=od)
+            check(self.lib.dv_vae_blend(plans[m][0], out.data_ptr(), _lib.dtype_code(od), _lib.stream_ptr()),
+                  "dv_vae_blend")
+            outs.append(out)
+        self._last = zs
+        return outs
+
     def encode(self, x, *a, **k):
         if self.reference_encoder is None:
             raise _lib.DeepVError("B200VAE.encode: the encoder is outside the hot path (SURVEY.md §8 "

@@ -195,6 +195,20 @@ double dv_vae_plan_flops(const dv_vae_plan* p);
  * out_dev: [1][3][8(T-1)+1][8h][8w] (dtype)                                                    */
 int dv_vae_decode(dv_vae_plan* p, const void* z_dev, int z_dtype, void* out_dev, int out_dtype,
                   void* stream);
+/* Tile-granular decode for multi-GPU sharding (the 6 tiles x {rgb, disparity} of one iteration
+ * are independent, vae.py:994-1000; only the blend needs all of them):
+ *   dv_vae_plan_geometry   tile grid (rows x cols) and output frame count
+ *   dv_vae_plan_tile_info  decoded size of tile i (row-major), buffer = [t_out][H][W][3] bf16
+ *   dv_vae_plan_bind_tile  make tile i live in a caller-owned device buffer (so the host can
+ *                          broadcast / all_gather it between ranks)
+ *   dv_vae_decode_tiles    decode the tiles whose bit is set in tile_mask
+ *   dv_vae_blend           the sequential-order blend + crop + concat of all tiles -> out_dev   */
+int dv_vae_plan_geometry(const dv_vae_plan* p, int* rows, int* cols, int* t_out);
+int dv_vae_plan_tile_info(const dv_vae_plan* p, int tile, int* H, int* W);
+int dv_vae_plan_bind_tile(dv_vae_plan* p, int tile, void* buf_dev);
+int dv_vae_decode_tiles(dv_vae_plan* p, const void* z_dev, int z_dtype,
+                        unsigned long long tile_mask, void* stream);
+int dv_vae_blend(dv_vae_plan* p, void* out_dev, int out_dtype, void* stream);
 
 #ifdef __cplusplus
 }

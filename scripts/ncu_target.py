@@ -1,0 +1,78 @@
+"""Short ncu target: a few launches of each hot kernel at its benchmark shape.
+
+    ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 6 -o prof python scripts/ncu_target.py
+"""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from deepv_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+st = None
+
+
+def p(t):
+    return t.data_ptr()
+
+
+torch.manual_seed(0)
+if which in ("all", "conv"):
+    # up3 resnet conv of the VAE decoder: 128 -> 128 channels at 256x256, 8 frames (464 GFLOP)
+    B, T, H, W, Ci, Co = 1, 8, 256, 256, 128, 128
+    x = (torch.randn(B, T, H, W, Ci, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(Co, 27, Ci, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(Co, device="cuda")
+    out = torch.empty(B, T, H, W, Co, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        _lib.check(lib.dv_conv3d_cl(p(x), p(w), p(bias), None, p(out), B, T, H, W, Ci, Co, Co, 3, 0, 0, st))
+    # up1 resnet conv: 512 -> 512 at 64x64, 15 frames
+    B, T, H, W, Ci, Co = 1, 15, 64, 64, 512, 512
+    x = (torch.randn(B, T, H, W, Ci, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(Co, 27, Ci, device="cuda") * 0.05).bfloat16()
+    out = torch.empty(B, T, H, W, Co, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        _lib.check(lib.dv_conv3d_cl(p(x), p(w), None, None, p(out), B, T, H, W, Ci, Co, Co, 3, 0, 0, st))
+if which in ("all", "gemm"):
+    # FF1 of a stage-2 forward: [3072, 1536] x [6144, 1536]^T, GELU epilogue
+    M, N, K = 3072, 6144, 1536
+    A = (torch.randn(1, M, K, device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    Cc = torch.empty(1, M, N, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), p(bias), p(Cc), 1, M, N, K, 1, st))
+    # FF2 of a stage-0 forward (small M): [2][96, 6144] x [1536, 6144]^T
+    A = (torch.randn(2, 96, 6144, device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn(1536, 6144, device="cuda") * 0.05).bfloat16()
+    Cc = torch.empty(2, 96, 1536, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), None, p(Cc), 2, 96, 1536, 6144, 0, st))
+if which in ("all", "attn"):
+    B, L, H = 3, 2237, 24
+    qkv = torch.randn(B, L, 3 * H * 64, device="cuda").bfloat16()
+    sizes = [269, 240, 192, 768, 768]
+    bounds, acc = [], 0
+    for s in sizes:
+        acc += s
+        bounds.append(acc)
+    kv = torch.empty(L, dtype=torch.int32)
+    pos = 0
+    for i, s in enumerate(sizes):
+        kv[pos:pos + s] = bounds[max(i, 1)]
+        pos += s
+    Lpad = (L + 127) // 128 * 128
+    kb = torch.zeros(B, Lpad, device="cuda")
+    kb[:, L:] = float("-inf")
+    kb[:2, :192] = float("-inf")
+    out = torch.empty(B, L, H * 64, device="cuda", dtype=torch.bfloat16)
+    kvd = kv.cuda()
+    for _ in range(3):
+        _lib.check(lib.dv_attention(p(qkv), p(out), p(kvd), p(kb), B, L, Lpad, H, st))
+torch.cuda.synchronize()
+print("ncu target done")

@@ -1,0 +1,87 @@
+"""CPU, world_size 2 (gloo): the multi-GPU sharding logic of deepv_b200/parallel.py.
+
+The kernels need a GPU, but who-computes-what and the exchange steps do not: these tests run the
+real Shard helpers over gloo with stand-in 'branch predictions' and 'decoded tiles'."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from deepv_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = parallel.Shard.current()
+        assert (sh.rank, sh.world, sh.active) == (rank, world, True)
+        # ---- CFG branches: rank r computes branch r % n; gather yields (uncond, text) in order
+        n_branch = 2
+        mb = sh.my_branch(n_branch)
+        pred = torch.full((1, 38, 1, 4, 4), float(10 + mb))
+        allp = sh.gather_branches(pred, n_branch)
+        assert allp.shape == (2, 38, 1, 4, 4)
+        assert torch.equal(allp[0], torch.full((38, 1, 4, 4), 10.0))
+        assert torch.equal(allp[1], torch.full((38, 1, 4, 4), 11.0))
+        # the combine every rank then runs must give identical latents everywhere
+        guided = allp[0] + 3.5 * (allp[1] - allp[0])
+        chk = [torch.empty_like(guided) for _ in range(world)]
+        dist.all_gather(chk, guided)
+        assert all(torch.equal(c, chk[0]) for c in chk)
+        # ---- VAE work items: every (modality, tile) decoded exactly once, then visible everywhere
+        items = parallel.decode_items(2, 6)
+        mine = sh.my_items(len(items))
+        bufs = [torch.zeros(3, 5) for _ in items]
+        for i in mine:
+            bufs[i].fill_(100 * items[i][0] + items[i][1] + 1)
+        sh.exchange_tiles(bufs)
+        for i, (m, t) in enumerate(items):
+            assert torch.equal(bufs[i], torch.full((3, 5), float(100 * m + t + 1))), (rank, i)
+        ret[rank] = len(mine)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_over_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert sorted(ret.values()) == [6, 6]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8, 12, 16])
+def test_item_partition_is_exact(world):
+    items = parallel.decode_items(2, 6)
+    seen = []
+    for r in range(world):
+        mine = parallel.items_of_rank(len(items), r, world)
+        assert all(parallel.owner_of_item(i, world) == r for i in mine)
+        seen += mine
+    assert sorted(seen) == list(range(len(items)))
+    # balance: no rank holds more than ceil(n / world)
+    assert max(len(parallel.items_of_rank(len(items), r, world)) for r in range(world)) == -(-len(items) // world)
+
+
+def test_branch_assignment():
+    assert [parallel.branch_of_rank(r, 3) for r in range(8)] == [0, 1, 2, 0, 1, 2, 0, 1]
+    assert parallel.branch_sources(8, 3) == [0, 1, 2]
+    with pytest.raises(ValueError):
+        parallel.branch_sources(2, 3)
+    sh = parallel.Shard(0, 1)
+    x = torch.randn(2, 3)
+    assert sh.gather_branches(x, 2) is x and not sh.active
