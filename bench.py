@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--layers", type=int, default=24, help="debug only; anything but 24 is not the benchmark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-dump", default=None, help="write the per-launch CSV of the profiled step here")
     return ap.parse_args()
 
 
@@ -409,6 +410,8 @@ def run_ours(args):
         _lib.check(lib.dv_profile_summary(k, C.byref(cnt), C.byref(kms), C.byref(fl), C.byref(by)))
         kinds[name] = dict(launches=cnt.value, ms=kms.value, tflop=fl.value / 1e12,
                            tflops=(fl.value / 1e12) / (kms.value / 1e3) if kms.value > 0 else 0.0)
+    if args.profile_dump and rank == 0:
+        _lib.check(lib.dv_profile_dump(args.profile_dump.encode()), "dv_profile_dump")
     lib.dv_profile_reset()
     peaks = {}
     try:

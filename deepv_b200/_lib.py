@@ -68,6 +68,7 @@ SIGNATURES = {
     "dv_launch_count_reset": (None, []),
     "dv_profile_enable": (None, [_i]),
     "dv_profile_reset": (None, []),
+    "dv_profile_dump": (_i, [C.c_char_p]),
     "dv_profile_summary": (_i, [_i, C.POINTER(_ll), C.POINTER(_d), C.POINTER(_d), C.POINTER(_d)]),
     "dv_cfg_euler_step": (_i, [_vp, _i, _vp, _vp, _ll, _f, _f, _d, _d, _i, _vp]),
     "dv_stage_renoise": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp]),

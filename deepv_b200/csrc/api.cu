@@ -16,6 +16,10 @@ extern "C" void dv_launch_count_reset(void) { launch_count_reset(); }
 
 extern "C" void dv_profile_enable(int on) { prof_enable(on != 0); }
 extern "C" void dv_profile_reset(void) { prof_reset(); }
+extern "C" int dv_profile_dump(const char* path) {
+  DV_REQUIRE(path, "dv_profile_dump: null path");
+  return prof_dump(path);
+}
 extern "C" int dv_profile_summary(int kind, long long* count, double* ms, double* flops,
                                   double* bytes) {
   DV_REQUIRE(count && ms && flops && bytes, "dv_profile_summary: null pointer");

@@ -17,6 +17,8 @@
 // only refreshed (and O rescaled in TMEM) when it grows by more than 2^8, so the rescale is
 // rare after the first tiles.  Masking is applied only on tiles that need it (frame boundary
 // or dead keys).
+#include <cstdio>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -364,7 +366,9 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
     attr_set = true;
   }
   dim3 grid((L + 2 * kTile - 1) / (2 * kTile), H, B);
-  const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream);
+  char tag[56] = "";
+  if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d", B, L, H);
+  const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);
   attn_kernel<<<grid, kAttnThreads, kSmemBytes, stream>>>(a);
   prof_end(pid, stream);
   DV_CHECK_CUDA(cudaGetLastError());

@@ -33,6 +33,7 @@ struct ProfRec {
   cudaEvent_t e0, e1;
   int kind;
   double flops, bytes;
+  char tag[56];
 };
 constexpr int kProfMax = 1 << 16;
 bool g_prof_on = false;
@@ -63,9 +64,11 @@ void prof_reset() {
   }
   g_prof->clear();
 }
-int prof_begin(int kind, double flops, double bytes, cudaStream_t st) {
+bool prof_on() { return g_prof_on; }
+int prof_begin(int kind, double flops, double bytes, cudaStream_t st, const char* tag) {
   if (!g_prof_on || static_cast<int>(g_prof->size()) >= kProfMax) return -1;
   ProfRec r;
+  snprintf(r.tag, sizeof(r.tag), "%s", tag ? tag : "");
   r.e0 = prof_event();
   r.e1 = prof_event();
   r.kind = kind;
@@ -95,6 +98,25 @@ int prof_summary(int kind, long long* count, double* ms, double* flops, double* 
     *flops += r.flops;
     *bytes += r.bytes;
   }
+  return 0;
+}
+
+// one CSV line per recorded launch: kind,tag,flops,bytes,ms (caller synchronised the stream)
+int prof_dump(const char* path) {
+  FILE* f = fopen(path, "w");
+  if (!f) {
+    set_error("prof_dump: cannot open %s", path);
+    return -1;
+  }
+  fprintf(f, "kind,tag,flops,bytes,ms\n");
+  if (g_prof) {
+    for (auto& r : *g_prof) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) t = -1.f;
+      fprintf(f, "%d,%s,%.0f,%.0f,%.6f\n", r.kind, r.tag, r.flops, r.bytes, t);
+    }
+  }
+  fclose(f);
   return 0;
 }
 

@@ -26,8 +26,18 @@ void launch_count_reset();
 enum ProfKind : int { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_OTHER = 3 };
 void prof_enable(bool on);
 void prof_reset();
-int prof_begin(int kind, double flops, double bytes, cudaStream_t st);
+bool prof_on();
+int prof_begin(int kind, double flops, double bytes, cudaStream_t st, const char* tag = nullptr);
 void prof_end(int id, cudaStream_t st);
+int prof_dump(const char* path);
+// RAII bracket for launchers: records only while the profiler is on
+struct ProfScope {
+  int id;
+  cudaStream_t st;
+  ProfScope(int kind, double flops, double bytes, cudaStream_t s, const char* tag)
+      : id(prof_on() ? prof_begin(kind, flops, bytes, s, tag) : -1), st(s) {}
+  ~ProfScope() { prof_end(id, st); }
+};
 int prof_summary(int kind, long long* count, double* ms, double* flops, double* bytes);
 #define DV_CHECK_CUDA(expr)                                                        \
   do {                                                                             \
@@ -249,7 +259,11 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(u));
+  // tanh.approx.f32: one MUFU op, max rel. error 2^-11 — below the bf16 rounding (2^-9) of the
+  // value this feeds; tanhf() made the FF1 epilogue as long as its mainloop
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 

@@ -264,6 +264,7 @@ int launch_ln_modulate(const float* x, long long x_bs, __nv_bfloat16* out, long 
   const long long rows = static_cast<long long>(B) * L;
   if (rows == 0) return 0;
   const int blocks = static_cast<int>((rows * 32 + 255) / 256);
+  ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(rows) * D * 6.0, stream, "ln_modulate");
   if (D == 1536)
     ln_modulate_kernel<1536><<<blocks, 256, 0, stream>>>(x, x_bs, out, out_bs, shift, scale,
                                                          mod_bs, B, L, eps);
@@ -296,6 +297,7 @@ int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int 
                                                                accumulate);                      \
   } while (0)
   DV_REQUIRE(smem <= 96 * 1024, "gemv: B*K too large for smem staging");
+  ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(N) * K * 2.0, stream, N > 100000 ? "gemv_adaln" : "gemv");
   switch (B) {
     case 1: DV_GEMV(1); break;
     case 2: DV_GEMV(2); break;

@@ -1,65 +1,124 @@
 // deepv_b200 — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM conv3d.
 //
-// One CTA per SM (grid = min(#tiles, #SMs)), 192 threads:
+// One CTA per SM, 192 threads:
 //   warp 0      TMA producer   (one lane): A/B k-blocks -> 128B-swizzled smem ring
-//   warp 1      MMA issuer     (one lane): tcgen05.mma M=128, N=BN, K=16, fp32 accum in TMEM;
+//   warp 1      MMA issuer     (one lane): tcgen05.mma M=128, N=256, K=16, fp32 accum in TMEM;
 //               also owns TMEM alloc/dealloc
 //   warps 2..5  epilogue       (128 threads, one accumulator row each): tcgen05.ld ->
-//               fused epilogue -> vectorised global stores
-// Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of
-// tile i+1.  See gemm.cuh for the operand / epilogue contract.
+//               fused epilogue (compile-time EpiMode) -> vectorised global stores
+// ONE tile shape, 128 x 256 x 64: measured on B200, an M128 tcgen05.mma with both operands in
+// shared memory takes >= 128 cycles whatever N is (the 128-row A read), so N = 256 is the only
+// width that runs the tensor pipe at rate; a CTA therefore needs ~K*8 cycles per tile and the
+// lever for problems with fewer tiles than SMs is split-K, not narrower tiles:
+//   * splits == 1: persistent grid, two TMEM accumulator stages (epilogue of tile i overlaps the
+//     mainloop of tile i+1);
+//   * splits  > 1: the S CTAs that share an output tile form a thread-block cluster; each
+//     reduces K/S, parks its fp32 partial tile in its own shared memory, and after a cluster
+//     barrier every CTA sums one row-slice over all peers through distributed shared memory in
+//     rank order (deterministic, no atomics, no workspace) and runs the epilogue for that slice.
+// Convolutions with Cout <= 128 swap the operand roles (weights = M side, a 16x16-pixel box =
+// N side).  See gemm.cuh for the operand / epilogue contract.
 #include "gemm.cuh"
+
+#include <cstdio>
+#include <cstdlib>
 
 namespace dv {
 
 namespace {
 
 constexpr int BM = 128;
+constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kThreads = 192;
-
-template <int BN>
-struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
-  static constexpr uint32_t kTmemCols = 2 * BN;  // 128, 256 or 512 (power of two)
-};
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kBBytes = BN * BK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kBarBytes = 256;
+constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+constexpr uint32_t kTmemCols = 2 * BN;
+constexpr int kMaxSplits = 8;  // portable cluster size
 
 struct KArgs {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
   GemmDesc d;
   int m_tiles, n_tiles, k_blocks, total_tiles;
-  int splits, kb_per_split;  // split-K (gate-residual epilogue only: fp32 atomics into x)
+  int splits, kb_per_split;  // split-K over a cluster of `splits` CTAs
   int tiles_w, tiles_h;      // conv: M-tile grid inside one frame
   int c_blocks;              // conv: Cin / 64
+  int swap;                  // conv, Cout <= 128: weights are the M operand, 16x16 pixels the N operand
 };
 
 struct TileCoord {
-  int b, m_tile, n_tile, split, kb0, kb1;
+  int b, m_tile, n_tile, kb0, kb1;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const KArgs& a, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const KArgs& a, int tile, int split) {
   TileCoord tc;
   tc.n_tile = tile % a.n_tiles;
-  int rest = tile / a.n_tiles;
-  tc.split = rest % a.splits;
-  rest /= a.splits;
+  const int rest = tile / a.n_tiles;
   tc.m_tile = rest % a.m_tiles;
   tc.b = rest / a.m_tiles;
-  tc.kb0 = tc.split * a.kb_per_split;
+  tc.kb0 = split * a.kb_per_split;
   tc.kb1 = min(tc.kb0 + a.kb_per_split, a.k_blocks);
   return tc;
 }
 
+// ---- cluster helpers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------
-// epilogue helpers: one thread = one output row, 32 columns at a time
+// epilogue: one thread = one output row, W (32 or 64) accumulator columns at a time
 // ------------------------------------------------------------------------------
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+struct RowCtx {
+  int b, m;        // batch, dense row index inside the batch (conv: unused)
+  bool ok;         // row exists
+  int ct, ch, cw;  // conv: output pixel
+};
+
+__device__ __forceinline__ RowCtx make_row(const KArgs& a, const TileCoord& tc, int row_in_tile) {
+  const GemmDesc& d = a.d;
+  RowCtx r;
+  r.b = tc.b;
+  r.m = tc.m_tile * BM + row_in_tile;
+  r.ct = r.ch = r.cw = 0;
+  if (d.a_mode == 1) {
+    const int per_frame = a.tiles_w * a.tiles_h;
+    r.ct = tc.m_tile / per_frame;
+    const int q = tc.m_tile % per_frame;
+    r.ch = (q / a.tiles_w) * 8 + (row_in_tile >> 4);
+    r.cw = (q % a.tiles_w) * 16 + (row_in_tile & 15);
+    r.ok = (r.ct < d.cT) && (r.ch < d.cH) && (r.cw < d.cW);
+  } else {
+    r.ok = r.m < d.M;
+  }
+  return r;
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float* v) {
   uint4* p = reinterpret_cast<uint4*>(dst);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -72,12 +131,13 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
   }
 }
 
-__device__ __forceinline__ void load_bias32(const float* bias, int n, float (&v)[32]) {
+template <int W>
+__device__ __forceinline__ void add_bias(const float* bias, int n, float (&v)[W]) {
   if (bias != nullptr) {
     const float4* bp = reinterpret_cast<const float4*>(bias + n);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = __ldg(bp + i);
+    for (int i = 0; i < W / 4; ++i) {
+      const float4 t = __ldg(bp + i);
       v[4 * i + 0] += t.x;
       v[4 * i + 1] += t.y;
       v[4 * i + 2] += t.z;
@@ -86,273 +146,268 @@ __device__ __forceinline__ void load_bias32(const float* bias, int n, float (&v)
   }
 }
 
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const KArgs& a, const TileCoord& tc,
-                                              uint32_t tmem_acc, int row_in_tile, int quarter) {
-  const GemmDesc& d = a.d;
-  const int n0 = tc.n_tile * BN;
-  const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-
-  // ---- row geometry ----------------------------------------------------------
-  int m = tc.m_tile * BM + row_in_tile;  // dense row index inside batch
-  bool row_ok;
-  // conv geometry
-  int ct = 0, ch = 0, cw = 0;
-  if (d.a_mode == 1) {
-    int per_frame = a.tiles_w * a.tiles_h;
-    ct = tc.m_tile / per_frame;
-    int r = tc.m_tile % per_frame;
-    int ty = r / a.tiles_w, tx = r % a.tiles_w;
-    ch = ty * 8 + (row_in_tile >> 4);
-    cw = tx * 16 + (row_in_tile & 15);
-    row_ok = (ct < d.cT) && (ch < d.cH) && (cw < d.cW);
-  } else {
-    row_ok = m < d.M;
+template <int W>
+__device__ __forceinline__ void add_bf16x32(const __nv_bfloat16* src, float (&v)[W]) {
+  const uint4* r4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 t = __ldg(r4 + i);
+    v[8 * i + 0] += bf16_lo(t.x);
+    v[8 * i + 1] += bf16_hi(t.x);
+    v[8 * i + 2] += bf16_lo(t.y);
+    v[8 * i + 3] += bf16_hi(t.y);
+    v[8 * i + 4] += bf16_lo(t.z);
+    v[8 * i + 5] += bf16_hi(t.z);
+    v[8 * i + 6] += bf16_lo(t.w);
+    v[8 * i + 7] += bf16_hi(t.w);
   }
+}
 
-  uint32_t raw[32];
-  float v[32];
+template <int MODE>
+struct EpiW {
+  static constexpr int value = (MODE == EPI_QKV) ? 64 : 32;
+};
 
-  if (d.mode == EPI_QKV) {
-    // 64 columns (one head) at a time: RMSNorm over the head, then RoPE pairs.
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out) +
-                         static_cast<long long>(tc.b) * d.out_batch_stride +
-                         static_cast<long long>(m + d.out_row_offset) * d.ldo;
-    const int fid = row_ok ? __ldg(d.frame_id + m) : 0;
-    const float2* cs = reinterpret_cast<const float2*>(d.rope_cs) + fid * 32;
-    for (int c = 0; c < BN / 64; ++c) {
-      float h[64];
-      const int n = n0 + c * 64;
-      tmem_ld_32x32(taddr_row + c * 64, raw);
-      tmem_ld_wait();
+// v = W accumulator columns [n, n + W) of output row `r`; n < d.N and r.ok hold.
+template <int MODE, int W>
+__device__ __forceinline__ void epi_row(const KArgs& a, const RowCtx& r, int n, float (&v)[W]) {
+  const GemmDesc& d = a.d;
+  if constexpr (MODE == EPI_BF16 || MODE == EPI_GELU) {
+    add_bias<W>(d.bias, n, v);
+    if constexpr (MODE == EPI_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h[i] = __uint_as_float(raw[i]);
-      tmem_ld_32x32(taddr_row + c * 64 + 32, raw);
-      tmem_ld_wait();
+      for (int i = 0; i < W; ++i) v[i] = gelu_tanh(v[i]);
+    }
+    const long long off = static_cast<long long>(r.b) * d.out_batch_stride +
+                          static_cast<long long>(r.m + d.out_row_offset) * d.ldo + n;
+    if (d.residual != nullptr)
+      add_bf16x32<W>(reinterpret_cast<const __nv_bfloat16*>(d.residual) + off, v);
+    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + off, v);
+  } else if constexpr (MODE == EPI_BF16_ROWBIAS) {
+    const float bm = d.bias ? __ldg(d.bias + r.m) : 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h[32 + i] = __uint_as_float(raw[i]);
-      if (n >= d.N || !row_ok) continue;
-      if (d.bias != nullptr) {
+    for (int i = 0; i < W; ++i) v[i] += bm;
+    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) +
+                      static_cast<long long>(r.b) * d.out_batch_stride +
+                      static_cast<long long>(r.m + d.out_row_offset) * d.ldo + n,
+                  v);
+  } else if constexpr (MODE == EPI_RESID_GATE) {
+    add_bias<W>(d.bias, n, v);
+    float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) +
+                                           static_cast<long long>(r.b) * d.out_batch_stride +
+                                           static_cast<long long>(r.m + d.out_row_offset) * d.ldo + n);
+    const float4* g4 = reinterpret_cast<const float4*>(d.gate + r.b * d.gate_batch_stride + n);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) h[i] += __ldg(d.bias + n + i);
+    for (int i = 0; i < W / 4; ++i) {
+      const float4 g = __ldg(g4 + i);
+      float4 t = x4[i];
+      t.x += g.x * v[4 * i + 0];
+      t.y += g.y * v[4 * i + 1];
+      t.z += g.z * v[4 * i + 2];
+      t.w += g.w * v[4 * i + 3];
+      x4[i] = t;
+    }
+  } else if constexpr (MODE == EPI_F32_ADD) {
+    add_bias<W>(d.bias, n, v);
+    if (d.addend != nullptr) {
+      const int ar = d.row_map ? __ldg(d.row_map + r.m) : r.m;
+      const float4* a4 =
+          reinterpret_cast<const float4*>(d.addend + static_cast<long long>(ar) * d.N + n);
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        const float4 t = __ldg(a4 + i);
+        v[4 * i + 0] += t.x;
+        v[4 * i + 1] += t.y;
+        v[4 * i + 2] += t.z;
+        v[4 * i + 3] += t.w;
       }
-      const int region = n / d.heads_dim;  // 0 q, 1 k, 2 v
-      if (region < 2) {
-        float ss = 0.f;
+    }
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) +
+                                           static_cast<long long>(r.b) * d.out_batch_stride +
+                                           static_cast<long long>(r.m + d.out_row_offset) * d.ldo + n);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) ss += h[i] * h[i];
-        const float rs = rsqrtf(ss * (1.0f / 64.0f) + 1e-5f);  // RMSNorm eps, mmdit.py:195,453-454
-        const float* w = d.qk_norm_w + region * 64;
+    for (int i = 0; i < W / 4; ++i)
+      o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if constexpr (MODE == EPI_QKV) {
+    // one head (64 columns): bias, per-head RMSNorm (q, k), temporal RoPE on adjacent pairs
+    add_bias<W>(d.bias, n, v);
+    const int region = n / d.heads_dim;  // 0 q, 1 k, 2 v
+    if (region < 2) {
+      float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x0 = h[2 * i] * rs * __ldg(w + 2 * i);
-          float x1 = h[2 * i + 1] * rs * __ldg(w + 2 * i + 1);
-          float2 t = __ldg(cs + i);  // (cos, sin) of frame * 10000^(-2i/64)
-          h[2 * i] = t.x * x0 - t.y * x1;
-          h[2 * i + 1] = t.y * x0 + t.x * x1;
-        }
-      }
-      float lo[32], hi[32];
+      for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
+      const float rs = rsqrtf(ss * (1.0f / 64.0f) + 1e-5f);  // RMSNorm eps, mmdit.py:195,453-454
+      const float2* w2 = reinterpret_cast<const float2*>(d.qk_norm_w + region * 64);
+      const int fid = __ldg(d.frame_id + r.m);
+      const float2* cs = reinterpret_cast<const float2*>(d.rope_cs) + fid * 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        lo[i] = h[i];
-        hi[i] = h[32 + i];
+        const float2 w = __ldg(w2 + i);
+        const float x0 = v[2 * i] * rs * w.x;
+        const float x1 = v[2 * i + 1] * rs * w.y;
+        const float2 t = __ldg(cs + i);  // (cos, sin) of frame * 10000^(-2i/64)
+        v[2 * i] = t.x * x0 - t.y * x1;
+        v[2 * i + 1] = t.y * x0 + t.x * x1;
       }
-      store_bf16x32(out + n, lo);
-      store_bf16x32(out + n + 32, hi);
     }
-    return;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out) +
+                         static_cast<long long>(r.b) * d.out_batch_stride +
+                         static_cast<long long>(r.m + d.out_row_offset) * d.ldo + n;
+    store_bf16x32(out, v);
+    store_bf16x32(out + 32, v + 32);
+  } else if constexpr (MODE == EPI_UNPATCH) {
+    // row m = (gy, gx) of the noisy clip's token grid; column n = (p1, p2, c)
+    // out[b][c][0][2*gy+p1][2*gx+p2]   (mmdit.py:1453-1457, patch 2)
+    const int gy = r.m / d.up_gw, gx = r.m % d.up_gw;
+    const int H2 = 2 * d.up_gh, W2 = 2 * d.up_gw;
+    const long long ob = static_cast<long long>(r.b) * d.out_batch_stride;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const int nn = n + i;
+      if (nn < d.N) {
+        const float val = v[i] + (d.bias ? __ldg(d.bias + nn) : 0.f);
+        const int cch = nn % d.up_C;
+        const int pq = nn / d.up_C;
+        const int p1 = pq >> 1, p2 = pq & 1;
+        const long long o =
+            ob + (static_cast<long long>(cch) * H2 + (2 * gy + p1)) * W2 + (2 * gx + p2);
+        if (d.out_f32)
+          reinterpret_cast<float*>(d.out)[o] = val;
+        else
+          reinterpret_cast<__nv_bfloat16*>(d.out)[o] = __float2bfloat16(val);
+      }
+    }
+  } else if constexpr (MODE == EPI_CONV) {
+    add_bias<W>(d.bias, n, v);
+    int ot = r.ct, oh = r.ch, ow = r.cw, oc = n, oH = d.cH, oW = d.cW;
+    if (d.conv_store == CONV_SHUFFLE_HW) {
+      // packed weight rows are ordered (p1, p2, c): vae.py:382
+      const int q = n / d.out_C;
+      oc = n % d.out_C;
+      oh = 2 * r.ch + (q >> 1);
+      ow = 2 * r.cw + (q & 1);
+      oH = 2 * d.cH;
+      oW = 2 * d.cW;
+    } else if (d.conv_store == CONV_INTERLEAVE_T) {
+      // packed weight rows are ordered (p, c): vae.py:407-409
+      const int p = n / d.out_C;
+      oc = n % d.out_C;
+      ot = 2 * r.ct + p - (d.conv_drop_first ? 1 : 0);
+      if (ot < 0) return;
+    }
+    const int oT =
+        (d.conv_store == CONV_INTERLEAVE_T) ? (2 * d.cT - (d.conv_drop_first ? 1 : 0)) : d.cT;
+    const long long off =
+        (((static_cast<long long>(r.b) * oT + ot) * oH + oh) * oW + ow) * d.out_C + oc;
+    if (d.residual != nullptr)
+      add_bf16x32<W>(reinterpret_cast<const __nv_bfloat16*>(d.residual) + off, v);
+    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + off, v);
   }
+}
 
-  for (int c = 0; c < BN / 32; ++c) {
-    const int n = n0 + c * 32;
-    tmem_ld_32x32(taddr_row + c * 32, raw);
+// Accumulator tile in TMEM -> epilogue, 32 columns in flight while 32 are processed.
+template <int MODE>
+__device__ __forceinline__ void epilogue_from_tmem(const KArgs& a, const TileCoord& tc,
+                                                   uint32_t tmem_acc, int row_in_tile, int quarter) {
+  constexpr int W = EpiW<MODE>::value;
+  const GemmDesc& d = a.d;
+  const RowCtx r = make_row(a, tc, row_in_tile);
+  const int n0 = tc.n_tile * BN;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  if constexpr (W == 64) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 64; ++c) {
+      const int n = n0 + c * 64;
+      if (n >= d.N) break;  // warp-uniform
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(taddr + c * 64, r0);
+      tmem_ld_32x32(taddr + c * 64 + 32, r1);
+      tmem_ld_wait();
+      float v[64];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r0[i]);
+        v[32 + i] = __uint_as_float(r1[i]);
+      }
+      if (r.ok) epi_row<MODE, 64>(a, r, n, v);
+    }
+  } else {
+    uint32_t buf[2][32];
+    tmem_ld_32x32(taddr, buf[0]);
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n = n0 + c * 32;
+      tmem_ld_wait();
+      if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, buf[(c + 1) & 1]);
+      if (n < d.N && r.ok) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(buf[c & 1][i]);
+        epi_row<MODE, 32>(a, r, n, v);
+      }
+    }
     tmem_ld_wait();
-    if (n >= d.N || !row_ok) continue;  // warp-uniform in n; row predicate only skips stores
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+  }
+}
 
-    switch (d.mode) {
-      case EPI_BF16:
-      case EPI_GELU: {
-        load_bias32(d.bias, n, v);
-        if (d.mode == EPI_GELU) {
+// Swapped-operand conv tile (Cout <= 128): TMEM lane = output channel, column = pixel of the
+// 16x16 tile (w fastest).  One thread owns one channel; for every pixel the warp writes a
+// contiguous run of 32 channels (64 B) into the NDHWC output.  Plain store mode only.
+__device__ __forceinline__ void epilogue_tile_swapped(const KArgs& a, const TileCoord& tc,
+                                                      uint32_t tmem_acc, int quarter, int lane) {
+  const GemmDesc& d = a.d;
+  const int per_frame = a.tiles_w * a.tiles_h;
+  const int ct = tc.m_tile / per_frame;
+  const int r = tc.m_tile % per_frame;
+  const int h0 = (r / a.tiles_w) * 16, w0 = (r % a.tiles_w) * 16;
+  const int c = quarter * 32 + lane;  // output channel of this thread
+  const bool c_ok = c < d.N;
+  const float bias = (c_ok && d.bias != nullptr) ? __ldg(d.bias + c) : 0.f;
+  const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual);
+  const long long frame_off = (static_cast<long long>(tc.b) * d.cT + ct) * d.cH;
+  if (quarter * 32 >= d.N) return;  // warp-uniform: no live channel in this lane quarter
+  uint32_t buf[2][32];
+  tmem_ld_32x32(taddr_row, buf[0]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(v[i]);
-        }
-        const long long off = static_cast<long long>(tc.b) * d.out_batch_stride +
-                              static_cast<long long>(m + d.out_row_offset) * d.ldo + n;
-        if (d.residual != nullptr) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const __nv_bfloat16*>(d.residual) + off);
+  for (int cc = 0; cc < 8; ++cc) {  // 8 chunks of 32 pixels = 2 tile rows each
+    tmem_ld_wait();
+    if (cc + 1 < 8) tmem_ld_32x32(taddr_row + (cc + 1) * 32, buf[(cc + 1) & 1]);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 t = __ldg(r4 + i);
-            v[8 * i + 0] += bf16_lo(t.x);
-            v[8 * i + 1] += bf16_hi(t.x);
-            v[8 * i + 2] += bf16_lo(t.y);
-            v[8 * i + 3] += bf16_hi(t.y);
-            v[8 * i + 4] += bf16_lo(t.z);
-            v[8 * i + 5] += bf16_hi(t.z);
-            v[8 * i + 6] += bf16_lo(t.w);
-            v[8 * i + 7] += bf16_hi(t.w);
-          }
-        }
-        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + off, v);
-      } break;
-      case EPI_BF16_ROWBIAS: {
-        const float bm = d.bias ? __ldg(d.bias + m) : 0.f;
+    for (int half = 0; half < 2; ++half) {
+      const int oh = h0 + cc * 2 + half;
+      if (oh >= d.cH || !c_ok) continue;
+      const long long row_off = ((frame_off + oh) * d.cW + w0) * d.out_C + c;
+      float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += bm;
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out) +
-                             static_cast<long long>(tc.b) * d.out_batch_stride +
-                             static_cast<long long>(m + d.out_row_offset) * d.ldo + n;
-        store_bf16x32(out, v);
-      } break;
-      case EPI_RESID_GATE: {
-        if (tc.split == 0) load_bias32(d.bias, n, v);
-        float* x = reinterpret_cast<float*>(d.out) +
-                   static_cast<long long>(tc.b) * d.out_batch_stride +
-                   static_cast<long long>(m + d.out_row_offset) * d.ldo + n;
-        const float4* g4 =
-            reinterpret_cast<const float4*>(d.gate + tc.b * d.gate_batch_stride + n);
-        if (a.splits > 1) {
-          // split-K partial sums: x += gate * partial, merged with fp32 reductions in L2
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(buf[cc & 1][half * 16 + i]) + bias;
+      if (res != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 g = __ldg(g4 + i);
-            atomicAdd(x + 4 * i + 0, g.x * v[4 * i + 0]);
-            atomicAdd(x + 4 * i + 1, g.y * v[4 * i + 1]);
-            atomicAdd(x + 4 * i + 2, g.z * v[4 * i + 2]);
-            atomicAdd(x + 4 * i + 3, g.w * v[4 * i + 3]);
-          }
-          break;
-        }
-        float4* x4 = reinterpret_cast<float4*>(x);
+        for (int i = 0; i < 16; ++i)
+          v[i] += __bfloat162float(res[row_off + static_cast<long long>(i) * d.out_C]);
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 g = __ldg(g4 + i);
-          float4 r = x4[i];
-          r.x += g.x * v[4 * i + 0];
-          r.y += g.y * v[4 * i + 1];
-          r.z += g.z * v[4 * i + 2];
-          r.w += g.w * v[4 * i + 3];
-          x4[i] = r;
-        }
-      } break;
-      case EPI_F32_ADD: {
-        load_bias32(d.bias, n, v);
-        if (d.addend != nullptr) {
-          const int ar = d.row_map ? __ldg(d.row_map + m) : m;
-          const float4* a4 =
-              reinterpret_cast<const float4*>(d.addend + static_cast<long long>(ar) * d.N + n);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 t = __ldg(a4 + i);
-            v[4 * i + 0] += t.x;
-            v[4 * i + 1] += t.y;
-            v[4 * i + 2] += t.z;
-            v[4 * i + 3] += t.w;
-          }
-        }
-        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) +
-                                               static_cast<long long>(tc.b) * d.out_batch_stride +
-                                               static_cast<long long>(m + d.out_row_offset) * d.ldo +
-                                               n);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      } break;
-      case EPI_UNPATCH: {
-        // row m = (gy, gx) of the noisy clip's token grid; column n = (p1, p2, c)
-        // out[b][c][0][2*gy+p1][2*gx+p2]   (mmdit.py:1453-1457, patch 2)
-        const int gy = m / d.up_gw, gx = m % d.up_gw;
-        const int H2 = 2 * d.up_gh, W2 = 2 * d.up_gw;
-        const long long ob = static_cast<long long>(tc.b) * d.out_batch_stride;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const int nn = n + i;
-          if (nn < d.N) {
-            float val = v[i] + (d.bias ? __ldg(d.bias + nn) : 0.f);
-            const int cch = nn % d.up_C;
-            const int pq = nn / d.up_C;
-            const int p1 = pq >> 1, p2 = pq & 1;
-            const long long o =
-                ob + (static_cast<long long>(cch) * H2 + (2 * gy + p1)) * W2 + (2 * gx + p2);
-            if (d.out_f32)
-              reinterpret_cast<float*>(d.out)[o] = val;
-            else
-              reinterpret_cast<__nv_bfloat16*>(d.out)[o] = __float2bfloat16(val);
-          }
-        }
-      } break;
-      case EPI_CONV: {
-        load_bias32(d.bias, n, v);
-        int ot = ct, oh = ch, ow = cw, oc = n, oH = d.cH, oW = d.cW;
-        if (d.conv_store == CONV_SHUFFLE_HW) {
-          // packed weight rows are ordered (p1, p2, c): vae.py:382
-          const int q = n / d.out_C;
-          oc = n % d.out_C;
-          oh = 2 * ch + (q >> 1);
-          ow = 2 * cw + (q & 1);
-          oH = 2 * d.cH;
-          oW = 2 * d.cW;
-        } else if (d.conv_store == CONV_INTERLEAVE_T) {
-          // packed weight rows are ordered (p, c): vae.py:407-409
-          const int p = n / d.out_C;
-          oc = n % d.out_C;
-          ot = 2 * ct + p - (d.conv_drop_first ? 1 : 0);
-          if (ot < 0) break;
-        }
-        const int oT = (d.conv_store == CONV_INTERLEAVE_T)
-                           ? (2 * d.cT - (d.conv_drop_first ? 1 : 0))
-                           : d.cT;
-        const long long off =
-            (((static_cast<long long>(tc.b) * oT + ot) * oH + oh) * oW + ow) * d.out_C + oc;
-        if (d.residual != nullptr) {
-          const uint4* r4 =
-              reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.residual) + off);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 t = __ldg(r4 + i);
-            v[8 * i + 0] += bf16_lo(t.x);
-            v[8 * i + 1] += bf16_hi(t.x);
-            v[8 * i + 2] += bf16_lo(t.y);
-            v[8 * i + 3] += bf16_hi(t.y);
-            v[8 * i + 4] += bf16_lo(t.z);
-            v[8 * i + 5] += bf16_hi(t.z);
-            v[8 * i + 6] += bf16_lo(t.w);
-            v[8 * i + 7] += bf16_hi(t.w);
-          }
-        }
-        if (d.out_C >= 32) {
-          store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + off, v);
-        } else {
-          // narrow outputs (conv_out: 3 channels padded to 16 weight rows)
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d.out) + off;
-          for (int i = 0; i < 32 && (n + i) < d.out_C; ++i) o[i] = __float2bfloat16(v[i]);
-        }
-      } break;
-      default:
-        break;
+      for (int i = 0; i < 16; ++i)
+        out[row_off + static_cast<long long>(i) * d.out_C] = __float2bfloat16(v[i]);
     }
   }
+  tmem_ld_wait();
 }
 
 // ------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------
-template <int BN>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ KArgs a) {
-  using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::kStages;
-  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -362,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -373,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<C::kTmemCols>(tmem_slot);
+    tmem_alloc<kTmemCols>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -381,44 +436,59 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const GemmDesc& d = a.d;
+  // split-K: the cluster = the splits of ONE tile (grid = tiles * splits, one pass);
+  // otherwise a persistent loop over tiles
+  const bool split_mode = a.splits > 1;
+  const int split = split_mode ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile0 =
+      split_mode ? static_cast<int>(blockIdx.x) / a.splits : static_cast<int>(blockIdx.x);
+  const int tile_step = split_mode ? a.total_tiles : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(a, tile);
+      for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
+        const TileCoord tc = decode_tile(a, tile, split);
         int ct = 0, h0 = 0, w0 = 0;
         if (d.a_mode == 1) {
-          int per_frame = a.tiles_w * a.tiles_h;
+          const int per_frame = a.tiles_w * a.tiles_h;
           ct = tc.m_tile / per_frame;
-          int r = tc.m_tile % per_frame;
-          h0 = (r / a.tiles_w) * 8;
+          const int r = tc.m_tile % per_frame;
+          h0 = (r / a.tiles_w) * (a.swap ? 16 : 8);
           w0 = (r % a.tiles_w) * 16;
         }
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + C::kABytes;
-          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
           if (d.a_mode == 1) {
             const int tap = kb / a.c_blocks;
             const int cb = kb - tap * a.c_blocks;
             const int dt = tap / (d.kh * d.kw);
             const int dh = (tap / d.kw) % d.kh;
             const int dw = tap % d.kw;
-            // causal in time (kt-1 frames of zero history), centred in space
-            tma_load_5d(&a.tmA, &full_bar[stage], sa, cb * 64, w0 + dw - d.kw / 2,
-                        h0 + dh - d.kh / 2, ct + dt - (d.kt - 1), tc.b);
+            // causal in time (kt-1 frames of zero history), centred in space; TMA's
+            // out-of-bounds zero fill is the padding
+            const int x = w0 + dw - d.kw / 2, y = h0 + dh - d.kh / 2, t = ct + dt - (d.kt - 1);
+            if (a.swap) {
+              // weights (<= 128 rows) feed the M side, a 16x16-pixel box the N side
+              tma_load_2d(&a.tmB, &full_bar[stage], sa, kb * BK, 0);
+              tma_load_5d(&a.tmA, &full_bar[stage], sb, cb * 64, x, y, t, tc.b);
+            } else {
+              tma_load_5d(&a.tmA, &full_bar[stage], sa, cb * 64, x, y, t, tc.b);
+              tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
+            }
           } else {
             tma_load_3d(&a.tmA, &full_bar[stage], sa, kb * BK, tc.m_tile * BM, tc.b);
+            if (d.w_batch_stride != 0)
+              tma_load_3d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN, tc.b);
+            else
+              tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
           }
-          if (d.w_batch_stride != 0)
-            tma_load_3d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN, tc.b);
-          else
-            tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
-          if (++stage == C::kStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -432,18 +502,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < a.total_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * BN;
-        const TileCoord tc = decode_tile(a, tile);
+        const TileCoord tc = decode_tile(a, tile, split);
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t sb = sa + C::kABytes;
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
           const uint64_t da = umma_desc_sw128(sa, 16, 1024);
           const uint64_t db = umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
@@ -452,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, ((kb - tc.kb0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == C::kStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -464,41 +534,145 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ============================ epilogue ================================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int row_in_tile = quarter * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      const TileCoord tc = decode_tile(a, tile);
-      mbar_wait(&tmem_full[as], aph);
+    if (!split_mode) {
+      int it = 0;
+      for (int tile = tile0; tile < a.total_tiles; tile += tile_step, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        const TileCoord tc = decode_tile(a, tile, 0);
+        mbar_wait(&tmem_full[as], aph);
+        tc_fence_after();
+        if (MODE == EPI_CONV && a.swap)
+          epilogue_tile_swapped(a, tc, tmem_base + as * BN, quarter, lane);
+        else
+          epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter);
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);
+      }
+    } else {
+      // park the fp32 partial tile in this CTA's smem as [col4][row] float4 (the operand ring is
+      // idle: every MMA that read it has retired once tmem_full fires)
+      mbar_wait(&tmem_full[0], 0);
       tc_fence_after();
-      epilogue_tile<BN>(a, tc, tmem_base + as * BN, row_in_tile, quarter);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      float4* part = reinterpret_cast<float4*>(smem);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          part[(c * 8 + i) * BM + row_in_tile] =
+              make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                          __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+      }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
     }
+  }
+
+  if (split_mode) {
+    // every CTA of the cluster has parked its partial tile
+    __syncwarp();
+    cluster_sync_all();
+    if (warp >= 2) {
+      constexpr int W = EpiW<MODE>::value;
+      const int t = threadIdx.x - 64;      // 0..127
+      const int rows_per = BM / a.splits;  // rows of the tile this CTA finishes
+      const int row_in_tile = split * rows_per + (t % rows_per);
+      const int group = t / rows_per;      // 0..splits-1: which column chunks
+      const TileCoord tc = decode_tile(a, tile0, split);
+      const RowCtx r = make_row(a, tc, row_in_tile);
+      const uint32_t part0 = smem_u32(smem);
+      for (int c = group; c < BN / W; c += a.splits) {
+        const int n = tc.n_tile * BN + c * W;
+        if (n >= d.N || !r.ok) continue;
+        float v[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] = 0.f;
+#pragma unroll 1
+        for (int p = 0; p < a.splits; ++p) {  // fixed order: bit-reproducible sums
+          const uint32_t peer = map_to_cta(part0, static_cast<uint32_t>(p));
+#pragma unroll
+          for (int i = 0; i < W / 4; ++i) {
+            const float4 q = ld_dsmem_f4(
+                peer + static_cast<uint32_t>(((c * (W / 4) + i) * BM + row_in_tile) * 16));
+            v[4 * i + 0] += q.x;
+            v[4 * i + 1] += q.y;
+            v[4 * i + 2] += q.z;
+            v[4 * i + 3] += q.w;
+          }
+        }
+        epi_row<MODE, W>(a, r, n, v);
+      }
+    }
+    // nobody leaves while a peer may still read its shared memory
+    __syncwarp();
+    cluster_sync_all();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
-template <int BN>
-int launch_bn(const KArgs& ka, cudaStream_t stream) {
-  using C = Cfg<BN>;
+template <int MODE>
+int launch_mode(const KArgs& ka, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    DV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  int grid = ka.total_tiles < sm_count() ? ka.total_tiles : sm_count();
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(ka);
-  DV_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (ka.splits > 1) {
+    cfg.gridDim = dim3(ka.total_tiles * ka.splits);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ka.splits;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(ka.total_tiles < sm_count() ? ka.total_tiles : sm_count());
+  }
+  DV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE>, ka));
   note_launch();
   return 0;
+}
+
+// CTAs that can be resident at once when launched as clusters of `s` (GPC packing leaves a few SMs
+// idle); the kernel's footprint does not depend on the epilogue mode
+int cluster_capacity(int s) {
+  static int cap[kMaxSplits + 1] = {0};
+  if (cap[s] != 0) return cap[s];
+  cudaFuncSetAttribute(gemm_tc_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.gridDim = dim3(s * 64);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = s;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<EPI_BF16>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    cap[s] = -1;
+  } else {
+    cap[s] = n * s;
+  }
+  return cap[s];
 }
 
 }  // namespace
@@ -506,20 +680,26 @@ int launch_bn(const KArgs& ka, cudaStream_t stream) {
 int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   KArgs ka;
   ka.d = d;
+  ka.swap = 0;
   DV_REQUIRE(d.batch > 0 && d.N > 0, "gemm: empty problem (batch=%d N=%d)", d.batch, d.N);
 
-  // ---- tile shape: wide tiles when there is enough work to fill the SMs -----
   int K;
   if (d.a_mode == 1) {
+    DV_REQUIRE(d.mode == EPI_CONV, "conv operand needs EPI_CONV (mode %d)", d.mode);
     DV_REQUIRE(d.cC % 64 == 0, "conv: Cin=%d must be a multiple of 64 (pad at pack time)", d.cC);
     DV_REQUIRE(d.cW % 16 == 0 && d.cH % 8 == 0, "conv: H=%d W=%d must be multiples of 8/16", d.cH,
                d.cW);
     ka.c_blocks = d.cC / 64;
     K = d.kt * d.kh * d.kw * d.cC;
+    ka.swap = (d.N <= 128 && d.conv_store == CONV_PLAIN && d.w_batch_stride == 0) ? 1 : 0;
+    DV_REQUIRE(ka.swap || (d.N % 32 == 0 && d.out_C % 32 == 0),
+               "conv: Cout=%d (stored channels %d) must be <= 128 with a plain store or multiples of 32",
+               d.N, d.out_C);
     ka.tiles_w = d.cW / 16;
-    ka.tiles_h = d.cH / 8;
+    ka.tiles_h = ka.swap ? (d.cH + 15) / 16 : d.cH / 8;
     ka.m_tiles = d.cT * ka.tiles_w * ka.tiles_h;
   } else {
+    DV_REQUIRE(d.mode != EPI_CONV, "EPI_CONV needs the conv operand");
     DV_REQUIRE(d.K % 64 == 0, "gemm: K=%d must be a multiple of 64", d.K);
     DV_REQUIRE(d.M > 0, "gemm: M=%d", d.M);
     K = d.K;
@@ -528,52 +708,38 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
     ka.m_tiles = (d.M + BM - 1) / BM;
   }
   ka.k_blocks = K / BK;
+  DV_REQUIRE(d.mode == EPI_UNPATCH || d.mode == EPI_CONV || d.N % 32 == 0,
+             "gemm: N=%d must be a multiple of 32 for epilogue mode %d", d.N, d.mode);
+  DV_REQUIRE(d.mode != EPI_QKV || d.N % 64 == 0, "gemm: QKV epilogue needs N %% 64 == 0 (N=%d)",
+             d.N);
+  ka.n_tiles = ka.swap ? 1 : (d.N + BN - 1) / BN;
+  const long long tiles_ll = static_cast<long long>(ka.m_tiles) * d.batch * ka.n_tiles;
+  DV_REQUIRE(tiles_ll < (1ll << 30), "gemm: too many tiles");
+  ka.total_tiles = static_cast<int>(tiles_ll);
 
-  // ---- tile width and split-K from a small cost model --------------------------------------
-  // A CTA streams (128 + BN) x K_split x 2 bytes through its SM's L2 port (~80 GB/s per SM, ~10
-  // TB/s aggregate) and spends 128 x BN x K_split / 4096 tensor cycles; small-M problems are
-  // port-bound unless the reduction is split across more SMs (only the gate-residual epilogue
-  // can merge partial sums: fp32 atomics into the residual stream).
-  const long long mt_total = static_cast<long long>(ka.m_tiles) * d.batch;
-  const int nsm = sm_count();
-  int bn = 64, splits = 1;
-  {
+  // ---- split-K: a CTA needs ~570 cycles per k-block (4 MMAs at the 128-cycle floor) plus ~3000
+  // cycles of fixed latency (first TMA round trip, epilogue); with fewer tiles than SMs the K
+  // loop is cut over a cluster.  Usable SMs shrink a little with the cluster size (GPC packing).
+  int splits = 1;
+  if (!ka.swap && getenv("DV_GEMM_NOSPLIT") == nullptr) {
+    const int nsm = sm_count();
     double best = 1e30;
-    const int cand_bn[3] = {256, 128, 64};
-    const int cand_s[6] = {1, 2, 3, 4, 6, 8};
-    for (int bi = 0; bi < 3; ++bi) {
-      const int b_ = cand_bn[bi];
-      if (b_ > 64 && (d.N % b_ != 0)) continue;
-      const long long tiles = mt_total * ((d.N + b_ - 1) / b_);
-      for (int si = 0; si < 6; ++si) {
-        const int s_ = cand_s[si];
-        if (s_ > 1 && (d.mode != EPI_RESID_GATE || ka.k_blocks / s_ < 4)) break;
-        const int kbs = (ka.k_blocks + s_ - 1) / s_;
-        const long long ctas = tiles * s_;
-        const double waves = static_cast<double>((ctas + nsm - 1) / nsm);
-        const double cta_bytes = (128.0 + b_) * kbs * 64 * 2;
-        const double t_port = waves * cta_bytes / 80e9;
-        const double t_l2 = ctas * cta_bytes / 10e12;
-        const double t_mma = waves * (128.0 * b_ * kbs * 64 / 4096.0) / 1.8e9;
-        const double t_epi = waves * (s_ > 1 ? 3.0e-6 : 1.0e-6) * (b_ / 64.0) * 0.5;
-        double t = t_port > t_l2 ? t_port : t_l2;
-        t = t > t_mma ? t : t_mma;
-        t += t_epi + 2.0e-6;
-        if (t < best) {
-          best = t;
-          bn = b_;
-          splits = s_;
-        }
+    for (int s = 1; s <= kMaxSplits; s *= 2) {
+      if (s > 1 && ka.k_blocks / s < 2) break;
+      const int usable = s == 1 ? nsm : cluster_capacity(s);
+      if (usable <= 0) break;
+      const long long ctas = tiles_ll * s;
+      const double waves = static_cast<double>((ctas + usable - 1) / usable);
+      const double kbs = static_cast<double>((ka.k_blocks + s - 1) / s);
+      const double t = waves * (kbs * 570.0 + 3000.0) + (s > 1 ? 2500.0 : 0.0);
+      if (t < best * 0.93) {  // a larger cluster has to pay for itself
+        best = t;
+        splits = s;
       }
     }
   }
-  DV_REQUIRE(d.mode == EPI_UNPATCH || d.mode == EPI_CONV || d.N % 32 == 0,
-             "gemm: N=%d must be a multiple of 32 for epilogue mode %d", d.N, d.mode);
-  ka.n_tiles = (d.N + bn - 1) / bn;
   ka.kb_per_split = (ka.k_blocks + splits - 1) / splits;
-  splits = (ka.k_blocks + ka.kb_per_split - 1) / ka.kb_per_split;  // no empty split
   ka.splits = splits;
-  ka.total_tiles = static_cast<int>(mt_total) * ka.n_tiles * splits;
 
   // ---- tensor maps ------------------------------------------------------------
   if (d.a_mode == 1) {
@@ -582,7 +748,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
     uint64_t strides[4] = {(uint64_t)d.cC * 2, (uint64_t)d.cC * d.cW * 2,
                            (uint64_t)d.cC * d.cW * d.cH * 2,
                            (uint64_t)d.cC * d.cW * d.cH * d.cT * 2};
-    uint32_t box[5] = {64, 16, 8, 1, 1};
+    uint32_t box[5] = {64, 16, ka.swap ? 16u : 8u, 1, 1};
     int rc = make_tensor_map_bf16(&ka.tmA, d.A, 5, dims, strides, box, 1);
     if (rc) return rc;
   } else {
@@ -597,32 +763,45 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   if (d.w_batch_stride != 0) {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)d.w_rows, (uint64_t)d.batch};
     uint64_t strides[2] = {ldw_bytes, (uint64_t)d.w_batch_stride * 2};
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint32_t box[3] = {64, (uint32_t)BN, 1};
     int rc = make_tensor_map_bf16(&ka.tmB, d.W, 3, dims, strides, box, 1);
     if (rc) return rc;
   } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)d.w_rows};
     uint64_t strides[1] = {ldw_bytes};
-    uint32_t box[2] = {64, (uint32_t)bn};
+    uint32_t box[2] = {64, ka.swap ? 128u : (uint32_t)BN};
     int rc = make_tensor_map_bf16(&ka.tmB, d.W, 2, dims, strides, box, 1);
     if (rc) return rc;
   }
 
-  const double rows = static_cast<double>(ka.m_tiles ? (d.a_mode == 1 ? (double)d.cT * d.cH * d.cW : d.M) : 0) * d.batch;
-  const int pid = prof_begin(d.a_mode == 1 ? PROF_CONV : PROF_GEMM, 2.0 * rows * d.N * K,
-                             2.0 * (rows * K / (d.a_mode == 1 ? d.kt * d.kh * d.kw : 1) + (double)d.N * K + rows * d.N),
-                             stream);
+  const double rows =
+      static_cast<double>(d.a_mode == 1 ? (double)d.cT * d.cH * d.cW : d.M) * d.batch;
+  char tag[56] = "";
+  if (prof_on()) {
+    if (d.a_mode == 1)
+      snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k%d%s e%d", d.cT, d.cH, d.cW, d.cC, d.N,
+               d.kt, ka.swap ? " sw" : "", d.conv_store);
+    else
+      snprintf(tag, sizeof(tag), "gemm B%d M%d N%d K%d s%d e%d", d.batch, d.M, d.N, K, splits,
+               d.mode);
+  }
+  const int pid = prof_begin(
+      d.a_mode == 1 ? PROF_CONV : PROF_GEMM, 2.0 * rows * d.N * K,
+      2.0 * (rows * K / (d.a_mode == 1 ? d.kt * d.kh * d.kw : 1) + (double)d.N * K + rows * d.N),
+      stream, tag);
   int rc;
-  switch (bn) {
-    case 256:
-      rc = launch_bn<256>(ka, stream);
-      break;
-    case 128:
-      rc = launch_bn<128>(ka, stream);
-      break;
+  switch (d.mode) {
+    case EPI_BF16: rc = launch_mode<EPI_BF16>(ka, stream); break;
+    case EPI_GELU: rc = launch_mode<EPI_GELU>(ka, stream); break;
+    case EPI_RESID_GATE: rc = launch_mode<EPI_RESID_GATE>(ka, stream); break;
+    case EPI_F32_ADD: rc = launch_mode<EPI_F32_ADD>(ka, stream); break;
+    case EPI_QKV: rc = launch_mode<EPI_QKV>(ka, stream); break;
+    case EPI_UNPATCH: rc = launch_mode<EPI_UNPATCH>(ka, stream); break;
+    case EPI_CONV: rc = launch_mode<EPI_CONV>(ka, stream); break;
+    case EPI_BF16_ROWBIAS: rc = launch_mode<EPI_BF16_ROWBIAS>(ka, stream); break;
     default:
-      rc = launch_bn<64>(ka, stream);
-      break;
+      set_error("gemm: unknown epilogue mode %d", d.mode);
+      rc = -1;
   }
   prof_end(pid, stream);
   return rc;

@@ -12,18 +12,19 @@ namespace {
 // merged with fp64 atomics; pass 2 (gn_finalize) turns them into (mean, rstd).
 // ---------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
-constexpr int kGnPixPerCta = 256;
 
+// Thread t of a CTA owns the 8-channel vector (t % (C/8)) of every pixel it visits, so its group
+// (two groups when a group has 4 channels) never changes; pixels are strided by 256 / (C/8) and
+// four loads are kept in flight per thread.
 __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloat16* __restrict__ x,
                                                                 double* __restrict__ acc, int HW,
-                                                                int C, int G) {
-  // grid: (ceil(HW / kGnPixPerCta), frames).  Thread t owns the 8-channel vector (t % (C/8)) and
-  // strides over pixels, so every thread always accumulates into ONE group.
+                                                                int C, int G, int pix_per_cta) {
+  // grid: (ceil(HW / pix_per_cta), frames)
   const int f = blockIdx.y;
   const int vec_per_pix = C / 8;
   const int cpg = C / G;  // channels per group: 4, 8 or 16
-  const int p0 = blockIdx.x * kGnPixPerCta;
-  const int p1 = min(p0 + kGnPixPerCta, HW);
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, HW);
   const uint4* xf = reinterpret_cast<const uint4*>(x + static_cast<long long>(f) * HW * C);
   __shared__ float s_sum[64], s_sq[64];
   if (threadIdx.x < 64) {
@@ -34,8 +35,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloa
   const int v = threadIdx.x % vec_per_pix;           // requires blockDim % vec_per_pix == 0
   const int pstep = kGnThreads / vec_per_pix;
   float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;      // cpg == 4 -> two groups per 8-vector
-  for (int p = p0 + threadIdx.x / vec_per_pix; p < p1; p += pstep) {
-    const uint4 t = __ldg(xf + static_cast<long long>(p) * vec_per_pix + v);
+  auto add = [&](const uint4& t) {
     const float e[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y),
                         bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
 #pragma unroll
@@ -48,7 +48,16 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloa
       s1 += e[i];
       q1 += e[i] * e[i];
     }
+  };
+  int p = p0 + threadIdx.x / vec_per_pix;
+  for (; p + 3 * pstep < p1; p += 4 * pstep) {
+    uint4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = __ldg(xf + static_cast<long long>(p + u * pstep) * vec_per_pix + v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add(t[u]);
   }
+  for (; p < p1; p += pstep) add(__ldg(xf + static_cast<long long>(p) * vec_per_pix + v));
   if (cpg == 4) {
     atomicAdd(&s_sum[(v * 8) / 4], s0);
     atomicAdd(&s_sq[(v * 8) / 4], q0);
@@ -80,42 +89,64 @@ __global__ void gn_finalize_kernel(double* __restrict__ acc, float* __restrict__
   acc[2 * i + 1] = 0.0;
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x,
-                                                       const float* __restrict__ stats,
-                                                       const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta,
-                                                       __nv_bfloat16* __restrict__ y, long long HWv,
-                                                       int C, int G, int do_silu, long long total) {
-  // one 8-channel vector per thread; total = frames * HW * C / 8
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+__device__ __forceinline__ float silu_fast(float x) {
+  return __fdividef(x, 1.0f + __expf(-x));
+}
+
+// y = silu?( (x - mean) * rstd * gamma + beta ): same thread -> channel-vector mapping as the
+// statistics pass, so the per-channel affine a*x + b is hoisted out of the pixel loop.
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              __nv_bfloat16* __restrict__ y, int HW,
+                                                              int C, int G, int do_silu,
+                                                              int pix_per_cta) {
+  const int f = blockIdx.y;
   const int vec_per_pix = C / 8;
-  const int v = i % vec_per_pix;
-  const long long f = i / HWv;  // HWv = HW * vec_per_pix
-  const int c0 = v * 8;
   const int cpg = C / G;
-  const uint4 t = __ldg(reinterpret_cast<const uint4*>(x) + i);
-  float e[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y),
-                bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
-  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
-  const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, HW);
+  const int v = threadIdx.x % vec_per_pix;
+  const int pstep = kGnThreads / vec_per_pix;
+  const int c0 = v * 8;
+  float a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int g = (c0 + k) / cpg;
-    const float2 ms = __ldg(reinterpret_cast<const float2*>(stats) + f * G + g);
-    float r = (e[k] - ms.x) * ms.y * gm[k] + bt[k];
-    e[k] = do_silu ? silu(r) : r;
+    const float2 ms = __ldg(reinterpret_cast<const float2*>(stats) + static_cast<long long>(f) * G + g);
+    const float gm = __ldg(gamma + c0 + k);
+    a[k] = ms.y * gm;
+    b[k] = __ldg(beta + c0 + k) - ms.x * a[k];
   }
-  uint4 o;
-  o.x = pack_bf16x2(e[0], e[1]);
-  o.y = pack_bf16x2(e[2], e[3]);
-  o.z = pack_bf16x2(e[4], e[5]);
-  o.w = pack_bf16x2(e[6], e[7]);
-  reinterpret_cast<uint4*>(y)[i] = o;
+  const long long base = static_cast<long long>(f) * HW * vec_per_pix;
+  const uint4* xf = reinterpret_cast<const uint4*>(x) + base;
+  uint4* yf = reinterpret_cast<uint4*>(y) + base;
+  auto apply = [&](const uint4& t) {
+    float e[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y),
+                  bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float r = fmaf(e[k], a[k], b[k]);
+      e[k] = do_silu ? silu_fast(r) : r;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(e[0], e[1]);
+    o.y = pack_bf16x2(e[2], e[3]);
+    o.z = pack_bf16x2(e[4], e[5]);
+    o.w = pack_bf16x2(e[6], e[7]);
+    return o;
+  };
+  int p = p0 + threadIdx.x / vec_per_pix;
+  for (; p + 3 * pstep < p1; p += 4 * pstep) {
+    uint4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = __ldg(xf + static_cast<long long>(p + u * pstep) * vec_per_pix + v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) yf[static_cast<long long>(p + u * pstep) * vec_per_pix + v] = apply(t[u]);
+  }
+  for (; p < p1; p += pstep)
+    yf[static_cast<long long>(p) * vec_per_pix + v] = apply(__ldg(xf + static_cast<long long>(p) * vec_per_pix + v));
 }
 
 // softmax over rows of fp32 scores (single 512-wide head of the mid block: diffusers
@@ -188,14 +219,25 @@ __global__ void latent_tile_kernel(const T* __restrict__ z, __nv_bfloat16* __res
 
 }  // namespace
 
+// pixels per CTA: every thread should see >= 8 vectors (two unrolled rounds) when the tensor is
+// large, while small tensors still spread over >= 2 CTAs per SM
+static int gn_pix_per_cta(int HW, int frames, int C) {
+  const int pstep = kGnThreads / (C / 8);
+  int ppc = pstep * 16;
+  while (ppc > pstep * 4 && static_cast<long long>((HW + ppc - 1) / ppc) * frames < 2 * sm_count()) ppc /= 2;
+  return ppc;
+}
+
 int launch_gn_stats(const __nv_bfloat16* x, double* acc, float* stats, int frames, int HW, int C,
                     int G, float eps, cudaStream_t stream) {
   DV_REQUIRE(C % 8 == 0 && G <= 64 && C % G == 0, "gn_stats: C=%d G=%d", C, G);
   const int cpg = C / G;
   DV_REQUIRE(cpg == 4 || cpg % 8 == 0, "gn_stats: %d channels per group unsupported", cpg);
   DV_REQUIRE(kGnThreads % (C / 8) == 0, "gn_stats: C=%d does not divide the CTA", C);
-  dim3 grid((HW + kGnPixPerCta - 1) / kGnPixPerCta, frames);
-  gn_partial_kernel<<<grid, kGnThreads, 0, stream>>>(x, acc, HW, C, G);
+  const int ppc = gn_pix_per_cta(HW, frames, C);
+  dim3 grid((HW + ppc - 1) / ppc, frames);
+  ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(frames) * HW * C * 2.0, stream, "gn_stats");
+  gn_partial_kernel<<<grid, kGnThreads, 0, stream>>>(x, acc, HW, C, G, ppc);
   DV_CHECK_CUDA(cudaGetLastError());
   const int n = frames * G;
   gn_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(
@@ -208,10 +250,11 @@ int launch_gn_stats(const __nv_bfloat16* x, double* acc, float* stats, int frame
 int launch_gn_apply(const __nv_bfloat16* x, const float* stats, const float* gamma,
                     const float* beta, __nv_bfloat16* y, int frames, int HW, int C, int G, int silu_on,
                     cudaStream_t stream) {
-  const long long total = static_cast<long long>(frames) * HW * C / 8;
-  const long long HWv = static_cast<long long>(HW) * (C / 8);
-  gn_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      x, stats, gamma, beta, y, HWv, C, G, silu_on, total);
+  DV_REQUIRE(C % 8 == 0 && C % G == 0 && kGnThreads % (C / 8) == 0, "gn_apply: C=%d G=%d", C, G);
+  const int ppc = gn_pix_per_cta(HW, frames, C);
+  dim3 grid((HW + ppc - 1) / ppc, frames);
+  ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(frames) * HW * C * 4.0, stream, "gn_apply");
+  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, stats, gamma, beta, y, HW, C, G, silu_on, ppc);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;

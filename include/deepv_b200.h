@@ -46,6 +46,8 @@ void dv_launch_count_reset(void);
  * stream first.                                                                               */
 void dv_profile_enable(int on);
 void dv_profile_reset(void);
+/* one CSV line per recorded launch (kind,tag,flops,bytes,ms); synchronise first */
+int dv_profile_dump(const char* path);
 int dv_profile_summary(int kind, long long* count, double* ms, double* flops, double* bytes);
 
 /* ------------------------------------------------------------------------------------------
