@@ -15,17 +15,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Reference: AdaLayerNormZero / AdaLayerNormContinuous / norm2 (+ modulate)
 // model/mmdit.py:558,505,412-413,427-428; LN eps 1e-6 inside the sqrt, biased variance.
 // ---------------------------------------------------------------------------------
+struct LnSeg {
+  const float* x;
+  long long x_bs;
+  __nv_bfloat16* out;
+  long long out_bs;
+  const float* shift;
+  const float* scale;
+  int L;
+};
+struct LnArgs {
+  LnSeg seg[2];  // seg[1].L == 0: single segment (rows of seg[0] come first)
+  int mod_bs, B;
+  float eps;
+};
+
 template <int D>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(
-    const float* __restrict__ x, long long x_bs, __nv_bfloat16* __restrict__ out, long long out_bs,
-    const float* __restrict__ shift, const float* __restrict__ scale, int mod_bs, int B, int L,
-    float eps) {
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant__ LnArgs a) {
   constexpr int V = D / 128;  // float4 per lane
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= B * L) return;
-  const int b = warp / L, l = warp - b * L;
-  const float4* xr = reinterpret_cast<const float4*>(x + b * x_bs + static_cast<long long>(l) * D);
+  const int rows0 = a.B * a.seg[0].L;
+  if (warp >= rows0 + a.B * a.seg[1].L) return;
+  const bool second = warp >= rows0;
+  if (second) warp -= rows0;
+  const LnSeg& sg = second ? a.seg[1] : a.seg[0];
+  const int b = warp / sg.L, l = warp - b * sg.L;
+  const float4* xr = reinterpret_cast<const float4*>(sg.x + b * sg.x_bs + static_cast<long long>(l) * D);
   float4 v[V];
   float s = 0.f;
 #pragma unroll
@@ -37,13 +53,13 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += a * a + bq * bq + c * c + d * d;
+    float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+    q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-  const float4* sh = reinterpret_cast<const float4*>(shift + static_cast<long long>(b) * mod_bs);
-  const float4* sc = reinterpret_cast<const float4*>(scale + static_cast<long long>(b) * mod_bs);
-  uint2* o = reinterpret_cast<uint2*>(out + b * out_bs + static_cast<long long>(l) * D);
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + a.eps);
+  const float4* sh = reinterpret_cast<const float4*>(sg.shift + static_cast<long long>(b) * a.mod_bs);
+  const float4* sc = reinterpret_cast<const float4*>(sg.scale + static_cast<long long>(b) * a.mod_bs);
+  uint2* o = reinterpret_cast<uint2*>(sg.out + b * sg.out_bs + static_cast<long long>(l) * D);
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const float4 h = __ldg(sh + lane + 32 * i);
@@ -257,23 +273,47 @@ __global__ void __launch_bounds__(128) key_bias_kernel(const float* __restrict__
 
 }  // namespace
 
-int launch_ln_modulate(const float* x, long long x_bs, __nv_bfloat16* out, long long out_bs,
-                       const float* shift, const float* scale, int mod_bs, int B, int L, int D,
-                       float eps, cudaStream_t stream) {
+int launch_ln_modulate2(const LnRows& r0, const LnRows* r1, int mod_bs, int B, int D, float eps,
+                        cudaStream_t stream) {
   DV_REQUIRE(D == 1536 || D == 512, "ln_modulate: D=%d unsupported", D);
-  const long long rows = static_cast<long long>(B) * L;
+  LnArgs a;
+  auto fill = [](LnSeg& s, const LnRows& r) {
+    s.x = r.x;
+    s.x_bs = r.x_bs;
+    s.out = r.out;
+    s.out_bs = r.out_bs;
+    s.shift = r.shift;
+    s.scale = r.scale;
+    s.L = r.L;
+  };
+  fill(a.seg[0], r0);
+  if (r1 != nullptr) {
+    fill(a.seg[1], *r1);
+  } else {
+    a.seg[1] = a.seg[0];
+    a.seg[1].L = 0;
+  }
+  a.mod_bs = mod_bs;
+  a.B = B;
+  a.eps = eps;
+  const long long rows = static_cast<long long>(B) * (a.seg[0].L + a.seg[1].L);
   if (rows == 0) return 0;
   const int blocks = static_cast<int>((rows * 32 + 255) / 256);
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(rows) * D * 6.0, stream, "ln_modulate");
   if (D == 1536)
-    ln_modulate_kernel<1536><<<blocks, 256, 0, stream>>>(x, x_bs, out, out_bs, shift, scale,
-                                                         mod_bs, B, L, eps);
+    ln_modulate_kernel<1536><<<blocks, 256, 0, stream>>>(a);
   else
-    ln_modulate_kernel<512><<<blocks, 256, 0, stream>>>(x, x_bs, out, out_bs, shift, scale, mod_bs,
-                                                        B, L, eps);
+    ln_modulate_kernel<512><<<blocks, 256, 0, stream>>>(a);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;
+}
+
+int launch_ln_modulate(const float* x, long long x_bs, __nv_bfloat16* out, long long out_bs,
+                       const float* shift, const float* scale, int mod_bs, int B, int L, int D,
+                       float eps, cudaStream_t stream) {
+  LnRows r = {x, x_bs, out, out_bs, shift, scale, L};
+  return launch_ln_modulate2(r, nullptr, mod_bs, B, D, eps, stream);
 }
 
 int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int in_stride,

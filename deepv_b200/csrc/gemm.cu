@@ -40,22 +40,36 @@ constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align
 constexpr uint32_t kTmemCols = 2 * BN;
 constexpr int kMaxSplits = 8;  // portable cluster size
 
-struct KArgs {
+struct Problem {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
   GemmDesc d;
-  int m_tiles, n_tiles, k_blocks, total_tiles;
-  int splits, kb_per_split;  // split-K over a cluster of `splits` CTAs
-  int tiles_w, tiles_h;      // conv: M-tile grid inside one frame
-  int c_blocks;              // conv: Cin / 64
-  int swap;                  // conv, Cout <= 128: weights are the M operand, 16x16 pixels the N operand
+  int m_tiles, n_tiles, k_blocks, tiles;
+  int kb_per_split;      // split-K over a cluster of `splits` CTAs
+  int tiles_w, tiles_h;  // conv: M-tile grid inside one frame
+  int c_blocks;          // conv: Cin / 64
+  int swap;              // conv, Cout <= 128: weights are the M operand, 16x16 pixels the N operand
+};
+
+// One launch runs up to two problems of the same epilogue mode (the video and the context stream
+// of a joint transformer block): tiles [0, p[0].tiles) belong to p[0], the rest to p[1].
+struct KArgs {
+  Problem p[2];
+  int total_tiles;
+  int splits;
 };
 
 struct TileCoord {
   int b, m_tile, n_tile, kb0, kb1;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const KArgs& a, int tile, int split) {
+__device__ __forceinline__ const Problem& problem_of(const KArgs& k, int& tile) {
+  if (tile < k.p[0].tiles) return k.p[0];
+  tile -= k.p[0].tiles;
+  return k.p[1];
+}
+
+__device__ __forceinline__ TileCoord decode_tile(const Problem& a, int tile, int split) {
   TileCoord tc;
   tc.n_tile = tile % a.n_tiles;
   const int rest = tile / a.n_tiles;
@@ -99,7 +113,7 @@ struct RowCtx {
   int ct, ch, cw;  // conv: output pixel
 };
 
-__device__ __forceinline__ RowCtx make_row(const KArgs& a, const TileCoord& tc, int row_in_tile) {
+__device__ __forceinline__ RowCtx make_row(const Problem& a, const TileCoord& tc, int row_in_tile) {
   const GemmDesc& d = a.d;
   RowCtx r;
   r.b = tc.b;
@@ -170,7 +184,7 @@ struct EpiW {
 
 // v = W accumulator columns [n, n + W) of output row `r`; n < d.N and r.ok hold.
 template <int MODE, int W>
-__device__ __forceinline__ void epi_row(const KArgs& a, const RowCtx& r, int n, float (&v)[W]) {
+__device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n, float (&v)[W]) {
   const GemmDesc& d = a.d;
   if constexpr (MODE == EPI_BF16 || MODE == EPI_GELU) {
     add_bias<W>(d.bias, n, v);
@@ -307,7 +321,7 @@ __device__ __forceinline__ void epi_row(const KArgs& a, const RowCtx& r, int n, 
 
 // Accumulator tile in TMEM -> epilogue, 32 columns in flight while 32 are processed.
 template <int MODE>
-__device__ __forceinline__ void epilogue_from_tmem(const KArgs& a, const TileCoord& tc,
+__device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileCoord& tc,
                                                    uint32_t tmem_acc, int row_in_tile, int quarter) {
   constexpr int W = EpiW<MODE>::value;
   const GemmDesc& d = a.d;
@@ -353,7 +367,7 @@ __device__ __forceinline__ void epilogue_from_tmem(const KArgs& a, const TileCoo
 // Swapped-operand conv tile (Cout <= 128): TMEM lane = output channel, column = pixel of the
 // 16x16 tile (w fastest).  One thread owns one channel; for every pixel the warp writes a
 // contiguous run of 32 channels (64 B) into the NDHWC output.  Plain store mode only.
-__device__ __forceinline__ void epilogue_tile_swapped(const KArgs& a, const TileCoord& tc,
+__device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const TileCoord& tc,
                                                       uint32_t tmem_acc, int quarter, int lane) {
   const GemmDesc& d = a.d;
   const int per_frame = a.tiles_w * a.tiles_h;
@@ -399,7 +413,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const KArgs& a, const Tile
 // the kernel
 // ------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ KArgs k) {
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -415,8 +429,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&a.tmA);
-    tma_prefetch_desc(&a.tmB);
+    tma_prefetch_desc(&k.p[0].tmA);
+    tma_prefetch_desc(&k.p[0].tmB);
+    if (k.p[1].tiles > 0) {
+      tma_prefetch_desc(&k.p[1].tmA);
+      tma_prefetch_desc(&k.p[1].tmB);
+    }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -435,21 +453,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const GemmDesc& d = a.d;
   // split-K: the cluster = the splits of ONE tile (grid = tiles * splits, one pass);
   // otherwise a persistent loop over tiles
-  const bool split_mode = a.splits > 1;
+  const bool split_mode = k.splits > 1;
   const int split = split_mode ? static_cast<int>(cluster_ctarank()) : 0;
   const int tile0 =
-      split_mode ? static_cast<int>(blockIdx.x) / a.splits : static_cast<int>(blockIdx.x);
-  const int tile_step = split_mode ? a.total_tiles : static_cast<int>(gridDim.x);
+      split_mode ? static_cast<int>(blockIdx.x) / k.splits : static_cast<int>(blockIdx.x);
+  const int tile_step = split_mode ? k.total_tiles : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
+      for (int gtile = tile0; gtile < k.total_tiles; gtile += tile_step) {
+        int tile = gtile;
+        const Problem& a = problem_of(k, tile);
+        const GemmDesc& d = a.d;
         const TileCoord tc = decode_tile(a, tile, split);
         int ct = 0, h0 = 0, w0 = 0;
         if (d.a_mode == 1) {
@@ -502,12 +522,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = tile0; tile < a.total_tiles; tile += tile_step, ++it) {
+      for (int gtile = tile0; gtile < k.total_tiles; gtile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * BN;
+        int tile = gtile;
+        const Problem& a = problem_of(k, tile);
         const TileCoord tc = decode_tile(a, tile, split);
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -527,7 +549,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);
+        if (tc.kb0 < tc.kb1)
+          umma_commit(&tmem_full[as]);
+        else
+          mbar_arrive(&tmem_full[as]);  // empty K range (tail split): nothing was issued
       }
     }
   } else {
@@ -536,9 +561,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int row_in_tile = quarter * 32 + lane;
     if (!split_mode) {
       int it = 0;
-      for (int tile = tile0; tile < a.total_tiles; tile += tile_step, ++it) {
+      for (int gtile = tile0; gtile < k.total_tiles; gtile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        int tile = gtile;
+        const Problem& a = problem_of(k, tile);
         const TileCoord tc = decode_tile(a, tile, 0);
         mbar_wait(&tmem_full[as], aph);
         tc_fence_after();
@@ -556,11 +583,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       float4* part = reinterpret_cast<float4*>(smem);
+      int tile = tile0;
+      const Problem& a = problem_of(k, tile);
+      const bool empty = split * a.kb_per_split >= a.k_blocks;  // tail split without k-blocks
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t raw[32];
         tmem_ld_32x32(taddr + c * 32, raw);
         tmem_ld_wait();
+        if (empty) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = 0u;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           part[(c * 8 + i) * BM + row_in_tile] =
@@ -578,20 +612,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (warp >= 2) {
       constexpr int W = EpiW<MODE>::value;
       const int t = threadIdx.x - 64;      // 0..127
-      const int rows_per = BM / a.splits;  // rows of the tile this CTA finishes
+      const int rows_per = BM / k.splits;  // rows of the tile this CTA finishes
       const int row_in_tile = split * rows_per + (t % rows_per);
       const int group = t / rows_per;      // 0..splits-1: which column chunks
-      const TileCoord tc = decode_tile(a, tile0, split);
+      int tile = tile0;
+      const Problem& a = problem_of(k, tile);
+      const GemmDesc& d = a.d;
+      const TileCoord tc = decode_tile(a, tile, split);
       const RowCtx r = make_row(a, tc, row_in_tile);
       const uint32_t part0 = smem_u32(smem);
-      for (int c = group; c < BN / W; c += a.splits) {
+      for (int c = group; c < BN / W; c += k.splits) {
         const int n = tc.n_tile * BN + c * W;
         if (n >= d.N || !r.ok) continue;
         float v[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) v[i] = 0.f;
 #pragma unroll 1
-        for (int p = 0; p < a.splits; ++p) {  // fixed order: bit-reproducible sums
+        for (int p = 0; p < k.splits; ++p) {  // fixed order: bit-reproducible sums
           const uint32_t peer = map_to_cta(part0, static_cast<uint32_t>(p));
 #pragma unroll
           for (int i = 0; i < W / 4; ++i) {
@@ -677,86 +714,61 @@ int cluster_capacity(int s) {
 
 }  // namespace
 
-int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
-  KArgs ka;
-  ka.d = d;
-  ka.swap = 0;
+// geometry + tensor maps of one problem
+static int setup_problem(const GemmDesc& d, Problem& pr) {
+  pr.d = d;
+  pr.swap = 0;
   DV_REQUIRE(d.batch > 0 && d.N > 0, "gemm: empty problem (batch=%d N=%d)", d.batch, d.N);
-
   int K;
   if (d.a_mode == 1) {
     DV_REQUIRE(d.mode == EPI_CONV, "conv operand needs EPI_CONV (mode %d)", d.mode);
     DV_REQUIRE(d.cC % 64 == 0, "conv: Cin=%d must be a multiple of 64 (pad at pack time)", d.cC);
     DV_REQUIRE(d.cW % 16 == 0 && d.cH % 8 == 0, "conv: H=%d W=%d must be multiples of 8/16", d.cH,
                d.cW);
-    ka.c_blocks = d.cC / 64;
+    pr.c_blocks = d.cC / 64;
     K = d.kt * d.kh * d.kw * d.cC;
-    ka.swap = (d.N <= 128 && d.conv_store == CONV_PLAIN && d.w_batch_stride == 0) ? 1 : 0;
-    DV_REQUIRE(ka.swap || (d.N % 32 == 0 && d.out_C % 32 == 0),
+    pr.swap = (d.N <= 128 && d.conv_store == CONV_PLAIN && d.w_batch_stride == 0) ? 1 : 0;
+    DV_REQUIRE(pr.swap || (d.N % 32 == 0 && d.out_C % 32 == 0),
                "conv: Cout=%d (stored channels %d) must be <= 128 with a plain store or multiples of 32",
                d.N, d.out_C);
-    ka.tiles_w = d.cW / 16;
-    ka.tiles_h = ka.swap ? (d.cH + 15) / 16 : d.cH / 8;
-    ka.m_tiles = d.cT * ka.tiles_w * ka.tiles_h;
+    pr.tiles_w = d.cW / 16;
+    pr.tiles_h = pr.swap ? (d.cH + 15) / 16 : d.cH / 8;
+    pr.m_tiles = d.cT * pr.tiles_w * pr.tiles_h;
   } else {
     DV_REQUIRE(d.mode != EPI_CONV, "EPI_CONV needs the conv operand");
     DV_REQUIRE(d.K % 64 == 0, "gemm: K=%d must be a multiple of 64", d.K);
     DV_REQUIRE(d.M > 0, "gemm: M=%d", d.M);
     K = d.K;
-    ka.c_blocks = 1;
-    ka.tiles_w = ka.tiles_h = 1;
-    ka.m_tiles = (d.M + BM - 1) / BM;
+    pr.c_blocks = 1;
+    pr.tiles_w = pr.tiles_h = 1;
+    pr.m_tiles = (d.M + BM - 1) / BM;
   }
-  ka.k_blocks = K / BK;
+  pr.k_blocks = K / BK;
   DV_REQUIRE(d.mode == EPI_UNPATCH || d.mode == EPI_CONV || d.N % 32 == 0,
              "gemm: N=%d must be a multiple of 32 for epilogue mode %d", d.N, d.mode);
   DV_REQUIRE(d.mode != EPI_QKV || d.N % 64 == 0, "gemm: QKV epilogue needs N %% 64 == 0 (N=%d)",
              d.N);
-  ka.n_tiles = ka.swap ? 1 : (d.N + BN - 1) / BN;
-  const long long tiles_ll = static_cast<long long>(ka.m_tiles) * d.batch * ka.n_tiles;
-  DV_REQUIRE(tiles_ll < (1ll << 30), "gemm: too many tiles");
-  ka.total_tiles = static_cast<int>(tiles_ll);
+  pr.n_tiles = pr.swap ? 1 : (d.N + BN - 1) / BN;
+  const long long tiles_ll = static_cast<long long>(pr.m_tiles) * d.batch * pr.n_tiles;
+  DV_REQUIRE(tiles_ll < (1ll << 28), "gemm: too many tiles");
+  pr.tiles = static_cast<int>(tiles_ll);
+  pr.kb_per_split = pr.k_blocks;
 
-  // ---- split-K: a CTA needs ~570 cycles per k-block (4 MMAs at the 128-cycle floor) plus ~3000
-  // cycles of fixed latency (first TMA round trip, epilogue); with fewer tiles than SMs the K
-  // loop is cut over a cluster.  Usable SMs shrink a little with the cluster size (GPC packing).
-  int splits = 1;
-  if (!ka.swap && getenv("DV_GEMM_NOSPLIT") == nullptr) {
-    const int nsm = sm_count();
-    double best = 1e30;
-    for (int s = 1; s <= kMaxSplits; s *= 2) {
-      if (s > 1 && ka.k_blocks / s < 2) break;
-      const int usable = s == 1 ? nsm : cluster_capacity(s);
-      if (usable <= 0) break;
-      const long long ctas = tiles_ll * s;
-      const double waves = static_cast<double>((ctas + usable - 1) / usable);
-      const double kbs = static_cast<double>((ka.k_blocks + s - 1) / s);
-      const double t = waves * (kbs * 570.0 + 3000.0) + (s > 1 ? 2500.0 : 0.0);
-      if (t < best * 0.93) {  // a larger cluster has to pay for itself
-        best = t;
-        splits = s;
-      }
-    }
-  }
-  ka.kb_per_split = (ka.k_blocks + splits - 1) / splits;
-  ka.splits = splits;
-
-  // ---- tensor maps ------------------------------------------------------------
   if (d.a_mode == 1) {
     uint64_t dims[5] = {(uint64_t)d.cC, (uint64_t)d.cW, (uint64_t)d.cH, (uint64_t)d.cT,
                         (uint64_t)d.batch};
     uint64_t strides[4] = {(uint64_t)d.cC * 2, (uint64_t)d.cC * d.cW * 2,
                            (uint64_t)d.cC * d.cW * d.cH * 2,
                            (uint64_t)d.cC * d.cW * d.cH * d.cT * 2};
-    uint32_t box[5] = {64, 16, ka.swap ? 16u : 8u, 1, 1};
-    int rc = make_tensor_map_bf16(&ka.tmA, d.A, 5, dims, strides, box, 1);
+    uint32_t box[5] = {64, 16, pr.swap ? 16u : 8u, 1, 1};
+    int rc = make_tensor_map_bf16(&pr.tmA, d.A, 5, dims, strides, box, 1);
     if (rc) return rc;
   } else {
     uint64_t dims[3] = {(uint64_t)d.K, (uint64_t)d.M, (uint64_t)d.batch};
     uint64_t strides[2] = {(uint64_t)d.lda * 2, (uint64_t)d.a_batch_stride * 2};
     if (d.batch == 1) strides[1] = (uint64_t)d.lda * 2 * (uint64_t)d.M;
     uint32_t box[3] = {64, 128, 1};
-    int rc = make_tensor_map_bf16(&ka.tmA, d.A, 3, dims, strides, box, 1);
+    int rc = make_tensor_map_bf16(&pr.tmA, d.A, 3, dims, strides, box, 1);
     if (rc) return rc;
   }
   const uint64_t ldw_bytes = (uint64_t)(d.ldw > 0 ? d.ldw : K) * 2;
@@ -764,45 +776,126 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
     uint64_t dims[3] = {(uint64_t)K, (uint64_t)d.w_rows, (uint64_t)d.batch};
     uint64_t strides[2] = {ldw_bytes, (uint64_t)d.w_batch_stride * 2};
     uint32_t box[3] = {64, (uint32_t)BN, 1};
-    int rc = make_tensor_map_bf16(&ka.tmB, d.W, 3, dims, strides, box, 1);
+    int rc = make_tensor_map_bf16(&pr.tmB, d.W, 3, dims, strides, box, 1);
     if (rc) return rc;
   } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)d.w_rows};
     uint64_t strides[1] = {ldw_bytes};
-    uint32_t box[2] = {64, ka.swap ? 128u : (uint32_t)BN};
-    int rc = make_tensor_map_bf16(&ka.tmB, d.W, 2, dims, strides, box, 1);
+    uint32_t box[2] = {64, pr.swap ? 128u : (uint32_t)BN};
+    int rc = make_tensor_map_bf16(&pr.tmB, d.W, 2, dims, strides, box, 1);
     if (rc) return rc;
   }
+  return 0;
+}
 
-  const double rows =
-      static_cast<double>(d.a_mode == 1 ? (double)d.cT * d.cH * d.cW : d.M) * d.batch;
+// ---- split-K choice: a CTA needs ~570 cycles per k-block (4 MMAs at the 128-cycle floor) plus
+// ~3000 cycles of fixed latency (first TMA round trip, epilogue); with fewer tiles than SMs the
+// K loop is cut over a cluster.  Returns the modelled cycles, the split factor in *splits_out.
+static double plan_splits(long long tiles, int k_blocks, bool allow_split, int* splits_out) {
+  const int nsm = sm_count();
+  double best = 1e30;
+  int splits = 1;
+  for (int s = 1; s <= kMaxSplits; s *= 2) {
+    if (s > 1 && (!allow_split || k_blocks / s < 2)) break;
+    const int usable = s == 1 ? nsm : cluster_capacity(s);
+    if (usable <= 0) break;
+    const long long ctas = tiles * s;
+    const double waves = static_cast<double>((ctas + usable - 1) / usable);
+    const double kbs = static_cast<double>((k_blocks + s - 1) / s);
+    const double t = waves * (kbs * 570.0 + 3000.0) + (s > 1 ? 2500.0 : 0.0);
+    if (t < best * 0.93) {  // a larger cluster has to pay for itself
+      best = t;
+      splits = s;
+    }
+  }
+  *splits_out = splits;
+  return best;
+}
+
+static double problem_flops(const GemmDesc& d, int K) {
+  const double rows = static_cast<double>(d.a_mode == 1 ? (double)d.cT * d.cH * d.cW : d.M) * d.batch;
+  return 2.0 * rows * d.N * K;
+}
+
+static int launch_args(KArgs& ka, int mode, cudaStream_t stream) {
+  switch (mode) {
+    case EPI_BF16: return launch_mode<EPI_BF16>(ka, stream);
+    case EPI_GELU: return launch_mode<EPI_GELU>(ka, stream);
+    case EPI_RESID_GATE: return launch_mode<EPI_RESID_GATE>(ka, stream);
+    case EPI_F32_ADD: return launch_mode<EPI_F32_ADD>(ka, stream);
+    case EPI_QKV: return launch_mode<EPI_QKV>(ka, stream);
+    case EPI_UNPATCH: return launch_mode<EPI_UNPATCH>(ka, stream);
+    case EPI_CONV: return launch_mode<EPI_CONV>(ka, stream);
+    case EPI_BF16_ROWBIAS: return launch_mode<EPI_BF16_ROWBIAS>(ka, stream);
+    default:
+      set_error("gemm: unknown epilogue mode %d", mode);
+      return -1;
+  }
+}
+
+int launch_gemm(const GemmDesc& d, cudaStream_t stream) { return launch_gemm_pair(d, nullptr, stream); }
+
+int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream) {
+  static const bool no_split = getenv("DV_GEMM_NOSPLIT") != nullptr;
+  static const bool no_group = getenv("DV_GEMM_NOGROUP") != nullptr;
+  KArgs ka;
+  int rc = setup_problem(d0, ka.p[0]);
+  if (rc) return rc;
+  ka.p[1].tiles = 0;
+  const bool split_ok0 = !ka.p[0].swap && !no_split;
+  if (d1 != nullptr) {
+    DV_REQUIRE(d1->mode == d0.mode, "gemm pair: epilogue modes differ (%d vs %d)", d0.mode, d1->mode);
+    DV_REQUIRE(d0.a_mode == 0 && d1->a_mode == 0, "gemm pair: dense problems only");
+    rc = setup_problem(*d1, ka.p[1]);
+    if (rc) return rc;
+    // one launch for both (the small problem fills the tail of the big one) unless wave
+    // quantisation makes two launches cheaper
+    int s_joint, s0, s1;
+    const int kb_max = ka.p[0].k_blocks > ka.p[1].k_blocks ? ka.p[0].k_blocks : ka.p[1].k_blocks;
+    const int kb_min = ka.p[0].k_blocks < ka.p[1].k_blocks ? ka.p[0].k_blocks : ka.p[1].k_blocks;
+    const double t_joint = plan_splits(static_cast<long long>(ka.p[0].tiles) + ka.p[1].tiles, kb_max,
+                                       !no_split && kb_min >= 2, &s_joint);
+    const double t_sep = plan_splits(ka.p[0].tiles, ka.p[0].k_blocks, !no_split, &s0) +
+                         plan_splits(ka.p[1].tiles, ka.p[1].k_blocks, !no_split, &s1) + 6000.0;
+    if (no_group || t_sep < t_joint) {
+      rc = launch_gemm_pair(d0, nullptr, stream);
+      if (rc) return rc;
+      return launch_gemm_pair(*d1, nullptr, stream);
+    }
+    while (s_joint > 1 && kb_min / s_joint < 1) s_joint /= 2;
+    ka.splits = s_joint;
+  } else {
+    int s;
+    plan_splits(ka.p[0].tiles, ka.p[0].k_blocks, split_ok0, &s);
+    ka.splits = s;
+  }
+  for (int i = 0; i < 2; ++i)
+    if (ka.p[i].tiles > 0) ka.p[i].kb_per_split = (ka.p[i].k_blocks + ka.splits - 1) / ka.splits;
+  ka.total_tiles = ka.p[0].tiles + ka.p[1].tiles;
+
+  const int K0 = ka.p[0].k_blocks * BK;
+  double flops = problem_flops(d0, K0);
+  double rows = static_cast<double>(d0.a_mode == 1 ? (double)d0.cT * d0.cH * d0.cW : d0.M) * d0.batch;
+  double bytes = 2.0 * (rows * K0 / (d0.a_mode == 1 ? d0.kt * d0.kh * d0.kw : 1) + (double)d0.N * K0 + rows * d0.N);
+  if (d1 != nullptr) {
+    const int K1 = ka.p[1].k_blocks * BK;
+    flops += problem_flops(*d1, K1);
+    bytes += 2.0 * ((double)d1->M * d1->batch * (K1 + d1->N) + (double)d1->N * K1);
+  }
   char tag[56] = "";
   if (prof_on()) {
-    if (d.a_mode == 1)
-      snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k%d%s e%d", d.cT, d.cH, d.cW, d.cC, d.N,
-               d.kt, ka.swap ? " sw" : "", d.conv_store);
+    if (d0.a_mode == 1)
+      snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k%d%s s%d e%d", d0.cT, d0.cH, d0.cW, d0.cC,
+               d0.N, d0.kt, ka.p[0].swap ? " sw" : "", ka.splits, d0.conv_store);
+    else if (d1 != nullptr)
+      snprintf(tag, sizeof(tag), "gemm B%d M%d+%d N%d K%d s%d e%d", d0.batch, d0.M, d1->M, d0.N, K0,
+               ka.splits, d0.mode);
     else
-      snprintf(tag, sizeof(tag), "gemm B%d M%d N%d K%d s%d e%d", d.batch, d.M, d.N, K, splits,
-               d.mode);
+      snprintf(tag, sizeof(tag), "gemm B%d M%d N%d K%d s%d e%d", d0.batch, d0.M, d0.N, K0, ka.splits,
+               d0.mode);
   }
-  const int pid = prof_begin(
-      d.a_mode == 1 ? PROF_CONV : PROF_GEMM, 2.0 * rows * d.N * K,
-      2.0 * (rows * K / (d.a_mode == 1 ? d.kt * d.kh * d.kw : 1) + (double)d.N * K + rows * d.N),
-      stream, tag);
-  int rc;
-  switch (d.mode) {
-    case EPI_BF16: rc = launch_mode<EPI_BF16>(ka, stream); break;
-    case EPI_GELU: rc = launch_mode<EPI_GELU>(ka, stream); break;
-    case EPI_RESID_GATE: rc = launch_mode<EPI_RESID_GATE>(ka, stream); break;
-    case EPI_F32_ADD: rc = launch_mode<EPI_F32_ADD>(ka, stream); break;
-    case EPI_QKV: rc = launch_mode<EPI_QKV>(ka, stream); break;
-    case EPI_UNPATCH: rc = launch_mode<EPI_UNPATCH>(ka, stream); break;
-    case EPI_CONV: rc = launch_mode<EPI_CONV>(ka, stream); break;
-    case EPI_BF16_ROWBIAS: rc = launch_mode<EPI_BF16_ROWBIAS>(ka, stream); break;
-    default:
-      set_error("gemm: unknown epilogue mode %d", d.mode);
-      rc = -1;
-  }
+  const int pid = prof_begin(d0.a_mode == 1 ? PROF_CONV : PROF_GEMM, flops, bytes, stream, tag);
+  rc = launch_args(ka, d0.mode, stream);
   prof_end(pid, stream);
   return rc;
 }

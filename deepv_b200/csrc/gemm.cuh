@@ -76,5 +76,8 @@ struct GemmDesc {
 
 // Enqueue on `stream`.  Returns 0 or a negative error (see dv_last_error()).
 int launch_gemm(const GemmDesc& d, cudaStream_t stream);
+// Two dense problems of the same epilogue mode in ONE launch (video + context stream of a joint
+// block); d1 may be null.  Falls back to two launches when wave quantisation makes that cheaper.
+int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream);
 
 }  // namespace dv

@@ -13,6 +13,18 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
 
 // ---- MMDiT elementwise (elementwise.cu) -----------------------------------------------
 // out_bf16[b][l][:] = LN(x[b][l][:]) * (1 + scale[b][:]) + shift[b][:]   (eps inside sqrt)
+struct LnRows {
+  const float* x;        // [B][L][D] fp32, batch stride x_bs
+  long long x_bs;
+  __nv_bfloat16* out;    // [B][L][D] bf16, batch stride out_bs
+  long long out_bs;
+  const float* shift;    // + b * mod_bs
+  const float* scale;
+  int L;
+};
+// two row sets (video + context stream) in one launch; r1 may be null
+int launch_ln_modulate2(const LnRows& r0, const LnRows* r1, int mod_bs, int B, int D, float eps,
+                        cudaStream_t stream);
 int launch_ln_modulate(const float* x, long long x_batch_stride, __nv_bfloat16* out,
                        long long out_batch_stride, const float* shift, const float* scale,
                        int mod_batch_stride, int B, int L, int D, float eps, cudaStream_t stream);

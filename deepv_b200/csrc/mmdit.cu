@@ -52,7 +52,7 @@ struct dv_mmdit_plan {
   float *pos_x = nullptr, *pos_h = nullptr;
   float *x = nullptr, *c = nullptr, *key_bias = nullptr;
   float *tfeat = nullptr, *g1 = nullptr, *g3 = nullptr, *temb = nullptr, *mod = nullptr;
-  __nv_bfloat16 *xn = nullptr, *cn = nullptr, *qkv = nullptr, *attn = nullptr, *ffh = nullptr;
+  __nv_bfloat16 *xn = nullptr, *cn = nullptr, *qkv = nullptr, *attn = nullptr, *ffh = nullptr, *ffh_c = nullptr;
   __nv_bfloat16 *patch_a = nullptr, *hist_a = nullptr, *enc_bf = nullptr, *xo = nullptr;
 };
 
@@ -256,7 +256,8 @@ extern "C" int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const i
   DV_A(p->cn, static_cast<long long>(B) * Lc * D);
   DV_A(p->qkv, static_cast<long long>(B) * L * 3 * D);
   DV_A(p->attn, static_cast<long long>(B) * L * D);
-  DV_A(p->ffh, static_cast<long long>(B) * (Lv > Lc ? Lv : Lc) * 4 * D);
+  DV_A(p->ffh, static_cast<long long>(B) * Lv * 4 * D);
+  DV_A(p->ffh_c, static_cast<long long>(B) * Lc * 4 * D);
   DV_A(p->patch_a, static_cast<long long>(B) * Lv * Kp);
   DV_A(p->hist_a, static_cast<long long>(B) * (p->hist_tokens ? p->hist_tokens : 1) * Kp);
   DV_A(p->enc_bf, static_cast<long long>(B) * text_len * m->cfg.joint_dim);
@@ -412,86 +413,93 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
   const long long xs = static_cast<long long>(Lv) * D, cs = static_cast<long long>(Lc) * D;
   const long long js = static_cast<long long>(L) * D;  // joint (attention output) batch stride
   // ---- transformer blocks ------------------------------------------------------------------
+  // Every step of a joint block is ONE launch covering the video and the context stream
+  // (the reference runs them as separate modules, mmdit.py:385-433).
   for (int i = 0; i < NL; ++i) {
     const bool last = (i == NL - 1);
     const float* mx = p->mod + static_cast<long long>(i) * 12 * D;  // video modulation, 6 chunks
     const float* mc = mx + 6 * D;                                   // context modulation
-    // norm1 / norm1_context: chunk order shift, scale, gate (msa), shift, scale, gate (mlp)
-    DV_RUN(launch_ln_modulate(p->x, xs, p->xn, xs, mx + 0 * D, mx + 1 * D, MR, B, Lv, D, 1e-6f, st));
-    if (!last) {
-      DV_RUN(launch_ln_modulate(p->c, cs, p->cn, cs, mc + 0 * D, mc + 1 * D, MR, B, Lc, D, 1e-6f, st));
-    } else {
-      // AdaLayerNormContinuous: chunk order scale, shift (mmdit.py:513)
-      DV_RUN(launch_ln_modulate(p->c, cs, p->cn, cs, mc + 1 * D, mc + 0 * D, MR, B, Lc, D, 1e-6f, st));
+    // norm1 / norm1_context: chunk order shift, scale, gate (msa), shift, scale, gate (mlp);
+    // last block: AdaLayerNormContinuous on the context, chunk order scale, shift (mmdit.py:513)
+    {
+      LnRows rx = {p->x, xs, p->xn, xs, mx + 0 * D, mx + 1 * D, Lv};
+      LnRows rcx = {p->c, cs, p->cn, cs, last ? mc + 1 * D : mc + 0 * D, last ? mc + 0 * D : mc + 1 * D, Lc};
+      DV_RUN(launch_ln_modulate2(rx, &rcx, MR, B, D, 1e-6f, st));
     }
     // fused q|k|v projection + per-head RMSNorm + temporal RoPE, written into the joint layout
-    for (int s = 0; s < 2; ++s) {
-      const bool vid = (s == 0);
-      GemmDesc d = dense_desc(vid ? p->xn : p->cn, vid ? xs : cs, D,
-                              vid ? m->p_w_qkv_x[i] : m->p_w_qkv_c[i], 3 * D,
-                              vid ? m->p_b_qkv_x[i] : m->p_b_qkv_c[i], B, vid ? Lv : Lc, 3 * D, D);
-      d.mode = EPI_QKV;
-      d.out = p->qkv;
-      d.out_batch_stride = static_cast<long long>(L) * 3 * D;
-      d.ldo = 3 * D;
-      d.out_row_offset = vid ? Lc : 0;
-      d.qk_norm_w = vid ? m->p_qk_norm_x[i] : m->p_qk_norm_c[i];
-      d.rope_cs = m->rope_cs;
-      d.frame_id = vid ? p->frame_x : p->frame_c;
-      d.heads_dim = D;
-      DV_RUN(launch_gemm(d, st));
+    {
+      GemmDesc dq[2];
+      for (int s = 0; s < 2; ++s) {
+        const bool vid = (s == 0);
+        GemmDesc d = dense_desc(vid ? p->xn : p->cn, vid ? xs : cs, D,
+                                vid ? m->p_w_qkv_x[i] : m->p_w_qkv_c[i], 3 * D,
+                                vid ? m->p_b_qkv_x[i] : m->p_b_qkv_c[i], B, vid ? Lv : Lc, 3 * D, D);
+        d.mode = EPI_QKV;
+        d.out = p->qkv;
+        d.out_batch_stride = static_cast<long long>(L) * 3 * D;
+        d.ldo = 3 * D;
+        d.out_row_offset = vid ? Lc : 0;
+        d.qk_norm_w = vid ? m->p_qk_norm_x[i] : m->p_qk_norm_c[i];
+        d.rope_cs = m->rope_cs;
+        d.frame_id = vid ? p->frame_x : p->frame_c;
+        d.heads_dim = D;
+        dq[s] = d;
+      }
+      DV_RUN(launch_gemm_pair(dq[0], &dq[1], st));
     }
     DV_RUN(launch_attention(p->qkv, p->attn, p->kv_end, p->key_bias, p->tile_dead, B, L, p->Lpad,
                             m->cfg.num_heads, st, p->attn_flops_layer));
-    // x += gate_msa * to_out(attn)
+    // x += gate_msa * to_out(attn);  c += c_gate_msa * to_add_out(attn_c)  (not in the last block)
     {
-      GemmDesc d = dense_desc(p->attn + static_cast<long long>(Lc) * D, js, D, m->p_w_out_x[i], D,
-                              m->p_b_out_x[i], B, Lv, D, D);
-      d.mode = EPI_RESID_GATE;
-      d.out = p->x;
-      d.out_batch_stride = xs;
-      d.ldo = D;
-      d.gate = mx + 2 * D;
-      d.gate_batch_stride = MR;
-      DV_RUN(launch_gemm(d, st));
+      GemmDesc dx = dense_desc(p->attn + static_cast<long long>(Lc) * D, js, D, m->p_w_out_x[i], D,
+                               m->p_b_out_x[i], B, Lv, D, D);
+      dx.mode = EPI_RESID_GATE;
+      dx.out = p->x;
+      dx.out_batch_stride = xs;
+      dx.ldo = D;
+      dx.gate = mx + 2 * D;
+      dx.gate_batch_stride = MR;
+      GemmDesc dc = dense_desc(p->attn, js, D, m->p_w_out_c[i], D, m->p_b_out_c[i], B, Lc, D, D);
+      dc.mode = EPI_RESID_GATE;
+      dc.out = p->c;
+      dc.out_batch_stride = cs;
+      dc.ldo = D;
+      dc.gate = mc + 2 * D;
+      dc.gate_batch_stride = MR;
+      DV_RUN(launch_gemm_pair(dx, last ? nullptr : &dc, st));
     }
-    if (!last) {
-      GemmDesc d = dense_desc(p->attn, js, D, m->p_w_out_c[i], D, m->p_b_out_c[i], B, Lc, D, D);
-      d.mode = EPI_RESID_GATE;
-      d.out = p->c;
-      d.out_batch_stride = cs;
-      d.ldo = D;
-      d.gate = mc + 2 * D;
-      d.gate_batch_stride = MR;
-      DV_RUN(launch_gemm(d, st));
-    }
-    // feed-forward, both streams
-    for (int s = 0; s < 2; ++s) {
-      const bool vid = (s == 0);
-      if (!vid && last) break;
-      const float* mm = vid ? mx : mc;
-      float* res = vid ? p->x : p->c;
-      __nv_bfloat16* nrm = vid ? p->xn : p->cn;
-      const long long rs = vid ? xs : cs;
-      const int Ls = vid ? Lv : Lc;
-      DV_RUN(launch_ln_modulate(res, rs, nrm, rs, mm + 3 * D, mm + 4 * D, MR, B, Ls, D, 1e-6f, st));
-      GemmDesc d1 = dense_desc(nrm, rs, D, vid ? m->p_w_ff1_x[i] : m->p_w_ff1_c[i], 4 * D,
-                               vid ? m->p_b_ff1_x[i] : m->p_b_ff1_c[i], B, Ls, 4 * D, D);
-      d1.mode = EPI_GELU;
-      d1.out = p->ffh;
-      d1.out_batch_stride = static_cast<long long>(Ls) * 4 * D;
-      d1.ldo = 4 * D;
-      DV_RUN(launch_gemm(d1, st));
-      GemmDesc d2 = dense_desc(p->ffh, static_cast<long long>(Ls) * 4 * D, 4 * D,
-                               vid ? m->p_w_ff2_x[i] : m->p_w_ff2_c[i], D,
-                               vid ? m->p_b_ff2_x[i] : m->p_b_ff2_c[i], B, Ls, D, 4 * D);
-      d2.mode = EPI_RESID_GATE;
-      d2.out = res;
-      d2.out_batch_stride = rs;
-      d2.ldo = D;
-      d2.gate = mm + 5 * D;
-      d2.gate_batch_stride = MR;
-      DV_RUN(launch_gemm(d2, st));
+    // feed-forward, both streams: LN + modulate, W1 + GELU, W2 + gated residual
+    {
+      LnRows rx = {p->x, xs, p->xn, xs, mx + 3 * D, mx + 4 * D, Lv};
+      LnRows rcx = {p->c, cs, p->cn, cs, mc + 3 * D, mc + 4 * D, Lc};
+      DV_RUN(launch_ln_modulate2(rx, last ? nullptr : &rcx, MR, B, D, 1e-6f, st));
+      GemmDesc d1[2], d2[2];
+      for (int s = 0; s < 2; ++s) {
+        const bool vid = (s == 0);
+        const float* mm = vid ? mx : mc;
+        float* res = vid ? p->x : p->c;
+        __nv_bfloat16* nrm = vid ? p->xn : p->cn;
+        __nv_bfloat16* hid = vid ? p->ffh : p->ffh_c;
+        const long long rs = vid ? xs : cs;
+        const int Ls = vid ? Lv : Lc;
+        d1[s] = dense_desc(nrm, rs, D, vid ? m->p_w_ff1_x[i] : m->p_w_ff1_c[i], 4 * D,
+                           vid ? m->p_b_ff1_x[i] : m->p_b_ff1_c[i], B, Ls, 4 * D, D);
+        d1[s].mode = EPI_GELU;
+        d1[s].out = hid;
+        d1[s].out_batch_stride = static_cast<long long>(Ls) * 4 * D;
+        d1[s].ldo = 4 * D;
+        d2[s] = dense_desc(hid, static_cast<long long>(Ls) * 4 * D, 4 * D,
+                           vid ? m->p_w_ff2_x[i] : m->p_w_ff2_c[i], D,
+                           vid ? m->p_b_ff2_x[i] : m->p_b_ff2_c[i], B, Ls, D, 4 * D);
+        d2[s].mode = EPI_RESID_GATE;
+        d2[s].out = res;
+        d2[s].out_batch_stride = rs;
+        d2[s].ldo = D;
+        d2[s].gate = mm + 5 * D;
+        d2[s].gate_batch_stride = MR;
+      }
+      DV_RUN(launch_gemm_pair(d1[0], last ? nullptr : &d1[1], st));
+      DV_RUN(launch_gemm_pair(d2[0], last ? nullptr : &d2[1], st));
     }
   }
 
