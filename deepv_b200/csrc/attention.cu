@@ -6,18 +6,24 @@
 // "same sample AND frame(q) >= frame(k)" collapses to  k < kv_end[q]  AND  key_bias[b][k] == 0
 // (dead keys = padded text / masked-history tokens, sample id 0 in the reference).
 //
-// One CTA = 256 queries (two 128-row tiles) x one head x one batch row; 320 threads:
-//   warp 0      TMA producer: Q0,Q1 once, then (K_j, V_j) into a 3-stage ring
-//   warp 1      MMA issuer: S_w = Q_w K_j^T (M128 N128 K64) into TMEM, O_w += P_w V_j (M128 N64
-//               K128, V as the MN-major B operand straight from the token-major qkv rows)
-//   warps 2-5   softmax group 0 (query tile 0), one row per thread
-//   warps 6-9   softmax group 1 (query tile 1)
-// The two groups ping-pong: while group 0 exponentiates S_0(j), the tensor pipe runs
-// O_1 += P_1 V_(j-1) and S_1(j).  O lives in TMEM for the whole KV sweep; the running max is
-// only refreshed (and O rescaled in TMEM) when it grows by more than 2^8, so the rescale is
-// rare after the first tiles.  Masking is applied only on tiles that need it (frame boundary
-// or dead keys).
+// One CTA = 128 queries x one head x one batch row, 192 threads, TWO CTAs per SM (256 TMEM columns
+// and ~83 KB of shared memory each) so that one CTA's softmax hides the other's MMAs:
+//   warp 0      TMA producer: Q once, then (K_j, V_j) into a 2-stage ring
+//   warp 1      MMA issuer.  Every MMA takes its A operand FROM TENSOR MEMORY: measured on B200 an
+//               M128 MMA with A in shared memory costs >= 128 cycles whatever N is (the 128-row A
+//               read), which would hold S = Q K^T (N = 128) to half rate and P V (N = 64) to a
+//               quarter; with A in TMEM they run at their math rate.
+//                 S  = Q K_j^T            (M128 N128 K64)   A = Q (bf16, parked in TMEM once)
+//                 O += P V_j              (M128 N64 K128)   A = P (bf16, written over S by the
+//                                                               softmax warps), V MN-major
+//                 l += P 1                (M128 N16 K128)   the softmax row sums come out of the
+//                                                               tensor pipe too (B = a tile of ones)
+//   warps 2-5   softmax, one query row per thread: S from TMEM, running max with a lazy rescale
+//               (O and l are rescaled in TMEM only when the max grows by more than 2^8), P back
+//               into TMEM.  Masking runs only on tiles that hold a frame boundary or dead keys.
+// Query tiles are issued heaviest-first (late frames see the most keys).
 #include <cstdio>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -25,15 +31,24 @@
 namespace dv {
 namespace {
 
-constexpr int kTile = 128;             // query rows per group, keys per inner tile
+constexpr int kTile = 128;             // query rows per CTA, keys per inner tile
 constexpr int kD = 64;                 // head dim
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
-constexpr int kKvStages = 3;
-constexpr int kAttnThreads = 320;
-constexpr uint32_t kTmemCols = 512;    // S0 | S1 (128 each) | O0 | O1 (64 each)
-constexpr int kSmemBytes = 2 * kTileBytes /*Q0,Q1*/ + kKvStages * 2 * kTileBytes /*K,V*/ +
-                           2 * 2 * kTileBytes /*P0,P1: two 64-key k-blocks each*/ + 256 + 1024;
+constexpr int kKvStages = 2;
+constexpr int kAttnThreads = 192;
+constexpr int kOnesBytes = 2048;       // 16 rows x 128 B of bf16 ones (B operand of the row-sum MMA)
+constexpr uint32_t kTmemCols = 256;
+// TMEM column map
+constexpr uint32_t kColS = 0;     // S fp32 [128]; P bf16x2 aliases [0, 64)
+constexpr uint32_t kColO = 128;   // O fp32 [64]
+constexpr uint32_t kColL = 192;   // row sums fp32 [16] (all columns equal)
+constexpr uint32_t kColQ = 208;   // Q bf16x2 [32]
+constexpr int kSmemBytes = kTileBytes /*Q*/ + kKvStages * 2 * kTileBytes /*K,V*/ + kOnesBytes + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;  // log2 domain
+#ifndef DV_ATTN_POLY
+#define DV_ATTN_POLY 0
+#endif
+constexpr int kPolyPer8 = DV_ATTN_POLY;    // exponentials per 8 computed on the FMA pipe
 
 struct AttnArgs {
   alignas(64) CUtensorMap tmQKV;  // (3*H*64, L, B) bf16, box {64, 128, 1}
@@ -45,9 +60,32 @@ struct AttnArgs {
   float scale_log2;               // head_dim^-0.5 * log2(e)
 };
 
+// 2^x on the FMA pipe: round-to-nearest split x = n + f, degree-3 minimax of 2^f on [-0.5, 0.5]
+// (relative error 2e-4, below the bf16 rounding of P), exponent added as integer bits.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float magic = 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float xr = x + magic;
+  const float f = x - (xr - magic);
+  float p = fmaf(f, 0.053027521818876266f, 0.24221394956111908f);
+  p = fmaf(p, f, 0.6935725808143616f);
+  p = fmaf(p, f, 0.9999590516090393f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+        "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+        "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -67,58 +105,63 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// one 32-bit column of this thread's lane
+__device__ __forceinline__ uint32_t tmem_ld_1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_st_1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_constant__ AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;                                  // [2][16 KB]
-  uint8_t* sKV = sQ + 2 * kTileBytes;                  // [stage][K | V]
-  uint8_t* sP = sKV + kKvStages * 2 * kTileBytes;      // [group][kblock 0 | kblock 1]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
-  uint64_t* q_full = bars;              // 1
-  uint64_t* kv_full = bars + 1;         // [3]
-  uint64_t* kv_empty = bars + 4;        // [3]
-  uint64_t* s_full = bars + 7;          // [2]
-  uint64_t* p_full = bars + 9;          // [2]
-  uint64_t* o_done = bars + 11;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint8_t* sQ = smem;                                  // [16 KB]
+  uint8_t* sKV = sQ + kTileBytes;                      // [stage][K | V]
+  uint8_t* sOnes = sKV + kKvStages * 2 * kTileBytes;   // 2 KB of bf16 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes);
+  uint64_t* q_full = bars;                       // TMA: Q landed in smem
+  uint64_t* q_ready = bars + 1;                  // softmax warps: Q parked in TMEM (128 arrivals)
+  uint64_t* kv_full = bars + 2;                  // [kKvStages]
+  uint64_t* kv_empty = kv_full + kKvStages;      // [kKvStages]
+  uint64_t* s_full = kv_empty + kKvStages;       // S_j ready (and P_{j-1} V consumed)
+  uint64_t* p_full = s_full + 1;                 // P_j in TMEM (128 arrivals)
+  uint64_t* o_done = p_full + 1;                 // last P V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * kTile;
+  // heaviest query tiles first: later frames see more keys
+  const int qt = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
+  const int q0 = qt * kTile;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
 
-  // keys needed by each query tile (kv_end is non-decreasing in q)
-  int n_kv_w[2];
-#pragma unroll
-  for (int w = 0; w < 2; ++w) {
-    const int first = q0 + w * kTile;
-    if (first >= a.L) {
-      n_kv_w[w] = 0;
-    } else {
-      const int last = min(first + kTile, a.L) - 1;
-      n_kv_w[w] = (__ldg(a.kv_end + last) + kTile - 1) / kTile;
-    }
-  }
-  const int n_kv = max(n_kv_w[0], n_kv_w[1]);
+  // keys needed by this query tile (kv_end is non-decreasing in q)
+  const int last_q = min(q0 + kTile, a.L) - 1;
+  const int n_kv = (__ldg(a.kv_end + last_q) + kTile - 1) / kTile;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmQKV);
     mbar_init(q_full, 1);
+    mbar_init(q_ready, 128);
     for (int i = 0; i < kKvStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int w = 0; w < 2; ++w) {
-      mbar_init(&s_full[w], 1);
-      mbar_init(&p_full[w], 128);
-      mbar_init(&o_done[w], 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  // the tile of ones read by the row-sum MMA (generic-proxy writes -> async proxy)
+  for (int i = threadIdx.x; i < kOnesBytes / 4; i += kAttnThreads)
+    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,9 +171,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * kTileBytes);
+      mbar_expect_tx(q_full, kTileBytes);
       tma_load_3d(&a.tmQKV, q_full, sQ, head * kD, q0, b);
-      tma_load_3d(&a.tmQKV, q_full, sQ + kTileBytes, head * kD, q0 + kTile, b);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % kKvStages;
         const uint32_t ph = (j / kKvStages) & 1;
@@ -144,81 +186,90 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0 && n_kv > 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
-      auto issue_s = [&](int w, int j) {
-        const uint32_t aQ = smem_u32(sQ + w * kTileBytes);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (TMEM) x K (K-major)
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // P (TMEM) x V (MN-major)
+      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 0);    // P (TMEM) x ones (K-major)
+      const uint32_t tS = tmem_base + kColS, tO = tmem_base + kColO, tL = tmem_base + kColL;
+      const uint32_t tQ = tmem_base + kColQ;
+      const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
+      auto issue_s = [&](int j) {
         const uint32_t aK = smem_u32(sKV + (j % kKvStages) * 2 * kTileBytes);
-        const uint64_t dq = umma_desc_sw128(aQ, 16, 1024);
         const uint64_t dk = umma_desc_sw128(aK, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_bf16_ss(tmem_base + w * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[w]);
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ts(tS, tQ + k * 8, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
       };
-      auto issue_pv = [&](int w, int j) {
-        const uint32_t aP = smem_u32(sP + w * 2 * kTileBytes);
+      mbar_wait(q_ready, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(p_full, j & 1);  // P_j in TMEM, S_j drained, O / l rescaled
+        tc_fence_after();
         const uint32_t aV = smem_u32(sKV + (j % kKvStages) * 2 * kTileBytes) + kTileBytes;
 #pragma unroll
         for (int k = 0; k < kTile / 16; ++k) {
-          // A = P: k-block (k / 4) of 16 KB, +32 B per K=16 slice inside the swizzle row;
+          // A = P in TMEM: 16 keys = 8 packed columns per K=16 slice;
           // B = V, MN-major: 16 kv rows (two 8-row groups, SBO = 1024 B) per K=16 slice
-          const uint64_t dp = umma_desc_sw128(aP + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024);
           const uint64_t dv = umma_desc_sw128(aV + k * 2048, 1024, 1024);
-          umma_bf16_ss(tmem_base + 256 + w * 64, dp, dv, idesc_pv, (j | k) != 0);
-        }
-      };
-      mbar_wait(q_full, 0);
-      int kv_waited = -1;  // highest KV tile whose kv_full has been observed
-      auto need_kv = [&](int j) {
-        if (j > kv_waited) {
-          mbar_wait(&kv_full[j % kKvStages], (j / kKvStages) & 1);
-          kv_waited = j;
-        }
-      };
-      need_kv(0);
-      tc_fence_after();
-      for (int w = 0; w < 2; ++w)
-        if (n_kv_w[w] > 0) issue_s(w, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        for (int w = 0; w < 2; ++w) {
-          if (j >= n_kv_w[w]) continue;
-          mbar_wait(&p_full[w], j & 1);  // P_w(j) in smem, S_w(j) drained, O_w rescaled
-          tc_fence_after();
-          issue_pv(w, j);
-          if (j + 1 < n_kv_w[w]) {
-            need_kv(j + 1);
-            tc_fence_after();
-            issue_s(w, j + 1);
-          } else {
-            umma_commit(&o_done[w]);
-          }
+          umma_bf16_ts(tO, tS + k * 8, dv, idesc_pv, (j | k) != 0);
+          umma_bf16_ts(tL, tS + k * 8, d_ones, idesc_l, (j | k) != 0);
         }
         umma_commit(&kv_empty[j % kKvStages]);
+        if (j + 1 < n_kv) {
+          mbar_wait(&kv_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
+          tc_fence_after();
+          issue_s(j + 1);  // in order behind P_j V: S may overwrite P
+        } else {
+          umma_commit(o_done);
+        }
       }
     }
   } else {
-    // ================================ softmax groups ==============================
-    const int w = (warp - 2) >> 2;       // group / query tile
+    // ================================ softmax =====================================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;   // row inside the tile == TMEM lane
-    const int qi = q0 + w * kTile + r;
+    const int qi = q0 + r;
     const bool row_ok = qi < a.L;
-    const int my_n_kv = n_kv_w[w];
-    if (my_n_kv > 0) {
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + kColS + lane_addr;
+    const uint32_t tO = tmem_base + kColO + lane_addr;
+    const uint32_t tL = tmem_base + kColL + lane_addr;
+    if (n_kv > 0) {
+      // park this row of Q (128 B, 128B-swizzled by TMA) in TMEM as the A operand of S = Q K^T
+      mbar_wait(q_full, 0);
+      {
+        uint32_t qr[32];
+        const uint8_t* row = sQ + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 t = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+          qr[4 * c + 0] = t.x;
+          qr[4 * c + 1] = t.y;
+          qr[4 * c + 2] = t.z;
+          qr[4 * c + 3] = t.w;
+        }
+        tmem_st_32x32(tmem_base + kColQ + lane_addr, qr);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(q_ready);
+      }
       const int kv_end = row_ok ? __ldg(a.kv_end + qi) : 0;
-      const int kv_end_min = __ldg(a.kv_end + q0 + w * kTile);  // first row of the tile
+      const int kv_end_min = __ldg(a.kv_end + q0);  // first row of the tile
       const float* kb = a.key_bias + static_cast<long long>(b) * a.Lpad;
-      const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t tS = tmem_base + w * 128 + lane_addr;
-      const uint32_t tO = tmem_base + 256 + w * 64 + lane_addr;
-      uint8_t* prow = sP + w * 2 * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;
-      const int sw = r & 7;
-      float m_ref = -INFINITY, l_run = 0.f;
+      const float sc = a.scale_log2;
+      float m_ref = -INFINITY;  // running max of the scaled scores (log2 domain)
 
-      for (int j = 0; j < my_n_kv; ++j) {
-        mbar_wait(&s_full[w], j & 1);
+      const int* dead_row = a.tile_dead ? a.tile_dead + b * (a.Lpad / kTile) : nullptr;
+      for (int j = 0; j < n_kv; ++j) {
+        const int k0 = j * kTile;
+        // (issued before the wait: the flag load overlaps the MMA)
+        const bool need_mask = (k0 + kTile > kv_end_min) || (dead_row == nullptr) || (__ldg(dead_row + j) != 0);
+        mbar_wait(s_full, j & 1);
         tc_fence_after();
+        // One pass over S: all 128 scores of the row come out of TMEM with a single wait (a
+        // tcgen05.ld queues behind the MMAs in flight — measured ~600 cycles per round trip with
+        // two CTAs per SM — so the number of round trips per tile is what matters).
         float s[kTile];
 #pragma unroll
         for (int c = 0; c < kTile / 32; ++c) {
@@ -228,12 +279,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
           for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(raw[i]);
         }
         tmem_ld_wait();
-        const int k0 = j * kTile;
-        const bool need_mask = (k0 + kTile > kv_end_min) ||
-                               (a.tile_dead == nullptr) ||
-                               (__ldg(a.tile_dead + b * (a.Lpad / kTile) + j) != 0);
         float m_tile = -INFINITY;
-        if (need_mask) {
+        if (need_mask) {  // frame boundary / dead keys in this tile
 #pragma unroll
           for (int i4 = 0; i4 < kTile / 4; ++i4) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(kb + k0) + i4);
@@ -241,7 +288,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i = 4 * i4 + e;
-              float x = s[i] * a.scale_log2 + bv[e];
+              float x = s[i] + bv[e];  // -inf for dead keys
               x = (k0 + i < kv_end) ? x : -INFINITY;
               s[i] = x;
               m_tile = fmaxf(m_tile, x);
@@ -249,17 +296,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < kTile; ++i) {
-            s[i] *= a.scale_log2;
-            m_tile = fmaxf(m_tile, s[i]);
-          }
+          for (int i = 0; i < kTile; ++i) m_tile = fmaxf(m_tile, s[i]);
         }
+        m_tile *= sc;  // sc > 0: max commutes with the scale
         // running-max policy: keep a stale reference unless the new max exceeds it by > 2^8
         const bool had = m_ref > -INFINITY;
         const bool grow = had ? (m_tile > m_ref + kRescaleThreshold) : (m_tile > -INFINITY);
         const float m_new = grow ? m_tile : m_ref;
         if (j > 0 && __any_sync(0xffffffffu, grow && had)) {
-          // rescale O_w (in TMEM) and l by 2^(m_ref - m_new); rows that do not grow use 1
+          // rescale O and l (in TMEM) by 2^(m_ref - m_new); rows that do not grow use 1
           const float alpha = (grow && had) ? ex2(m_ref - m_new) : 1.0f;
 #pragma unroll
           for (int c = 0; c < kD / 32; ++c) {
@@ -270,39 +315,39 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x32(tO + c * 32, o);
           }
+          const uint32_t lv = tmem_ld_1(tL);
+          tmem_ld_wait();
+          tmem_st_1(tL, __float_as_uint(__uint_as_float(lv) * alpha));
           tmem_st_wait();
-          l_run *= alpha;
         }
         m_ref = m_new;
-        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;  // fully-masked-so-far rows -> p = 0
-        float l_tile = 0.f;
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;  // fully-masked-so-far rows -> p = 0
+        // P = 2^(s*scale - m) as bf16, two keys per 32-bit column, written back into TMEM over the
+        // first 64 columns of S: the A operand of the P V and row-sum MMAs.  The XU pipe (MUFU, 16
+        // lanes per SM on B200) is the busiest unit of this kernel (ncu: 74 %), so kPolyPer8 of
+        // every 8 exponentials run as a polynomial on the FMA pipe instead.
 #pragma unroll
-        for (int g = 0; g < kTile / 8; ++g) {  // 16-byte chunks of 8 keys
-          float p[8];
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t pk[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            p[i] = ex2(s[g * 8 + i] - m_use);
-            l_tile += p[i];
+          for (int i = 0; i < 32; ++i) {
+            const float x0 = fmaf(s[hlf * 64 + 2 * i], sc, neg_m);
+            const float x1 = fmaf(s[hlf * 64 + 2 * i + 1], sc, neg_m);
+            const float p0 = (((2 * i) & 7) < kPolyPer8) ? ex2_poly(x0) : ex2(x0);
+            const float p1 = (((2 * i + 1) & 7) < kPolyPer8) ? ex2_poly(x1) : ex2(x1);
+            pk[i] = pack_bf16x2(p0, p1);
           }
-          uint4 q;
-          q.x = pack_bf16x2(p[0], p[1]);
-          q.y = pack_bf16x2(p[2], p[3]);
-          q.z = pack_bf16x2(p[4], p[5]);
-          q.w = pack_bf16x2(p[6], p[7]);
-          const int kblk = g >> 3;   // which 64-key k-block
-          const int chunk = g & 7;   // 16 B chunk inside the 128 B row
-          *reinterpret_cast<uint4*>(prow + kblk * kTileBytes + ((chunk ^ sw) << 4)) = q;
+          tmem_st_32x32(tS + hlf * 32, pk);
         }
-        l_run += l_tile;
-        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core proxy
+        tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[w]);
+        mbar_arrive(p_full);
       }
 
-      // epilogue: O_w / l -> bf16, token-major store
-      mbar_wait(&o_done[w], 0);
+      // epilogue: O / l -> bf16, token-major store
+      mbar_wait(o_done, 0);
       tc_fence_after();
-      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      const float l_run = __uint_as_float(tmem_ld_1(tL));
       float o[kD];
 #pragma unroll
       for (int c = 0; c < kD / 32; ++c) {
@@ -310,18 +355,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         tmem_ld_32x32(tO + c * 32, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]) * inv;
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]);
       }
+      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
       if (row_ok) {
         uint4* d4 = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(b) * a.L + qi) * HD +
                                              head * kD);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           uint4 q;
-          q.x = pack_bf16x2(o[8 * i + 0], o[8 * i + 1]);
-          q.y = pack_bf16x2(o[8 * i + 2], o[8 * i + 3]);
-          q.z = pack_bf16x2(o[8 * i + 4], o[8 * i + 5]);
-          q.w = pack_bf16x2(o[8 * i + 6], o[8 * i + 7]);
+          q.x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+          q.y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+          q.z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+          q.w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
           d4[i] = q;
         }
       }
@@ -365,7 +411,7 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
                                        kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((L + 2 * kTile - 1) / (2 * kTile), H, B);
+  dim3 grid((L + kTile - 1) / kTile, H, B);
   char tag[56] = "";
   if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d", B, L, H);
   const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);

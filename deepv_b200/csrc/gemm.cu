@@ -43,9 +43,11 @@ constexpr int kMaxSplits = 8;  // portable cluster size
 struct Problem {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmBh;  // CTA-pair mode: same matrix, 128-row box (each CTA loads half of N)
   GemmDesc d;
   int m_tiles, n_tiles, k_blocks, tiles;
   int kb_per_split;      // split-K over a cluster of `splits` CTAs
+  int m_pairs, pair_tiles;  // CTA-pair mode: 256-row tiles (two m-tiles) x n_tiles x batch
   int tiles_w, tiles_h;  // conv: M-tile grid inside one frame
   int c_blocks;          // conv: Cin / 64
   int swap;              // conv, Cout <= 128: weights are the M operand, 16x16 pixels the N operand
@@ -57,6 +59,7 @@ struct KArgs {
   Problem p[2];
   int total_tiles;
   int splits;
+  int total_pair_tiles;
 };
 
 struct TileCoord {
@@ -656,6 +659,256 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------
+// CTA-pair kernel (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256
+// tile.  Each CTA loads its own 128 A rows and HALF of the B tile (128 of the 256 N rows), so the
+// L2 -> SM and shared-memory traffic per SM drops from 48 KB to 32 KB per k-block; the leader CTA
+// issues one M=256 MMA that reads both CTAs' shared memory and writes both CTAs' TMEM.  Used when
+// there are at least as many 256-row tiles as SM pairs (no split-K).
+// ------------------------------------------------------------------------------
+constexpr int kPairStages = 6;
+constexpr int kPairStageBytes = kABytes + kBBytes / 2;  // 32 KB
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kBarBytes + 1024;
+
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst,
+                                                 int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the same-offset mbarrier of BOTH CTAs of the pair when the issued MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(slot_in_smem)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+               : "memory");
+}
+
+__device__ __forceinline__ const Problem& pair_problem_of(const KArgs& k, int& tile) {
+  if (tile < k.p[0].pair_tiles) return k.p[0];
+  tile -= k.p[0].pair_tiles;
+  return k.p[1];
+}
+__device__ __forceinline__ TileCoord decode_pair_tile(const Problem& a, int tile, int rank) {
+  TileCoord tc;
+  tc.n_tile = tile % a.n_tiles;
+  const int rest = tile / a.n_tiles;
+  tc.m_tile = 2 * (rest % a.m_pairs) + rank;  // may be == m_tiles (odd count): all rows out of range
+  tc.b = rest / a.m_pairs;
+  tc.kb0 = 0;
+  tc.kb1 = a.k_blocks;
+  return tc;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_constant__ KArgs k) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint64_t* full_bar = bars;                      // leader's are used (both CTAs' TMA signal them)
+  uint64_t* empty_bar = bars + kPairStages;       // local, arrived by the leader's multicast commit
+  uint64_t* tmem_full = bars + 2 * kPairStages;   // local, multicast commit
+  uint64_t* tmem_empty = tmem_full + 2;           // leader's: 4 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&k.p[0].tmA);
+    tma_prefetch_desc(&k.p[0].tmBh);
+    if (k.p[1].tiles > 0) {
+      tma_prefetch_desc(&k.p[1].tmA);
+      tma_prefetch_desc(&k.p[1].tmBh);
+    }
+    for (int i = 0; i < kPairStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // peer barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int cluster_id = static_cast<int>(blockIdx.x) >> 1;
+  const int n_clusters = static_cast<int>(gridDim.x) >> 1;
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int gtile = cluster_id; gtile < k.total_pair_tiles; gtile += n_clusters) {
+        int tile = gtile;
+        const Problem& a = pair_problem_of(k, tile);
+        const GemmDesc& d = a.d;
+        const TileCoord tc = decode_pair_tile(a, tile, rank);
+        int ct = 0, h0 = 0, w0 = 0;
+        if (d.a_mode == 1) {
+          const int per_frame = a.tiles_w * a.tiles_h;
+          ct = tc.m_tile / per_frame;
+          const int r = tc.m_tile % per_frame;
+          h0 = (r / a.tiles_w) * 8;
+          w0 = (r % a.tiles_w) * 16;
+        }
+        const int n_row = tc.n_tile * BN + rank * (BN / 2);  // this CTA's half of the B tile
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kPairStageBytes;
+          uint8_t* sb = sa + kABytes;
+          const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          if (d.a_mode == 1) {
+            const int tap = kb / a.c_blocks;
+            const int cb = kb - tap * a.c_blocks;
+            const int dt = tap / (d.kh * d.kw);
+            const int dh = (tap / d.kw) % d.kh;
+            const int dw = tap % d.kw;
+            tma_load_5d_pair(&a.tmA, lbar, sa, cb * 64, w0 + dw - d.kw / 2, h0 + dh - d.kh / 2,
+                             ct + dt - (d.kt - 1), tc.b);
+            tma_load_2d_pair(&a.tmBh, lbar, sb, kb * BK, n_row);
+          } else {
+            tma_load_3d_pair(&a.tmA, lbar, sa, kb * BK, tc.m_tile * BM, tc.b);
+            if (d.w_batch_stride != 0)
+              tma_load_3d_pair(&a.tmBh, lbar, sb, kb * BK, n_row, tc.b);
+            else
+              tma_load_2d_pair(&a.tmBh, lbar, sb, kb * BK, n_row);
+          }
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA only) ========================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int gtile = cluster_id; gtile < k.total_pair_tiles; gtile += n_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        int tile = gtile;
+        const Problem& a = pair_problem_of(k, tile);
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t db = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_bf16_ss_pair(tmem_acc, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ============================ epilogue (both CTAs, own 128 rows) ==================
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (int gtile = cluster_id; gtile < k.total_pair_tiles; gtile += n_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      int tile = gtile;
+      const Problem& a = pair_problem_of(k, tile);
+      const TileCoord tc = decode_pair_tile(a, tile, rank);
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // the peer's MMAs / commits no longer touch this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<kTmemCols>(tmem_base);
+  }
+}
+
 template <int MODE>
 int launch_mode(const KArgs& ka, cudaStream_t stream) {
   static bool attr_set = false;
@@ -681,6 +934,33 @@ int launch_mode(const KArgs& ka, cudaStream_t stream) {
     cfg.gridDim = dim3(ka.total_tiles < sm_count() ? ka.total_tiles : sm_count());
   }
   DV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE>, ka));
+  note_launch();
+  return 0;
+}
+
+template <int MODE>
+int launch_pair_mode(const KArgs& ka, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<MODE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    attr_set = true;
+  }
+  const int max_clusters = sm_count() / 2;
+  const int clusters = ka.total_pair_tiles < max_clusters ? ka.total_pair_tiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.dynamicSmemBytes = kPairSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<MODE>, ka));
   note_launch();
   return 0;
 }
@@ -778,13 +1058,21 @@ static int setup_problem(const GemmDesc& d, Problem& pr) {
     uint32_t box[3] = {64, (uint32_t)BN, 1};
     int rc = make_tensor_map_bf16(&pr.tmB, d.W, 3, dims, strides, box, 1);
     if (rc) return rc;
+    box[1] = BN / 2;
+    rc = make_tensor_map_bf16(&pr.tmBh, d.W, 3, dims, strides, box, 1);
+    if (rc) return rc;
   } else {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)d.w_rows};
     uint64_t strides[1] = {ldw_bytes};
     uint32_t box[2] = {64, pr.swap ? 128u : (uint32_t)BN};
     int rc = make_tensor_map_bf16(&pr.tmB, d.W, 2, dims, strides, box, 1);
     if (rc) return rc;
+    box[1] = BN / 2;
+    rc = make_tensor_map_bf16(&pr.tmBh, d.W, 2, dims, strides, box, 1);
+    if (rc) return rc;
   }
+  pr.m_pairs = (pr.m_tiles + 1) / 2;
+  pr.pair_tiles = pr.m_pairs * d.batch * pr.n_tiles;
   return 0;
 }
 
@@ -817,7 +1105,19 @@ static double problem_flops(const GemmDesc& d, int K) {
   return 2.0 * rows * d.N * K;
 }
 
-static int launch_args(KArgs& ka, int mode, cudaStream_t stream) {
+static int launch_args(KArgs& ka, int mode, bool pair, cudaStream_t stream) {
+  if (pair) {
+    switch (mode) {
+      case EPI_BF16: return launch_pair_mode<EPI_BF16>(ka, stream);
+      case EPI_GELU: return launch_pair_mode<EPI_GELU>(ka, stream);
+      case EPI_RESID_GATE: return launch_pair_mode<EPI_RESID_GATE>(ka, stream);
+      case EPI_F32_ADD: return launch_pair_mode<EPI_F32_ADD>(ka, stream);
+      case EPI_QKV: return launch_pair_mode<EPI_QKV>(ka, stream);
+      case EPI_CONV: return launch_pair_mode<EPI_CONV>(ka, stream);
+      case EPI_BF16_ROWBIAS: return launch_pair_mode<EPI_BF16_ROWBIAS>(ka, stream);
+      default: break;  // no pair variant: fall through to the single-CTA kernel
+    }
+  }
   switch (mode) {
     case EPI_BF16: return launch_mode<EPI_BF16>(ka, stream);
     case EPI_GELU: return launch_mode<EPI_GELU>(ka, stream);
@@ -872,6 +1172,20 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
   for (int i = 0; i < 2; ++i)
     if (ka.p[i].tiles > 0) ka.p[i].kb_per_split = (ka.p[i].k_blocks + ka.splits - 1) / ka.splits;
   ka.total_tiles = ka.p[0].tiles + ka.p[1].tiles;
+  if (ka.p[1].tiles == 0) ka.p[1].pair_tiles = 0;
+  ka.total_pair_tiles = ka.p[0].pair_tiles + ka.p[1].pair_tiles;
+  // CTA pairs (cta_group::2) once every SM pair has a 256-row tile: ~570 cycles per k-block instead
+  // of the ~850 a lone CTA gets when all SMs pull 48 KB per k-block through L2
+  bool pair = false;
+  // (dense only: the implicit-GEMM convs measured the same with and without pairing)
+  if (ka.splits == 1 && d0.a_mode == 0 && d0.mode != EPI_UNPATCH) {
+    const int nsm = sm_count();
+    const double w1 = static_cast<double>((ka.total_tiles + nsm - 1) / nsm);
+    const double w2 = static_cast<double>((ka.total_pair_tiles + nsm / 2 - 1) / (nsm / 2));
+    pair = ka.total_tiles >= nsm && w2 * 0.75 < w1;
+    static const char* ep = getenv("DV_GEMM_PAIR");
+    if (ep) pair = atoi(ep) != 0 && ka.total_pair_tiles > 0;
+  }
 
   const int K0 = ka.p[0].k_blocks * BK;
   double flops = problem_flops(d0, K0);
@@ -885,17 +1199,18 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
   char tag[56] = "";
   if (prof_on()) {
     if (d0.a_mode == 1)
-      snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k%d%s s%d e%d", d0.cT, d0.cH, d0.cW, d0.cC,
-               d0.N, d0.kt, ka.p[0].swap ? " sw" : "", ka.splits, d0.conv_store);
+      snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k%d%s%s s%d e%d", d0.cT, d0.cH, d0.cW,
+               d0.cC, d0.N, d0.kt, ka.p[0].swap ? " sw" : "", pair ? " 2cta" : "", ka.splits,
+               d0.conv_store);
     else if (d1 != nullptr)
-      snprintf(tag, sizeof(tag), "gemm B%d M%d+%d N%d K%d s%d e%d", d0.batch, d0.M, d1->M, d0.N, K0,
-               ka.splits, d0.mode);
+      snprintf(tag, sizeof(tag), "gemm B%d M%d+%d N%d K%d s%d%s e%d", d0.batch, d0.M, d1->M, d0.N, K0,
+               ka.splits, pair ? " 2cta" : "", d0.mode);
     else
-      snprintf(tag, sizeof(tag), "gemm B%d M%d N%d K%d s%d e%d", d0.batch, d0.M, d0.N, K0, ka.splits,
-               d0.mode);
+      snprintf(tag, sizeof(tag), "gemm B%d M%d N%d K%d s%d%s e%d", d0.batch, d0.M, d0.N, K0, ka.splits,
+               pair ? " 2cta" : "", d0.mode);
   }
   const int pid = prof_begin(d0.a_mode == 1 ? PROF_CONV : PROF_GEMM, flops, bytes, stream, tag);
-  rc = launch_args(ka, d0.mode, stream);
+  rc = launch_args(ka, d0.mode, pair, stream);
   prof_end(pid, stream);
   return rc;
 }

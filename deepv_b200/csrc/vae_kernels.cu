@@ -26,12 +26,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloa
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, HW);
   const uint4* xf = reinterpret_cast<const uint4*>(x + static_cast<long long>(f) * HW * C);
-  __shared__ float s_sum[64], s_sq[64];
-  if (threadIdx.x < 64) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
+  __shared__ float4 s_part[kGnThreads];  // (sum, sumsq) of channels 0-3 and 4-7 of every thread
   const int v = threadIdx.x % vec_per_pix;           // requires blockDim % vec_per_pix == 0
   const int pstep = kGnThreads / vec_per_pix;
   float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;      // cpg == 4 -> two groups per 8-vector
@@ -58,21 +53,30 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloa
     for (int u = 0; u < 4; ++u) add(t[u]);
   }
   for (; p < p1; p += pstep) add(__ldg(xf + static_cast<long long>(p) * vec_per_pix + v));
-  if (cpg == 4) {
-    atomicAdd(&s_sum[(v * 8) / 4], s0);
-    atomicAdd(&s_sq[(v * 8) / 4], q0);
-    atomicAdd(&s_sum[(v * 8) / 4 + 1], s1);
-    atomicAdd(&s_sq[(v * 8) / 4 + 1], q1);
-  } else {
-    atomicAdd(&s_sum[(v * 8) / cpg], s0 + s1);
-    atomicAdd(&s_sq[(v * 8) / cpg], q0 + q1);
-  }
+  // fixed-order reduction inside the CTA (bit-reproducible), fp64 atomics between CTAs
+  s_part[threadIdx.x] = make_float4(s0, q0, s1, q1);
   __syncthreads();
   if (threadIdx.x < G) {
-    atomicAdd(&acc[(static_cast<long long>(f) * G + threadIdx.x) * 2 + 0],
-              static_cast<double>(s_sum[threadIdx.x]));
-    atomicAdd(&acc[(static_cast<long long>(f) * G + threadIdx.x) * 2 + 1],
-              static_cast<double>(s_sq[threadIdx.x]));
+    const int g = threadIdx.x;
+    float sum = 0.f, sq = 0.f;
+    if (cpg == 4) {
+      const int vv = g >> 1;
+      for (int k = 0; k < pstep; ++k) {
+        const float4 t = s_part[vv + k * vec_per_pix];
+        sum += (g & 1) ? t.z : t.x;
+        sq += (g & 1) ? t.w : t.y;
+      }
+    } else {
+      const int v0 = g * (cpg / 8), v1 = v0 + cpg / 8;
+      for (int vv = v0; vv < v1; ++vv)
+        for (int k = 0; k < pstep; ++k) {
+          const float4 t = s_part[vv + k * vec_per_pix];
+          sum += t.x + t.z;
+          sq += t.y + t.w;
+        }
+    }
+    atomicAdd(&acc[(static_cast<long long>(f) * G + g) * 2 + 0], static_cast<double>(sum));
+    atomicAdd(&acc[(static_cast<long long>(f) * G + g) * 2 + 1], static_cast<double>(sq));
   }
 }
 

@@ -60,6 +60,28 @@ class Shard:
             return Shard(dist.get_rank(group), dist.get_world_size(group), group)
         return Shard(0, 1, None)
 
+    @staticmethod
+    def grouped(group_size: int) -> "Shard":
+        """Split the world into consecutive groups of `group_size` ranks (one rollout per group) and
+        return this rank's shard of its group.  Every rank must call this (new_group is collective)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return Shard(0, 1, None)
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if group_size <= 1:
+            return Shard(0, 1, None)
+        if world % group_size != 0:
+            raise ValueError(f"world size {world} is not a multiple of the rollout group size {group_size}")
+        mine = None
+        for g in range(world // group_size):
+            ranks = list(range(g * group_size, (g + 1) * group_size))
+            grp = dist.new_group(ranks)
+            if rank in ranks:
+                mine = grp
+        return Shard(dist.get_rank(mine), group_size, mine)
+
+    def _global(self, group_rank: int) -> int:
+        return dist.get_global_rank(self.group, group_rank) if self.group is not None else group_rank
+
     @property
     def active(self) -> bool:
         return self.world > 1
@@ -86,7 +108,7 @@ class Shard:
         from its owner so that every rank can blend."""
         if not self.active:
             return
-        works = [dist.broadcast(buf, src=owner_of_item(i, self.world), group=self.group, async_op=True)
+        works = [dist.broadcast(buf, src=self._global(owner_of_item(i, self.world)), group=self.group, async_op=True)
                  for i, buf in enumerate(tile_buffers)]
         for w in works:
             w.wait()

@@ -1,6 +1,6 @@
-"""Short ncu target: a few launches of each hot kernel at its benchmark shape.
+"""Short ncu target: one launch of each hot kernel at its benchmark shape.
 
-    ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 6 -o prof python scripts/ncu_target.py
+    ncu --set full --clock-control none --import-source on -k regex:"gemm_|attn_" -o prof python scripts/ncu_target.py
 """
 import ctypes as C
 import sys
@@ -23,40 +23,42 @@ def p(t):
 
 torch.manual_seed(0)
 if which in ("all", "conv"):
-    # up3 resnet conv of the VAE decoder: 128 -> 128 channels at 256x256, 8 frames (464 GFLOP)
-    B, T, H, W, Ci, Co = 1, 8, 256, 256, 128, 128
+    # up3 resnet conv of the VAE decoder: 128 -> 128 channels at 256x256, 9 frames (swapped-operand path)
+    B, T, H, W, Ci, Co = 1, 9, 256, 256, 128, 128
     x = (torch.randn(B, T, H, W, Ci, device="cuda") * 0.5).bfloat16()
     w = (torch.randn(Co, 27, Ci, device="cuda") * 0.05).bfloat16()
     bias = torch.randn(Co, device="cuda")
     out = torch.empty(B, T, H, W, Co, device="cuda", dtype=torch.bfloat16)
-    for _ in range(3):
-        _lib.check(lib.dv_conv3d_cl(p(x), p(w), p(bias), None, p(out), B, T, H, W, Ci, Co, Co, 3, 0, 0, st))
-    # up1 resnet conv: 512 -> 512 at 64x64, 15 frames
-    B, T, H, W, Ci, Co = 1, 15, 64, 64, 512, 512
+    _lib.check(lib.dv_conv3d_cl(p(x), p(w), p(bias), None, p(out), B, T, H, W, Ci, Co, Co, 3, 0, 0, st))
+    # up2 resnet conv: 256 -> 256 at 128x128, 5 frames
+    B, T, H, W, Ci, Co = 1, 5, 128, 128, 256, 256
     x = (torch.randn(B, T, H, W, Ci, device="cuda") * 0.5).bfloat16()
     w = (torch.randn(Co, 27, Ci, device="cuda") * 0.05).bfloat16()
     out = torch.empty(B, T, H, W, Co, device="cuda", dtype=torch.bfloat16)
-    for _ in range(3):
-        _lib.check(lib.dv_conv3d_cl(p(x), p(w), None, None, p(out), B, T, H, W, Ci, Co, Co, 3, 0, 0, st))
+    _lib.check(lib.dv_conv3d_cl(p(x), p(w), None, None, p(out), B, T, H, W, Ci, Co, Co, 3, 0, 0, st))
 if which in ("all", "gemm"):
-    # FF1 of a stage-2 forward: [3072, 1536] x [6144, 1536]^T, GELU epilogue
-    M, N, K = 3072, 6144, 1536
-    A = (torch.randn(1, M, K, device="cuda") * 0.5).bfloat16()
+    # FF1 of a stage-2 forward: [2][1536, 1536] x [6144, 1536]^T, GELU epilogue
+    Bt, M, N, K = 2, 1536, 6144, 1536
+    A = (torch.randn(Bt, M, K, device="cuda") * 0.5).bfloat16()
     Wt = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
     bias = torch.randn(N, device="cuda")
+    Cc = torch.empty(Bt, M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), p(bias), p(Cc), Bt, M, N, K, 1, st))
+    # a large square problem
+    M = N = K = 4096
+    A = (torch.randn(1, M, K, device="cuda") * 0.5).bfloat16()
+    Wt = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
     Cc = torch.empty(1, M, N, device="cuda", dtype=torch.bfloat16)
-    for _ in range(3):
-        _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), p(bias), p(Cc), 1, M, N, K, 1, st))
-    # FF2 of a stage-0 forward (small M): [2][96, 6144] x [1536, 6144]^T
-    A = (torch.randn(2, 96, 6144, device="cuda") * 0.5).bfloat16()
+    _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), None, p(Cc), 1, M, N, K, 0, st))
+    # FF2 of the context stream (small M, split-K cluster): [2][77, 6144] x [1536, 6144]^T
+    A = (torch.randn(2, 77, 6144, device="cuda") * 0.5).bfloat16()
     Wt = (torch.randn(1536, 6144, device="cuda") * 0.05).bfloat16()
-    Cc = torch.empty(2, 96, 1536, device="cuda", dtype=torch.bfloat16)
-    for _ in range(3):
-        _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), None, p(Cc), 2, 96, 1536, 6144, 0, st))
+    Cc = torch.empty(2, 77, 1536, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), None, p(Cc), 2, 77, 1536, 6144, 0, st))
 if which in ("all", "attn"):
-    B, L, H = 3, 2237, 24
+    B, L, H = 2, 1613, 24
     qkv = torch.randn(B, L, 3 * H * 64, device="cuda").bfloat16()
-    sizes = [269, 240, 192, 768, 768]
+    sizes = [77, 768, 768]
     bounds, acc = [], 0
     for s in sizes:
         acc += s
@@ -69,10 +71,10 @@ if which in ("all", "attn"):
     Lpad = (L + 127) // 128 * 128
     kb = torch.zeros(B, Lpad, device="cuda")
     kb[:, L:] = float("-inf")
-    kb[:2, :192] = float("-inf")
+    kb[0, 1:77] = float("-inf")
+    kb[1, 12:77] = float("-inf")
     out = torch.empty(B, L, H * 64, device="cuda", dtype=torch.bfloat16)
     kvd = kv.cuda()
-    for _ in range(3):
-        _lib.check(lib.dv_attention(p(qkv), p(out), p(kvd), p(kb), B, L, Lpad, H, st))
+    _lib.check(lib.dv_attention(p(qkv), p(out), p(kvd), p(kb), B, L, Lpad, H, st))
 torch.cuda.synchronize()
 print("ncu target done")

@@ -85,3 +85,34 @@ def test_branch_assignment():
     sh = parallel.Shard(0, 1)
     x = torch.randn(2, 3)
     assert sh.gather_branches(x, 2) is x and not sh.active
+
+
+def _worker_grouped(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = parallel.Shard.grouped(2)   # world 4 -> two independent rollouts on rank pairs
+        assert (sh.rank, sh.world) == (rank % 2, 2)
+        rollout = rank // 2
+        pred = torch.full((1, 2, 2), float(100 * rollout + sh.my_branch(2)))
+        allp = sh.gather_branches(pred, 2)
+        assert allp[:, 0, 0].tolist() == [100.0 * rollout, 100.0 * rollout + 1]
+        items = parallel.decode_items(2, 3)
+        bufs = [torch.zeros(4) for _ in items]
+        for i in sh.my_items(len(items)):
+            bufs[i].fill_(1000 * rollout + i + 1)
+        sh.exchange_tiles(bufs)   # owners are GROUP ranks; the broadcast must map them to global ranks
+        assert [b[0].item() for b in bufs] == [1000.0 * rollout + i + 1 for i in range(len(items))]
+        ret[rank] = rollout
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rollout_groups_over_gloo_world4():
+    world = 4
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_grouped, args=(world, port, ret), nprocs=world, join=True)
+    assert [ret[r] for r in range(4)] == [0, 0, 1, 1]
