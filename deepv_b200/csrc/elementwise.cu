@@ -97,32 +97,51 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * kGemvWarps + warp) * kGemvRowsPerWarp;
-  for (int rr = 0; rr < kGemvRowsPerWarp; ++rr) {
-    const int n = row0 + rr;
-    if (n >= N) break;
-    const uint4* wr = reinterpret_cast<const uint4*>(W + static_cast<long long>(n) * K);
-    float acc[NB];
+  // four weight rows in flight per warp (4 x 16 B loads per lane and k-step): the kernel is pure
+  // weight streaming, so memory-level parallelism is what sets its bandwidth
+  constexpr int R = 4;
+  for (int rr = 0; rr < kGemvRowsPerWarp; rr += R) {
+    const int n0 = row0 + rr;
+    if (n0 >= N) break;
+    const uint4* wr[R];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const int n = (n0 + r < N) ? n0 + r : N - 1;  // clamp: tail rows re-read the last row
+      wr[r] = reinterpret_cast<const uint4*>(W + static_cast<long long>(n) * K);
+    }
+    float acc[R][NB];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
+#pragma unroll 2
     for (int k8 = lane; k8 < K / 8; k8 += 32) {
-      const uint4 w = __ldg(wr + k8);
-      const float wf[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y),
-                           bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+      uint4 w[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = __ldg(wr[r] + k8);
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const float4 a0 = *reinterpret_cast<const float4*>(s_in + b * K + k8 * 8);
         const float4 a1 = *reinterpret_cast<const float4*>(s_in + b * K + k8 * 8 + 4);
-        acc[b] += wf[0] * a0.x + wf[1] * a0.y + wf[2] * a0.z + wf[3] * a0.w + wf[4] * a1.x +
-                  wf[5] * a1.y + wf[6] * a1.z + wf[7] * a1.w;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r][b] += bf16_lo(w[r].x) * a0.x + bf16_hi(w[r].x) * a0.y + bf16_lo(w[r].y) * a0.z +
+                       bf16_hi(w[r].y) * a0.w + bf16_lo(w[r].z) * a1.x + bf16_hi(w[r].z) * a1.y +
+                       bf16_lo(w[r].w) * a1.z + bf16_hi(w[r].w) * a1.w;
+        }
       }
     }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      float r = warp_sum(acc[b]);
-      if (lane == 0) {
-        r += bias ? bias[n] : 0.f;
-        float* o = out + b * out_stride + n;
-        *o = accumulate ? (*o + r) : r;
+    for (int r = 0; r < R; ++r) {
+      const int n = n0 + r;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float v = warp_sum(acc[r][b]);
+        if (lane == 0 && n < N) {
+          v += bias ? bias[n] : 0.f;
+          float* o = out + b * out_stride + n;
+          *o = accumulate ? (*o + v) : v;
+        }
       }
     }
   }

@@ -294,6 +294,13 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
           reinterpret_cast<__nv_bfloat16*>(d.out)[o] = __float2bfloat16(val);
       }
     }
+  } else if constexpr (MODE == EPI_TAPS) {
+    float4* o4 = reinterpret_cast<float4*>(d.out);
+    const long long row = static_cast<long long>(r.b) * d.M + r.m;
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i)
+      o4[static_cast<long long>(n / 4 + i) * d.ldo + row] =
+          make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   } else if constexpr (MODE == EPI_CONV) {
     add_bias<W>(d.bias, n, v);
     int ot = r.ct, oh = r.ch, ow = r.cw, oc = n, oH = d.cH, oW = d.cW;
@@ -1115,6 +1122,7 @@ static int launch_args(KArgs& ka, int mode, bool pair, cudaStream_t stream) {
       case EPI_QKV: return launch_pair_mode<EPI_QKV>(ka, stream);
       case EPI_CONV: return launch_pair_mode<EPI_CONV>(ka, stream);
       case EPI_BF16_ROWBIAS: return launch_pair_mode<EPI_BF16_ROWBIAS>(ka, stream);
+      case EPI_TAPS: return launch_pair_mode<EPI_TAPS>(ka, stream);
       default: break;  // no pair variant: fall through to the single-CTA kernel
     }
   }
@@ -1127,6 +1135,7 @@ static int launch_args(KArgs& ka, int mode, bool pair, cudaStream_t stream) {
     case EPI_UNPATCH: return launch_mode<EPI_UNPATCH>(ka, stream);
     case EPI_CONV: return launch_mode<EPI_CONV>(ka, stream);
     case EPI_BF16_ROWBIAS: return launch_mode<EPI_BF16_ROWBIAS>(ka, stream);
+    case EPI_TAPS: return launch_mode<EPI_TAPS>(ka, stream);
     default:
       set_error("gemm: unknown epilogue mode %d", mode);
       return -1;

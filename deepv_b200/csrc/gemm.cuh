@@ -24,7 +24,9 @@ enum EpiMode : int {
   EPI_UNPATCH = 5,     // proj_out + unpatchify store               (mmdit.py:1527,1452-1457)
   EPI_CONV = 6,        // conv3d: bias (+residual), NDHWC store with optional pixel-shuffle /
                        // frame-interleave address map              (vae.py:251,309,382,407-409)
-  EPI_BF16_ROWBIAS = 7 // out_bf16 = acc + bias[m]  (transposed projections, V^T for VAE attention)
+  EPI_BF16_ROWBIAS = 7, // out_bf16 = acc + bias[m]  (transposed projections, V^T for VAE attention)
+  EPI_TAPS = 8         // out_f32[n/4][b*M + m][4] = acc: per-tap partial products of a conv with <= 4
+                       // output channels (plane-major so that the tap gather is coalesced); ldo = batch*M
 };
 
 enum ConvStore : int { CONV_PLAIN = 0, CONV_SHUFFLE_HW = 1, CONV_INTERLEAVE_T = 2 };

@@ -32,6 +32,9 @@ int launch_transpose(const __nv_bfloat16* in, int ld_in, __nv_bfloat16* out, int
                      int cols, cudaStream_t stream);
 int launch_latent_tile(const void* z, int is_bf16, __nv_bfloat16* out, int C, int T, int h, int w,
                        int y0, int x0, int th, int tw, int Cpad, cudaStream_t stream);
+// conv with <= 4 output channels from per-tap partial products (EPI_TAPS planes), vae.py:225-252
+int launch_tap_gather(const float* planes, const float* bias, __nv_bfloat16* out, int T, int H, int W,
+                      int Cout, cudaStream_t stream);
 }  // namespace dv
 
 struct dv_vae {
@@ -60,6 +63,8 @@ struct dv_vae_plan {
   float* sc = nullptr;
   double* gn_acc = nullptr;
   float* gn_stats = nullptr;
+  float* taps = nullptr;        // conv_out per-tap planes [32][T*H*W][4] fp32 of the largest tile
+  long long taps_elems = 0;
   TileOut* tiles_dev = nullptr;
   double flops = 0;
   std::vector<void*> allocs;
@@ -352,7 +357,42 @@ static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, c
   }
   x = r.gn("decoder.conv_norm_out", x, true, B[other(1)]);
   TileOut& to = p->tiles[ti * p->cols + tj];
-  Act y = r.conv("decoder.conv_out.conv", x, c.out_channels, 3, CONV_PLAIN, 0, nullptr, to.px, 16);
+  // conv_out (C -> 3): a full implicit GEMM would spend a 128-row MMA tile on 3 output channels.
+  // Instead ONE K = C GEMM produces the 27 x 3 per-tap partial products of every pixel and a
+  // gather kernel sums the 27 shifted planes (same terms, fp32 throughout).
+  Act y = x;
+  y.p = to.px;
+  y.C = c.out_channels;
+  {
+    const long long npix = static_cast<long long>(x.T) * x.H * x.W;
+    r.flops += 2.0 * npix * c.out_channels * 27.0 * x.C;
+    if (dry) {
+      if (32 * npix * 4 > p->taps_elems) p->taps_elems = 32 * npix * 4;
+    } else if (r.rc == 0) {
+      GemmDesc d = {};
+      d.batch = 1;
+      d.M = static_cast<int>(npix);
+      d.N = 128;  // 27 taps x 4 columns = 108, padded to the 32-column epilogue chunk (weight rows
+                  // beyond 108 are zero-filled by TMA; their planes are written but never read)
+      d.K = x.C;
+      d.A = x.p;
+      d.a_batch_stride = npix * x.C;
+      d.lda = x.C;
+      d.W = r.W("decoder.conv_out.conv.weight_taps");
+      d.w_rows = 27 * 4;
+      d.mode = EPI_TAPS;
+      d.out = p->taps;
+      d.ldo = static_cast<int>(npix);
+      if (npix >= (1ll << 31) || x.C % 64 != 0) {
+        set_error("conv_out: %lld pixels, C=%d", npix, x.C);
+        r.rc = DV_ERR_INVALID;
+      }
+      if (r.rc == 0) r.rc = launch_gemm(d, st);
+      if (r.rc == 0)
+        r.rc = launch_tap_gather(p->taps, reinterpret_cast<const float*>(r.W("decoder.conv_out.conv.bias")),
+                                 to.px, x.T, x.H, x.W, c.out_channels, st);
+    }
+  }
   if (dry) {
     to.H = y.H;
     to.W = y.W;
@@ -411,6 +451,7 @@ extern "C" int dv_vae_plan_create(dv_vae* v, int T, int h, int w, int tile_laten
   if ((rc = plan_alloc(p, &p->gn_acc, static_cast<long long>(max_frames) * 64 * 2)) != 0) return fail(rc);
   if ((rc = plan_alloc(p, &p->gn_stats, static_cast<long long>(max_frames) * 64 * 2)) != 0) return fail(rc);
   cudaError_t e = cudaMemset(p->gn_acc, 0, static_cast<size_t>(max_frames) * 64 * 2 * sizeof(double));
+  if ((rc = plan_alloc(p, &p->taps, p->taps_elems)) != 0) return fail(rc);
   for (auto& to : p->tiles) {
     if ((rc = plan_alloc(p, &to.px, static_cast<long long>(p->Tout) * to.H * to.W * 3)) != 0)
       return fail(rc);

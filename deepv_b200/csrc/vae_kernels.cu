@@ -221,7 +221,61 @@ __global__ void latent_tile_kernel(const T* __restrict__ z, __nv_bfloat16* __res
   out[i] = __float2bfloat16(v);
 }
 
+// Tap gather of a causal 3x3x3 conv with <= 4 output channels (conv_out: 128 -> 3).  The GEMM
+// wrote per-tap partial products P[tap][pixel][4] (EPI_TAPS); out[t][h][w][c] = bias[c] +
+// sum_tap P[tap][(t+dt-2, h+dh-1, w+dw-1)][c], zero outside the frame / before the first frame
+// (vae.py:225-252).  One thread per pixel: every tap plane is read with coalesced 16-byte loads.
+__global__ void __launch_bounds__(256) tap_gather_kernel(const float4* __restrict__ P,
+                                                         const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ out, int T, int H,
+                                                         int W, int Cout) {
+  const long long npix = static_cast<long long>(T) * H * W;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const int w = static_cast<int>(i % W);
+  const int h = static_cast<int>((i / W) % H);
+  const int t = static_cast<int>(i / (static_cast<long long>(W) * H));
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int dt = 0; dt < 3; ++dt) {
+    const int tt = t + dt - 2;
+    if (tt < 0) continue;
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hh = h + dh - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int ww = w + dw - 1;
+        if (ww < 0 || ww >= W) continue;
+        const int tap = (dt * 3 + dh) * 3 + dw;
+        const float4 v = __ldg(P + static_cast<long long>(tap) * npix +
+                               (static_cast<long long>(tt) * H + hh) * W + ww);
+        a0 += v.x;
+        a1 += v.y;
+        a2 += v.z;
+        a3 += v.w;
+      }
+    }
+  }
+  const float acc[4] = {a0, a1, a2, a3};
+  __nv_bfloat16* o = out + i * Cout;
+  for (int c = 0; c < Cout; ++c) o[c] = __float2bfloat16(acc[c] + __ldg(bias + c));
+}
+
 }  // namespace
+
+int launch_tap_gather(const float* planes, const float* bias, __nv_bfloat16* out, int T, int H, int W,
+                      int Cout, cudaStream_t stream) {
+  DV_REQUIRE(Cout >= 1 && Cout <= 4, "tap_gather: Cout=%d", Cout);
+  const long long npix = static_cast<long long>(T) * H * W;
+  ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(npix) * (27 * 16.0 + Cout * 2.0), stream, "tap_gather");
+  tap_gather_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(planes), bias, out, T, H, W, Cout);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
 
 // pixels per CTA: every thread should see >= 8 vectors (two unrolled rounds) when the tensor is
 // large, while small tensors still spread over >= 2 CTAs per SM

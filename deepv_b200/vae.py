@@ -88,6 +88,13 @@ def pack_decoder_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Dict
     vec("decoder.conv_norm_out.weight")
     vec("decoder.conv_norm_out.bias")
     conv("decoder.conv_out.conv", rows=16)
+    # conv_out as per-tap partial products (csrc/vae.cu): rows (tap, c padded to 4), K = Cin
+    w = sd["decoder.conv_out.conv.weight"].float()            # [co, ci, kt, kh, kw]
+    co, ci = w.shape[0], w.shape[1]
+    if co > 4 or tuple(w.shape[2:]) != (3, 3, 3):
+        raise _lib.DeepVError(f"conv_out {tuple(w.shape)}: the tap-gather path needs <= 4 output channels, 3x3x3")
+    taps = F.pad(w.permute(2, 3, 4, 0, 1).reshape(27, co, ci), (0, (ci + 63) // 64 * 64 - ci, 0, 4 - co))
+    out["decoder.conv_out.conv.weight_taps"] = taps.reshape(27 * 4, -1).to(device=device, dtype=torch.bfloat16).contiguous()
     return out
 
 
