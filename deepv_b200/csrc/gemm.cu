@@ -36,7 +36,8 @@ constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kBarBytes = 256;
-constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+constexpr int kGnBytes = 4 * 8 * 8 * 2 * 4;  // fused GroupNorm partials: [warp][chunk][group][2] floats
+constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kGnBytes + 1024;  // + align slack
 constexpr uint32_t kTmemCols = 2 * BN;
 constexpr int kMaxSplits = 8;  // portable cluster size
 
@@ -180,14 +181,72 @@ __device__ __forceinline__ void add_bf16x32(const __nv_bfloat16* src, float (&v)
   }
 }
 
+// sum / sum of squares of the bf16-rounded values of 32 / CPG GroupNorm groups over the rows a warp
+// holds.  `uniform` (all 32 lanes on the same chunk): butterfly over the lanes, then lane 0 either
+// parks the warp's partial in shared memory (`part`: [8 groups][2] floats of this warp and chunk;
+// the tile flush merges the four warps in a fixed order) or adds it to the fp64 accumulators.
+template <int CPG>
+__device__ __forceinline__ void gn_accumulate(const float (&v)[32], bool row_ok, double* acc,
+                                              bool uniform, float* part) {
+#pragma unroll
+  for (int g = 0; g < 32 / CPG; ++g) {
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) {
+      const float x = row_ok ? __bfloat162float(__float2bfloat16(v[g * CPG + i])) : 0.f;
+      sm += x;
+      sq += x * x;
+    }
+    if (uniform) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        if (part != nullptr) {
+          part[2 * g] = sm;
+          part[2 * g + 1] = sq;
+        } else {
+          atomicAdd(acc + 2 * g, static_cast<double>(sm));
+          atomicAdd(acc + 2 * g + 1, static_cast<double>(sq));
+        }
+      }
+    } else if (row_ok) {
+      atomicAdd(acc + 2 * g, static_cast<double>(sm));
+      atomicAdd(acc + 2 * g + 1, static_cast<double>(sq));
+    }
+  }
+}
+
+// output frame / first stored channel of accumulator column n of a conv tile whose rows sit in
+// input frame ct (the store-mode address maps of vae.py:382,407-409)
+__device__ __forceinline__ void conv_out_coord(const GemmDesc& d, int ct, int n, int* ot, int* oc) {
+  *ot = ct;
+  *oc = n;
+  if (d.conv_store == CONV_SHUFFLE_HW) {
+    *oc = n % d.out_C;
+  } else if (d.conv_store == CONV_INTERLEAVE_T) {
+    *oc = n % d.out_C;
+    *ot = 2 * ct + n / d.out_C - (d.conv_drop_first ? 1 : 0);
+  }
+}
+
+__device__ __forceinline__ double* gn_replica(const GemmDesc& d) {
+  return d.gn_acc + static_cast<long long>(blockIdx.x % d.gn_replicas) * d.gn_replica_stride;
+}
+
 template <int MODE>
 struct EpiW {
   static constexpr int value = (MODE == EPI_QKV) ? 64 : 32;
 };
 
 // v = W accumulator columns [n, n + W) of output row `r`; n < d.N and r.ok hold.
+// `uniform`: every lane of the warp handles the same column chunk n of rows of ONE tile (true on the
+// TMEM path; false in the split-K reduction, where lanes may sit on different chunks).
 template <int MODE, int W>
-__device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n, float (&v)[W]) {
+__device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n, float (&v)[W],
+                                        bool uniform = true, float* gn_part = nullptr) {
   const GemmDesc& d = a.d;
   if constexpr (MODE == EPI_BF16 || MODE == EPI_GELU) {
     add_bias<W>(d.bias, n, v);
@@ -323,16 +382,30 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
         (d.conv_store == CONV_INTERLEAVE_T) ? (2 * d.cT - (d.conv_drop_first ? 1 : 0)) : d.cT;
     const long long off =
         (((static_cast<long long>(r.b) * oT + ot) * oH + oh) * oW + ow) * d.out_C + oc;
-    if (d.residual != nullptr)
-      add_bf16x32<W>(reinterpret_cast<const __nv_bfloat16*>(d.residual) + off, v);
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + off, v);
+    if (r.ok) {
+      if (d.residual != nullptr)
+        add_bf16x32<W>(reinterpret_cast<const __nv_bfloat16*>(d.residual) + off, v);
+      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(d.out) + off, v);
+    }
+    if (d.gn_acc != nullptr) {
+      // fused GroupNorm statistics of what was just stored (bf16-rounded), per (frame, group)
+      double* acc = gn_replica(d) + (static_cast<long long>(ot) * (d.out_C / d.gn_cpg) + oc / d.gn_cpg) * 2;
+      if (d.gn_cpg == 4)
+        gn_accumulate<4>(v, r.ok, acc, uniform, gn_part);
+      else if (d.gn_cpg == 8)
+        gn_accumulate<8>(v, r.ok, acc, uniform, gn_part);
+      else
+        gn_accumulate<16>(v, r.ok, acc, uniform, gn_part);
+    }
   }
 }
 
 // Accumulator tile in TMEM -> epilogue, 32 columns in flight while 32 are processed.
+// gn_smem: [4 warps][8 chunks][8 groups][2] floats for the fused GroupNorm statistics (conv only)
 template <int MODE>
 __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileCoord& tc,
-                                                   uint32_t tmem_acc, int row_in_tile, int quarter) {
+                                                   uint32_t tmem_acc, int row_in_tile, int quarter,
+                                                   float* gn_smem = nullptr) {
   constexpr int W = EpiW<MODE>::value;
   const GemmDesc& d = a.d;
   const RowCtx r = make_row(a, tc, row_in_tile);
@@ -363,14 +436,32 @@ __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileC
       const int n = n0 + c * 32;
       tmem_ld_wait();
       if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, buf[(c + 1) & 1]);
-      if (n < d.N && r.ok) {
+      if (n < d.N && (r.ok || MODE == EPI_CONV)) {  // conv rows always enter: warp-wide GN reduction
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(buf[c & 1][i]);
-        epi_row<MODE, 32>(a, r, n, v);
+        epi_row<MODE, 32>(a, r, n, v, true, gn_smem ? gn_smem + ((quarter * 8 + c) * 8) * 2 : nullptr);
       }
     }
     tmem_ld_wait();
+    if (MODE == EPI_CONV && gn_smem != nullptr && d.gn_acc != nullptr) {
+      // merge the four warps' partials in a fixed order: one fp64 atomic pair per (chunk, group)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = row_in_tile;  // 0..127 -> (chunk, group, sum | sumsq)
+      const int c = e >> 4, g = (e >> 1) & 7, which = e & 1;
+      const int n = n0 + c * 32;
+      if (n < d.N && g < 32 / d.gn_cpg) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) tot += gn_smem[((w * 8 + c) * 8 + g) * 2 + which];
+        int ot, oc;
+        conv_out_coord(d, r.ct, n, &ot, &oc);
+        if (ot >= 0)
+          atomicAdd(gn_replica(d) + (static_cast<long long>(ot) * (d.out_C / d.gn_cpg) + oc / d.gn_cpg + g) * 2 + which,
+                    static_cast<double>(tot));
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // partials may be overwritten by the next tile
+    }
   }
 }
 
@@ -392,6 +483,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const Ti
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual);
   const long long frame_off = (static_cast<long long>(tc.b) * d.cT + ct) * d.cH;
   if (quarter * 32 >= d.N) return;  // warp-uniform: no live channel in this lane quarter
+  float gsum = 0.f, gsq = 0.f;      // fused GroupNorm statistics of this thread's channel
   uint32_t buf[2][32];
   tmem_ld_32x32(taddr_row, buf[0]);
 #pragma unroll
@@ -412,11 +504,28 @@ __device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const Ti
           v[i] += __bfloat162float(res[row_off + static_cast<long long>(i) * d.out_C]);
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        out[row_off + static_cast<long long>(i) * d.out_C] = __float2bfloat16(v[i]);
+      for (int i = 0; i < 16; ++i) {
+        const __nv_bfloat16 q = __float2bfloat16(v[i]);
+        out[row_off + static_cast<long long>(i) * d.out_C] = q;
+        const float x = __bfloat162float(q);
+        gsum += x;
+        gsq += x * x;
+      }
     }
   }
   tmem_ld_wait();
+  if (d.gn_acc != nullptr) {
+    // channels of a group sit on adjacent lanes: fold them, one fp64 atomic pair per group
+    for (int o = 1; o < d.gn_cpg; o <<= 1) {
+      gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+      gsq += __shfl_xor_sync(0xffffffffu, gsq, o);
+    }
+    if (c_ok && (c % d.gn_cpg) == 0) {
+      double* acc = gn_replica(d) + (static_cast<long long>(ct) * (d.out_C / d.gn_cpg) + c / d.gn_cpg) * 2;
+      atomicAdd(acc, static_cast<double>(gsum));
+      atomicAdd(acc + 1, static_cast<double>(gsq));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------
@@ -582,7 +691,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (MODE == EPI_CONV && a.swap)
           epilogue_tile_swapped(a, tc, tmem_base + as * BN, quarter, lane);
         else
-          epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter);
+          epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter,
+                                   reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarBytes));
         tc_fence_before();
         mbar_arrive(&tmem_empty[as]);
       }
@@ -633,7 +743,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const uint32_t part0 = smem_u32(smem);
       for (int c = group; c < BN / W; c += k.splits) {
         const int n = tc.n_tile * BN + c * W;
-        if (n >= d.N || !r.ok) continue;
+        // (conv rows always enter when the warp is uniform: warp-wide GroupNorm reduction)
+        if (n >= d.N || (!r.ok && !(MODE == EPI_CONV && rows_per >= 32))) continue;
         float v[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) v[i] = 0.f;
@@ -650,7 +761,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             v[4 * i + 3] += q.w;
           }
         }
-        epi_row<MODE, W>(a, r, n, v);
+        epi_row<MODE, W>(a, r, n, v, rows_per >= 32);
       }
     }
     // nobody leaves while a peer may still read its shared memory
@@ -675,7 +786,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 // ------------------------------------------------------------------------------
 constexpr int kPairStages = 6;
 constexpr int kPairStageBytes = kABytes + kBBytes / 2;  // 32 KB
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kBarBytes + 1024;
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kBarBytes + kGnBytes + 1024;
 
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst,
                                                  int c0, int c1) {
@@ -900,7 +1011,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
       const TileCoord tc = decode_pair_tile(a, tile, rank);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
-      epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter);
+      epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter,
+                               reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + kBarBytes));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0));

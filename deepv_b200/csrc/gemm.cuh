@@ -74,6 +74,12 @@ struct GemmDesc {
   int conv_drop_first;         // INTERLEAVE_T: drop output frame 0 (vae.py:408-409)
   const void* residual;        // bf16, same layout as out (PLAIN store only), may be null
   int out_C;                   // channels of the stored tensor (N, N/4 or N/2)
+  // CONV: optional fused GroupNorm statistics of the STORED tensor (vae.py:161-167): the epilogue
+  // adds sum / sum of squares of the bf16-rounded outputs into gn_acc[(frame * G + group) * 2 + {0,1}]
+  double* gn_acc;              // fp64 accumulators (zeroed by the caller), or null
+  int gn_cpg;                  // channels per group of the stored tensor (4, 8 or 16)
+  int gn_replicas;             // accumulator copies (CTA i adds into copy i % replicas; the reader
+  long long gn_replica_stride; //   sums them) — spreads the same-address atomics; stride in doubles
 };
 
 // Enqueue on `stream`.  Returns 0 or a negative error (see dv_last_error()).

@@ -75,8 +75,9 @@ int launch_block_noise(const float* z, void* out, int planes, int h, int w, floa
 
 // ---- VAE elementwise (vae_kernels.cu) ---------------------------------------------------
 // y = silu?( (x - mean) * rstd * gamma + beta ) over channels-last bf16 [frames][HW][C]
-int launch_gn_apply(const __nv_bfloat16* x, const float* stats, const float* gamma,
-                    const float* beta, __nv_bfloat16* y, int frames, int HW, int C, int G, int silu,
-                    cudaStream_t stream);
+// acc: `replicas` copies (stride in doubles) of [frames][G][2] fp64 (sum, sum of squares)
+int launch_gn_apply(const __nv_bfloat16* x, const double* acc, int replicas, long long replica_stride,
+                    const float* gamma, const float* beta, __nv_bfloat16* y, int frames, int HW, int C,
+                    int G, float eps, int silu_on, cudaStream_t stream);
 
 }  // namespace dv

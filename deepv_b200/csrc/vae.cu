@@ -24,8 +24,8 @@
 using namespace dv;
 
 namespace dv {
-int launch_gn_stats(const __nv_bfloat16* x, double* acc, float* stats, int frames, int HW, int C,
-                    int G, float eps, cudaStream_t stream);
+int launch_gn_stats(const __nv_bfloat16* x, double* acc, int frames, int HW, int C, int G,
+                    cudaStream_t stream);
 int launch_softmax_rows(const float* s, __nv_bfloat16* p, long long rows, int cols, float scale,
                         cudaStream_t stream);
 int launch_transpose(const __nv_bfloat16* in, int ld_in, __nv_bfloat16* out, int frames, int rows,
@@ -61,8 +61,11 @@ struct dv_vae_plan {
   long long buf_elems = 0;
   __nv_bfloat16 *qk = nullptr, *vt = nullptr, *pr = nullptr;
   float* sc = nullptr;
+  // GroupNorm (sum, sumsq) accumulators: one slot of [frames][groups][2] fp64 per normalised tensor
+  // of a tile run, zeroed by one memset per tile; filled by the producing conv's epilogue
   double* gn_acc = nullptr;
-  float* gn_stats = nullptr;
+  int gn_slots = 0, gn_slot_elems = 0, gn_replica_elems = 0;
+  static constexpr int kGnReplicas = 8;
   float* taps = nullptr;        // conv_out per-tap planes [32][T*H*W][4] fp32 of the largest tile
   long long taps_elems = 0;
   TileOut* tiles_dev = nullptr;
@@ -139,6 +142,7 @@ int plan_alloc(dv_vae_plan* p, T** out, long long n) {
 struct Act {  // channels-last activation
   __nv_bfloat16* p;
   int T, H, W, C;
+  double* gn = nullptr;  // GroupNorm statistics accumulated by the producer, or null
   long long elems() const { return static_cast<long long>(T) * H * W * C; }
 };
 
@@ -149,6 +153,15 @@ struct Runner {
   double flops = 0;
   bool dry = false;  // count flops / buffer sizes only
   long long max_elems = 0;
+  int gn_slot = 0;   // next free accumulator slot of this tile run
+  double* new_gn_slot() {
+    const int i = gn_slot++;
+    if (dry) {
+      if (gn_slot > pl->gn_slots) pl->gn_slots = gn_slot;
+      return nullptr;
+    }
+    return pl->gn_acc + static_cast<long long>(i) * pl->gn_slot_elems;
+  }
 
   const void* W(const std::string& n) {
     const void* p = pl->v->get(n);
@@ -161,8 +174,9 @@ struct Runner {
   void note(const Act& a) { max_elems = a.elems() > max_elems ? a.elems() : max_elems; }
 
   // causal conv (vae.py:225-252) as implicit GEMM
+  // `stats`: also accumulate the GroupNorm statistics of the output (its consumer is a norm)
   Act conv(const std::string& name, const Act& x, int cout, int ks, int store, int drop_first,
-           const __nv_bfloat16* residual, __nv_bfloat16* outbuf, int w_rows = -1) {
+           const __nv_bfloat16* residual, __nv_bfloat16* outbuf, int w_rows = -1, bool stats = false) {
     Act y;
     y.p = outbuf;
     y.T = x.T;
@@ -179,10 +193,16 @@ struct Runner {
     }
     note(y);
     flops += 2.0 * x.T * x.H * x.W * cout * static_cast<double>(ks * ks * ks) * x.C;
+    const int G = pl->v->cfg.norm_groups;
+    if (stats && y.C % G == 0 && (y.C / G == 4 || y.C / G == 8 || y.C / G == 16)) y.gn = new_gn_slot();
     if (dry || rc) return y;
     GemmDesc d = {};
     d.batch = 1;
     d.N = cout;
+    d.gn_acc = y.gn;
+    d.gn_cpg = y.gn ? y.C / G : 0;
+    d.gn_replicas = dv_vae_plan::kGnReplicas;
+    d.gn_replica_stride = pl->gn_replica_elems;
     d.A = x.p;
     d.a_mode = 1;
     d.cT = x.T;
@@ -207,13 +227,21 @@ struct Runner {
   Act gn(const std::string& name, const Act& x, bool act, __nv_bfloat16* outbuf) {
     Act y = x;
     y.p = outbuf;
+    y.gn = nullptr;
+    if (dry && x.gn == nullptr) new_gn_slot();  // (sizes the accumulator ring)
     if (dry || rc) return y;
     const int G = pl->v->cfg.norm_groups;
-    rc = launch_gn_stats(x.p, pl->gn_acc, pl->gn_stats, x.T, x.H * x.W, x.C, G, 1e-6f, st);
+    const double* acc = x.gn;
+    if (acc == nullptr) {  // producer without fused statistics: one read pass
+      double* slot = new_gn_slot();
+      rc = launch_gn_stats(x.p, slot, x.T, x.H * x.W, x.C, G, st);
+      acc = slot;
+    }
     if (rc == 0)
-      rc = launch_gn_apply(x.p, pl->gn_stats, reinterpret_cast<const float*>(W(name + ".weight")),
+      rc = launch_gn_apply(x.p, acc, dv_vae_plan::kGnReplicas, pl->gn_replica_elems,
+                           reinterpret_cast<const float*>(W(name + ".weight")),
                            reinterpret_cast<const float*>(W(name + ".bias")), outbuf, x.T, x.H * x.W,
-                           x.C, G, act ? 1 : 0, st);
+                           x.C, G, 1e-6f, act ? 1 : 0, st);
     return y;
   }
 
@@ -221,14 +249,14 @@ struct Runner {
   Act resnet(const std::string& name, const Act& x, int cout, int ia, int ib, int iout) {
     __nv_bfloat16** B = pl->buf;
     Act a = gn(name + ".norm1", x, true, B[ia]);
-    Act h = conv(name + ".conv1.conv", a, cout, 3, CONV_PLAIN, 0, nullptr, B[ib]);
+    Act h = conv(name + ".conv1.conv", a, cout, 3, CONV_PLAIN, 0, nullptr, B[ib], -1, true);
     Act a2 = gn(name + ".norm2", h, true, B[ia]);
     const __nv_bfloat16* res = x.p;
     if (x.C != cout) {
       Act sc = conv(name + ".conv_shortcut.conv", x, cout, 1, CONV_PLAIN, 0, nullptr, B[ib]);
       res = sc.p;  // conv1's output (in B[ib]) has been consumed by norm2 already
     }
-    return conv(name + ".conv2.conv", a2, cout, 3, CONV_PLAIN, 0, res, B[iout]);
+    return conv(name + ".conv2.conv", a2, cout, 3, CONV_PLAIN, 0, res, B[iout], -1, true);
   }
 
   // diffusers Attention of the mid block (vae.py:439-445,463-467): per frame, one head of width C
@@ -239,6 +267,7 @@ struct Runner {
     flops += 2.0 * F * pix * C * C * 4 + 4.0 * F * pix * static_cast<double>(pix) * C;
     Act y = x;
     y.p = B[iout];
+    y.gn = nullptr;  // the attention output has no fused statistics
     note(y);
     if (dry || rc) return y;
     auto dense = [&](const void* A, long long abs_, int lda, const void* Wp, int wrows, long long wbs,
@@ -320,12 +349,18 @@ static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, c
   Act x{B[0], p->T, th, tw, 64};
   r.note(x);
   if (!dry) {
+    cudaError_t e = cudaMemsetAsync(p->gn_acc, 0,
+                                    static_cast<size_t>(p->gn_slots + 1) * p->gn_slot_elems * sizeof(double), st);
+    if (e != cudaSuccess) {
+      set_error("vae: memset of the GroupNorm accumulators: %s", cudaGetErrorString(e));
+      return DV_ERR_CUDA;
+    }
     r.rc = launch_latent_tile(z, z_bf16, B[0], c.latent_channels, p->T, p->h, p->w, y0, x0, th, tw, 64, st);
   }
   const int top = c.block_channels[3];
   // post_quant_conv (1x1x1, output padded to 64 channels so it can feed conv_in's TMA boxes)
   x = r.conv("post_quant_conv.conv", x, 64, 1, CONV_PLAIN, 0, nullptr, B[1], 64);
-  x = r.conv("decoder.conv_in.conv", x, top, 3, CONV_PLAIN, 0, nullptr, B[0]);
+  x = r.conv("decoder.conv_in.conv", x, top, 3, CONV_PLAIN, 0, nullptr, B[0], -1, true);
   // buffers: x in B[0]; scratch B[1], B[2]; result B[3] -> rotate
   int cur = 0;
   auto other = [&](int k) { return (cur + k) & 3; };
@@ -346,12 +381,12 @@ static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, c
     }
     if (c.spatial_up[i]) {
       x = r.conv("decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv.conv", x, co * 4, 3,
-                 CONV_SHUFFLE_HW, 0, nullptr, B[other(1)]);
+                 CONV_SHUFFLE_HW, 0, nullptr, B[other(1)], -1, !c.temporal_up[i]);
       cur = other(1);
     }
     if (c.temporal_up[i]) {
       x = r.conv("decoder.up_blocks." + std::to_string(i) + ".temporal_upsamplers.0.conv.conv", x,
-                 co * 2, 3, CONV_INTERLEAVE_T, 1, nullptr, B[other(1)]);
+                 co * 2, 3, CONV_INTERLEAVE_T, 1, nullptr, B[other(1)], -1, true);
       cur = other(1);
     }
   }
@@ -448,9 +483,11 @@ extern "C" int dv_vae_plan_create(dv_vae* v, int T, int h, int w, int tile_laten
   if ((rc = plan_alloc(p, &p->sc, static_cast<long long>(T) * pix * pix)) != 0) return fail(rc);
   if ((rc = plan_alloc(p, &p->pr, static_cast<long long>(T) * pix * pix)) != 0) return fail(rc);
   const int max_frames = 8 * T + 8;
-  if ((rc = plan_alloc(p, &p->gn_acc, static_cast<long long>(max_frames) * 64 * 2)) != 0) return fail(rc);
-  if ((rc = plan_alloc(p, &p->gn_stats, static_cast<long long>(max_frames) * 64 * 2)) != 0) return fail(rc);
-  cudaError_t e = cudaMemset(p->gn_acc, 0, static_cast<size_t>(max_frames) * 64 * 2 * sizeof(double));
+  p->gn_replica_elems = max_frames * 64 * 2;
+  p->gn_slot_elems = dv_vae_plan::kGnReplicas * p->gn_replica_elems;
+  if ((rc = plan_alloc(p, &p->gn_acc, static_cast<long long>(p->gn_slots + 1) * p->gn_slot_elems)) != 0)
+    return fail(rc);
+  cudaError_t e = cudaSuccess;
   if ((rc = plan_alloc(p, &p->taps, p->taps_elems)) != 0) return fail(rc);
   for (auto& to : p->tiles) {
     if ((rc = plan_alloc(p, &to.px, static_cast<long long>(p->Tout) * to.H * to.W * 3)) != 0)

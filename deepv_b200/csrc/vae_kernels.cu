@@ -80,19 +80,6 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloa
   }
 }
 
-__global__ void gn_finalize_kernel(double* __restrict__ acc, float* __restrict__ stats, int n,
-                                   double inv_count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double mean = acc[2 * i] * inv_count;
-  double var = acc[2 * i + 1] * inv_count - mean * mean;
-  var = var < 0.0 ? 0.0 : var;
-  stats[2 * i] = static_cast<float>(mean);
-  stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  acc[2 * i] = 0.0;  // leave the accumulator clean for the next use
-  acc[2 * i + 1] = 0.0;
-}
-
 __device__ __forceinline__ float silu_fast(float x) {
   return __fdividef(x, 1.0f + __expf(-x));
 }
@@ -100,7 +87,9 @@ __device__ __forceinline__ float silu_fast(float x) {
 // y = silu?( (x - mean) * rstd * gamma + beta ): same thread -> channel-vector mapping as the
 // statistics pass, so the per-channel affine a*x + b is hoisted out of the pixel loop.
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              const float* __restrict__ stats,
+                                                              const double* __restrict__ acc,
+                                                              int replicas, long long replica_stride,
+                                                              double inv_count, float eps,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta,
                                                               __nv_bfloat16* __restrict__ y, int HW,
@@ -114,11 +103,28 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat1
   const int v = threadIdx.x % vec_per_pix;
   const int pstep = kGnThreads / vec_per_pix;
   const int c0 = v * 8;
+  // mean / rstd of this frame's groups once per CTA: (sum, sum of squares) over the accumulator
+  // replicas -> mean, 1/sqrt(var + eps) in fp64 (biased variance)
+  __shared__ float2 s_ms[64];
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    double sx = 0.0, sy = 0.0;
+    for (int rp = 0; rp < replicas; ++rp) {
+      const double2 sq = __ldg(reinterpret_cast<const double2*>(acc + rp * replica_stride) +
+                               static_cast<long long>(f) * G + g);
+      sx += sq.x;
+      sy += sq.y;
+    }
+    const double mean = sx * inv_count;
+    double var = sy * inv_count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_ms[g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  }
+  __syncthreads();
   float a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int g = (c0 + k) / cpg;
-    const float2 ms = __ldg(reinterpret_cast<const float2*>(stats) + static_cast<long long>(f) * G + g);
+    const float2 ms = s_ms[(c0 + k) / cpg];
     const float gm = __ldg(gamma + c0 + k);
     a[k] = ms.y * gm;
     b[k] = __ldg(beta + c0 + k) - ms.x * a[k];
@@ -286,8 +292,8 @@ static int gn_pix_per_cta(int HW, int frames, int C) {
   return ppc;
 }
 
-int launch_gn_stats(const __nv_bfloat16* x, double* acc, float* stats, int frames, int HW, int C,
-                    int G, float eps, cudaStream_t stream) {
+int launch_gn_stats(const __nv_bfloat16* x, double* acc, int frames, int HW, int C, int G,
+                    cudaStream_t stream) {
   DV_REQUIRE(C % 8 == 0 && G <= 64 && C % G == 0, "gn_stats: C=%d G=%d", C, G);
   const int cpg = C / G;
   DV_REQUIRE(cpg == 4 || cpg % 8 == 0, "gn_stats: %d channels per group unsupported", cpg);
@@ -297,22 +303,20 @@ int launch_gn_stats(const __nv_bfloat16* x, double* acc, float* stats, int frame
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(frames) * HW * C * 2.0, stream, "gn_stats");
   gn_partial_kernel<<<grid, kGnThreads, 0, stream>>>(x, acc, HW, C, G, ppc);
   DV_CHECK_CUDA(cudaGetLastError());
-  const int n = frames * G;
-  gn_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(
-      acc, stats, n, 1.0 / (static_cast<double>(HW) * cpg), eps);
-  DV_CHECK_CUDA(cudaGetLastError());
-  note_launch(2);
+  note_launch();
   return 0;
 }
 
-int launch_gn_apply(const __nv_bfloat16* x, const float* stats, const float* gamma,
-                    const float* beta, __nv_bfloat16* y, int frames, int HW, int C, int G, int silu_on,
-                    cudaStream_t stream) {
+int launch_gn_apply(const __nv_bfloat16* x, const double* acc, int replicas, long long replica_stride,
+                    const float* gamma, const float* beta, __nv_bfloat16* y, int frames, int HW, int C,
+                    int G, float eps, int silu_on, cudaStream_t stream) {
   DV_REQUIRE(C % 8 == 0 && C % G == 0 && kGnThreads % (C / 8) == 0, "gn_apply: C=%d G=%d", C, G);
   const int ppc = gn_pix_per_cta(HW, frames, C);
   dim3 grid((HW + ppc - 1) / ppc, frames);
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(frames) * HW * C * 4.0, stream, "gn_apply");
-  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, stats, gamma, beta, y, HW, C, G, silu_on, ppc);
+  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, acc, replicas, replica_stride,
+                                                   1.0 / (static_cast<double>(HW) * (C / G)), eps,
+                                                   gamma, beta, y, HW, C, G, silu_on, ppc);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;
