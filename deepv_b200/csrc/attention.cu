@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int HD = a.H * kD;
+  pdl_wait();  // (kv_end is plan data written long before; everything above overlapped the predecessor)
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
     }
   }
 
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -415,7 +417,7 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   char tag[56] = "";
   if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d", B, L, H);
   const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);
-  attn_kernel<<<grid, kAttnThreads, kSmemBytes, stream>>>(a);
+  DV_CHECK_CUDA(launch_pdl(attn_kernel, grid, dim3(kAttnThreads), kSmemBytes, stream, 1, a));
   prof_end(pid, stream);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -164,6 +165,11 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
   DV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r,
              rank);
   return 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("DV_NO_PDL") == nullptr;
+  return on;
 }
 
 int sm_count() {

@@ -268,6 +268,17 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- programmatic dependent launch ------------------------------------------------
+// A kernel launched with the programmatic-serialization attribute may start (prologue: barrier
+// init, TMEM allocation, descriptor prefetch) while its predecessor in the stream drains.
+// pdl_wait(): block until the predecessor has completed and its writes are visible — EVERY such
+// kernel executes it before touching global memory.  pdl_trigger(): this CTA is done with its main
+// work; once all CTAs have triggered (or exited) the successor may be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- small math ---------------------------------------------------------------
 __device__ __forceinline__ float gelu_tanh(float x) {
   // 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))
@@ -298,5 +309,36 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
 
 int sm_count();
+bool pdl_enabled();  // false when DV_NO_PDL is set
+
+#if defined(__CUDACC__)
+// Launch with the programmatic-dependent-launch attribute (+ an optional cluster dimension).
+template <typename... KP, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
+}
+#endif
 
 }  // namespace dv

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant_
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int rows0 = a.B * a.seg[0].L;
+  pdl_wait();
   if (warp >= rows0 + a.B * a.seg[1].L) return;
   const bool second = warp >= rows0;
   if (second) warp -= rows0;
@@ -320,9 +321,9 @@ int launch_ln_modulate2(const LnRows& r0, const LnRows* r1, int mod_bs, int B, i
   const int blocks = static_cast<int>((rows * 32 + 255) / 256);
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(rows) * D * 6.0, stream, "ln_modulate");
   if (D == 1536)
-    ln_modulate_kernel<1536><<<blocks, 256, 0, stream>>>(a);
+    DV_CHECK_CUDA(launch_pdl(ln_modulate_kernel<1536>, dim3(blocks), dim3(256), 0, stream, 1, a));
   else
-    ln_modulate_kernel<512><<<blocks, 256, 0, stream>>>(a);
+    DV_CHECK_CUDA(launch_pdl(ln_modulate_kernel<512>, dim3(blocks), dim3(256), 0, stream, 1, a));
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;

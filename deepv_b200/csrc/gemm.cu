@@ -30,7 +30,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter: each takes half of a tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
@@ -402,10 +403,11 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
 
 // Accumulator tile in TMEM -> epilogue, 32 columns in flight while 32 are processed.
 // gn_smem: [4 warps][8 chunks][8 groups][2] floats for the fused GroupNorm statistics (conv only)
+// `half`: which 128 of the tile's 256 columns this warp handles (two warps share a lane quarter)
 template <int MODE>
 __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileCoord& tc,
                                                    uint32_t tmem_acc, int row_in_tile, int quarter,
-                                                   float* gn_smem = nullptr) {
+                                                   int half, float* gn_smem = nullptr) {
   constexpr int W = EpiW<MODE>::value;
   const GemmDesc& d = a.d;
   const RowCtx r = make_row(a, tc, row_in_tile);
@@ -413,7 +415,7 @@ __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileC
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
   if constexpr (W == 64) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 64; ++c) {
+    for (int c = half * (BN / 128); c < (half + 1) * (BN / 128); ++c) {
       const int n = n0 + c * 64;
       if (n >= d.N) break;  // warp-uniform
       uint32_t r0[32], r1[32];
@@ -430,27 +432,29 @@ __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileC
     }
   } else {
     uint32_t buf[2][32];
-    tmem_ld_32x32(taddr, buf[0]);
+    const int c0 = half * (BN / 64);  // 4 chunks of 32 columns per warp
+    tmem_ld_32x32(taddr + c0 * 32, buf[0]);
 #pragma unroll
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int cc = 0; cc < BN / 64; ++cc) {
+      const int c = c0 + cc;
       const int n = n0 + c * 32;
       tmem_ld_wait();
-      if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, buf[(c + 1) & 1]);
+      if (cc + 1 < BN / 64) tmem_ld_32x32(taddr + (c + 1) * 32, buf[(cc + 1) & 1]);
       if (n < d.N && (r.ok || MODE == EPI_CONV)) {  // conv rows always enter: warp-wide GN reduction
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(buf[c & 1][i]);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(buf[cc & 1][i]);
         epi_row<MODE, 32>(a, r, n, v, true, gn_smem ? gn_smem + ((quarter * 8 + c) * 8) * 2 : nullptr);
       }
     }
     tmem_ld_wait();
     if (MODE == EPI_CONV && gn_smem != nullptr && d.gn_acc != nullptr) {
       // merge the four warps' partials in a fixed order: one fp64 atomic pair per (chunk, group)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = row_in_tile;  // 0..127 -> (chunk, group, sum | sumsq)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      const int e = row_in_tile;  // 0..127 -> (chunk, group, sum | sumsq); the first four warps flush
       const int c = e >> 4, g = (e >> 1) & 7, which = e & 1;
       const int n = n0 + c * 32;
-      if (n < d.N && g < 32 / d.gn_cpg) {
+      if (half == 0 && n < d.N && g < 32 / d.gn_cpg) {
         float tot = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) tot += gn_smem[((w * 8 + c) * 8 + g) * 2 + which];
@@ -460,7 +464,7 @@ __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileC
           atomicAdd(gn_replica(d) + (static_cast<long long>(ot) * (d.out_C / d.gn_cpg) + oc / d.gn_cpg + g) * 2 + which,
                     static_cast<double>(tot));
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // partials may be overwritten by the next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // partials may be overwritten by the next tile
     }
   }
 }
@@ -469,7 +473,8 @@ __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileC
 // 16x16 tile (w fastest).  One thread owns one channel; for every pixel the warp writes a
 // contiguous run of 32 channels (64 B) into the NDHWC output.  Plain store mode only.
 __device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const TileCoord& tc,
-                                                      uint32_t tmem_acc, int quarter, int lane) {
+                                                      uint32_t tmem_acc, int quarter, int lane,
+                                                      int half) {
   const GemmDesc& d = a.d;
   const int per_frame = a.tiles_w * a.tiles_h;
   const int ct = tc.m_tile / per_frame;
@@ -485,19 +490,20 @@ __device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const Ti
   if (quarter * 32 >= d.N) return;  // warp-uniform: no live channel in this lane quarter
   float gsum = 0.f, gsq = 0.f;      // fused GroupNorm statistics of this thread's channel
   uint32_t buf[2][32];
-  tmem_ld_32x32(taddr_row, buf[0]);
+  tmem_ld_32x32(taddr_row + half * 128, buf[0]);
 #pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {  // 8 chunks of 32 pixels = 2 tile rows each
+  for (int ci = 0; ci < 4; ++ci) {  // this warp's 4 of the 8 chunks of 32 pixels (2 tile rows each)
+    const int cc = half * 4 + ci;
     tmem_ld_wait();
-    if (cc + 1 < 8) tmem_ld_32x32(taddr_row + (cc + 1) * 32, buf[(cc + 1) & 1]);
+    if (ci + 1 < 4) tmem_ld_32x32(taddr_row + (cc + 1) * 32, buf[(ci + 1) & 1]);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int oh = h0 + cc * 2 + half;
+    for (int hr = 0; hr < 2; ++hr) {
+      const int oh = h0 + cc * 2 + hr;
       if (oh >= d.cH || !c_ok) continue;
       const long long row_off = ((frame_off + oh) * d.cW + w0) * d.out_C + c;
       float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(buf[cc & 1][half * 16 + i]) + bias;
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(buf[ci & 1][hr * 16 + i]) + bias;
       if (res != nullptr) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -560,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 32 * kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -571,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   // split-K: the cluster = the splits of ONE tile (grid = tiles * splits, one pass);
   // otherwise a persistent loop over tiles
@@ -676,7 +683,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     // ============================ epilogue ================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;   // which 128 columns of the tile
     const int row_in_tile = quarter * 32 + lane;
     if (!split_mode) {
       int it = 0;
@@ -689,9 +697,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(&tmem_full[as], aph);
         tc_fence_after();
         if (MODE == EPI_CONV && a.swap)
-          epilogue_tile_swapped(a, tc, tmem_base + as * BN, quarter, lane);
+          epilogue_tile_swapped(a, tc, tmem_base + as * BN, quarter, lane, half);
         else
-          epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter,
+          epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half,
                                    reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarBytes));
         tc_fence_before();
         mbar_arrive(&tmem_empty[as]);
@@ -707,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const Problem& a = problem_of(k, tile);
       const bool empty = split * a.kb_per_split >= a.k_blocks;  // tail split without k-blocks
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
         uint32_t raw[32];
         tmem_ld_32x32(taddr + c * 32, raw);
         tmem_ld_wait();
@@ -731,17 +739,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     cluster_sync_all();
     if (warp >= 2) {
       constexpr int W = EpiW<MODE>::value;
-      const int t = threadIdx.x - 64;      // 0..127
+      const int t = threadIdx.x - 64;      // 0..255
       const int rows_per = BM / k.splits;  // rows of the tile this CTA finishes
       const int row_in_tile = split * rows_per + (t % rows_per);
-      const int group = t / rows_per;      // 0..splits-1: which column chunks
+      const int group = t / rows_per;      // 0..2*splits-1: which column chunks
       int tile = tile0;
       const Problem& a = problem_of(k, tile);
       const GemmDesc& d = a.d;
       const TileCoord tc = decode_tile(a, tile, split);
       const RowCtx r = make_row(a, tc, row_in_tile);
       const uint32_t part0 = smem_u32(smem);
-      for (int c = group; c < BN / W; c += k.splits) {
+      for (int c = group; c < BN / W; c += 2 * k.splits) {
         const int n = tc.n_tile * BN + c * W;
         // (conv rows always enter when the warp is uniform: warp-wide GroupNorm reduction)
         if (n >= d.N || (!r.ok && !(MODE == EPI_CONV && rows_per >= 32))) continue;
@@ -769,6 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     cluster_sync_all();
   }
 
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -902,7 +911,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -912,6 +921,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
   cluster_sync_all();  // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int cluster_id = static_cast<int>(blockIdx.x) >> 1;
   const int n_clusters = static_cast<int>(gridDim.x) >> 1;
@@ -1001,6 +1011,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
   } else {
     // ============================ epilogue (both CTAs, own 128 rows) ==================
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     int it = 0;
     for (int gtile = cluster_id; gtile < k.total_pair_tiles; gtile += n_clusters, ++it) {
@@ -1011,7 +1022,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
       const TileCoord tc = decode_pair_tile(a, tile, rank);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
-      epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter,
+      epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half,
                                reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + kBarBytes));
       tc_fence_before();
       __syncwarp();
@@ -1019,6 +1030,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
     }
   }
 
+  pdl_trigger();
   tc_fence_before();
   __syncwarp();
   cluster_sync_all();  // the peer's MMAs / commits no longer touch this CTA
@@ -1036,23 +1048,9 @@ int launch_mode(const KArgs& ka, cudaStream_t stream) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  if (ka.splits > 1) {
-    cfg.gridDim = dim3(ka.total_tiles * ka.splits);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ka.splits;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  } else {
-    cfg.gridDim = dim3(ka.total_tiles < sm_count() ? ka.total_tiles : sm_count());
-  }
-  DV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE>, ka));
+  const dim3 grid(ka.splits > 1 ? ka.total_tiles * ka.splits
+                                : (ka.total_tiles < sm_count() ? ka.total_tiles : sm_count()));
+  DV_CHECK_CUDA(launch_pdl(gemm_tc_kernel<MODE>, grid, dim3(kThreads), kSmemBytes, stream, ka.splits, ka));
   note_launch();
   return 0;
 }
@@ -1067,19 +1065,8 @@ int launch_pair_mode(const KArgs& ka, cudaStream_t stream) {
   }
   const int max_clusters = sm_count() / 2;
   const int clusters = ka.total_pair_tiles < max_clusters ? ka.total_pair_tiles : max_clusters;
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kThreads);
-  cfg.gridDim = dim3(2 * clusters);
-  cfg.dynamicSmemBytes = kPairSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  DV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<MODE>, ka));
+  DV_CHECK_CUDA(launch_pdl(gemm_pair_kernel<MODE>, dim3(2 * clusters), dim3(kThreads), kPairSmemBytes,
+                           stream, 2, ka));
   note_launch();
   return 0;
 }

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat1
   // mean / rstd of this frame's groups once per CTA: (sum, sum of squares) over the accumulator
   // replicas -> mean, 1/sqrt(var + eps) in fp64 (biased variance)
   __shared__ float2 s_ms[64];
+  pdl_wait();
   if (threadIdx.x < G) {
     const int g = threadIdx.x;
     double sx = 0.0, sy = 0.0;
@@ -314,9 +315,9 @@ int launch_gn_apply(const __nv_bfloat16* x, const double* acc, int replicas, lon
   const int ppc = gn_pix_per_cta(HW, frames, C);
   dim3 grid((HW + ppc - 1) / ppc, frames);
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(frames) * HW * C * 4.0, stream, "gn_apply");
-  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(x, acc, replicas, replica_stride,
-                                                   1.0 / (static_cast<double>(HW) * (C / G)), eps,
-                                                   gamma, beta, y, HW, C, G, silu_on, ppc);
+  DV_CHECK_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(kGnThreads), 0, stream, 1, x, acc, replicas,
+                           replica_stride, 1.0 / (static_cast<double>(HW) * (C / G)), eps, gamma, beta, y,
+                           HW, C, G, silu_on, ppc));
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;
