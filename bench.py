@@ -324,13 +324,15 @@ def run_ours(args):
     gsz = args.group if args.group > 0 else (2 if world % 2 == 0 else 1)
     shard = Shard.grouped(gsz) if world > 1 else Shard(0, 1, None)
     n_rollouts = world // gsz if world > 1 else 1
+    if world > 1:
+        shard.setup_sp(dev)   # CFG branch groups x Ulysses ranks inside every rollout group
 
     def step(units, dec, fetch):
         outs = []
         for d in units:
             # one rollout sharded over the ranks: CFG branches on different GPUs when there are enough
             # ranks (all-gather of the branch predictions per step), else the whole CFG batch locally
-            sh = shard if (shard.active and shard.world >= d["n_branch"]) else None
+            sh = shard if shard.active else None
             lat = pipe.generate_one_unit(d["latents"], d["history"], d["cond_tensors"], d["enc"], d["mask"],
                                          d["pooled"], STEPS_PER_STAGE, block_noise=d["block_noise"], shard=sh)
             outs.append(lat[-1])
@@ -451,8 +453,9 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args, {"parallelism": (
-                    f"{n_rollouts} rollout(s) x {gsz} GPU(s) each: CFG branches split over the group (all-gather of the "
-                    f"branch predictions per step), VAE tiles x modalities dealt over the group (tile broadcast)"
+                    f"{n_rollouts} rollout(s) x {gsz} GPU(s) each: CFG branches on sub-groups (all-gather of the branch "
+                    f"predictions per step) x Ulysses sequence parallelism inside a branch (all-to-all of heads<->tokens "
+                    f"around every attention, NCCL), VAE tiles x modalities dealt over the group (tile broadcast)"
                     if world > 1 else "single GPU")}),
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "clock_rejected": bool(bad),
                 "roofline": roofline, "cpu_baseline": cpu,

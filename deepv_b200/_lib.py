@@ -83,6 +83,11 @@ SIGNATURES = {
     "dv_mmdit_plan_workspace_bytes": (_ll, [_vp]),
     "dv_mmdit_plan_flops": (_d, [_vp]),
     "dv_mmdit_forward": (_i, [_vp, _PP, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dv_mmdit_plan_set_sp": (_i, [_vp, _i, _i, _vp, _vp]),
+    "dv_comm_unique_id": (_i, [C.c_char_p, _vp]),
+    "dv_comm_create": (_i, [C.c_char_p, _vp, _i, _i, C.POINTER(_vp)]),
+    "dv_comm_destroy": (None, [_vp]),
+    "dv_comm_exchange": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "dv_vae_create": (_i, [C.POINTER(VAEConfig), C.POINTER(TensorRef), _i, C.POINTER(_vp)]),
     "dv_vae_destroy": (None, [_vp]),
     "dv_vae_plan_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),

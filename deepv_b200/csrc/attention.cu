@@ -56,7 +56,8 @@ struct AttnArgs {
   const int* kv_end;              // [L]
   const float* key_bias;          // [B][Lpad]: 0 live, -inf dead / beyond L (Lpad % 128 == 0)
   const int* tile_dead;           // [B][Lpad/128]: tile holds a dead key (nullptr: assume yes)
-  int L, Lpad, H, B;
+  int L, Lpad, H, B;              // H = heads in the qkv / out rows
+  int head0;                      // first head this launch handles (Ulysses: a rank's head slice)
   float scale_log2;               // head_dim^-0.5 * log2(e)
 };
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   // heaviest query tiles first: later frames see more keys
   const int qt = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
   const int q0 = qt * kTile;
-  const int head = blockIdx.y;
+  const int head = a.head0 + static_cast<int>(blockIdx.y);
   const int b = blockIdx.z;
 
   // keys needed by this query tile (kv_end is non-decreasing in q)
@@ -388,7 +389,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
                      const int* tile_dead, int B, int L, int Lpad, int H, cudaStream_t stream,
-                     double flops) {
+                     double flops, int head0, int n_heads) {
+  if (n_heads <= 0) n_heads = H;
+  DV_REQUIRE(head0 >= 0 && head0 + n_heads <= H, "attention: heads [%d, %d) of %d", head0, head0 + n_heads, H);
   DV_REQUIRE(Lpad % 128 == 0 && Lpad >= L, "attention: Lpad=%d must be a multiple of 128 >= L=%d",
              Lpad, L);
   DV_REQUIRE(B > 0 && L > 0 && H > 0, "attention: empty problem B=%d L=%d H=%d", B, L, H);
@@ -406,6 +409,7 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   a.Lpad = Lpad;
   a.H = H;
   a.B = B;
+  a.head0 = head0;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
@@ -413,7 +417,7 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
                                        kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((L + kTile - 1) / kTile, H, B);
+  dim3 grid((L + kTile - 1) / kTile, n_heads, B);
   char tag[56] = "";
   if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d", B, L, H);
   const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);

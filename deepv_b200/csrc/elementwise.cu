@@ -291,6 +291,112 @@ __global__ void __launch_bounds__(128) key_bias_kernel(const float* __restrict__
   if (tile_dead != nullptr && threadIdx.x == 0) tile_dead[b * (Lpad / 128) + tile] = any;
 }
 
+// ---------------------------------------------------------------------------------
+// Ulysses sequence parallelism: staging copies around the all-to-all.
+// qkv [B][L][3D] / attn [B][L][D] are the joint buffers; rank r owns the video rows
+// [Lc + r*Lw, Lc + (r+1)*Lw) and the heads [r*Hc/64, ...) (Hc = columns per rank).
+// 16-byte vectors; one thread per vector.
+// ---------------------------------------------------------------------------------
+// stage[j][b][l][part][Hc] <- qkv[b][row0 + l][part*D + j*Hc + :]        (my rows, peer j's heads)
+__global__ void sp_qkv_pack_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ stage, int B,
+                                   int L, int D, int row0, int Lw, int P, int Hc) {
+  const int hv = Hc / 8, dv = D / 8;
+  const long long total = static_cast<long long>(P) * B * Lw * 3 * hv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % hv;
+  long long t = idx / hv;
+  const int part = t % 3;
+  t /= 3;
+  const int l = t % Lw;
+  t /= Lw;
+  const int b = t % B;
+  const int j = t / B;
+  stage[idx] = qkv[(static_cast<long long>(b) * L + row0 + l) * 3 * dv + part * dv + j * hv + c];
+}
+// qkv[b][Lc + i*Lw + l][part*D + r*Hc + :] <- stage[i][b][l][part][Hc]    (peer i's rows, my heads)
+__global__ void sp_qkv_unpack_kernel(const uint4* __restrict__ stage, uint4* __restrict__ qkv, int B,
+                                     int L, int D, int Lc, int Lw, int P, int Hc, int r) {
+  const int hv = Hc / 8, dv = D / 8;
+  const long long total = static_cast<long long>(P) * B * Lw * 3 * hv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % hv;
+  long long t = idx / hv;
+  const int part = t % 3;
+  t /= 3;
+  const int l = t % Lw;
+  t /= Lw;
+  const int b = t % B;
+  const int i = t / B;
+  if (i == r) return;  // my own rows are already in place
+  qkv[(static_cast<long long>(b) * L + Lc + i * Lw + l) * 3 * dv + part * dv + r * hv + c] = stage[idx];
+}
+// stage[j][b][row][Hc] <- attn[b][row < Lc ? row : Lc + j*Lw + (row - Lc)][r*Hc + :]
+//   (all context rows and peer j's video rows, my heads)
+__global__ void sp_attn_pack_kernel(const uint4* __restrict__ attn, uint4* __restrict__ stage, int B,
+                                    int L, int D, int Lc, int Lw, int P, int Hc, int r) {
+  const int hv = Hc / 8, dv = D / 8, rows = Lc + Lw;
+  const long long total = static_cast<long long>(P) * B * rows * hv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % hv;
+  long long t = idx / hv;
+  const int row = t % rows;
+  t /= rows;
+  const int b = t % B;
+  const int j = t / B;
+  const int src_row = row < Lc ? row : Lc + j * Lw + (row - Lc);
+  stage[idx] = attn[(static_cast<long long>(b) * L + src_row) * dv + r * hv + c];
+}
+// attn[b][row < Lc ? row : Lc + r*Lw + (row - Lc)][i*Hc + :] <- stage[i][b][row][Hc]
+__global__ void sp_attn_unpack_kernel(const uint4* __restrict__ stage, uint4* __restrict__ attn, int B,
+                                      int L, int D, int Lc, int Lw, int P, int Hc, int r) {
+  const int hv = Hc / 8, dv = D / 8, rows = Lc + Lw;
+  const long long total = static_cast<long long>(P) * B * rows * hv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % hv;
+  long long t = idx / hv;
+  const int row = t % rows;
+  t /= rows;
+  const int b = t % B;
+  const int i = t / B;
+  if (i == r) return;  // my own heads are already in place
+  const int dst_row = row < Lc ? row : Lc + r * Lw + (row - Lc);
+  attn[(static_cast<long long>(b) * L + dst_row) * dv + i * hv + c] = stage[idx];
+}
+// all-gather of the fp32 video stream: stage[j][b][l][D] <- x[b][r*Lw + l][:] (same block for every
+// peer), then x[b][i*Lw + l][:] <- stage[i][b][l][D]
+__global__ void sp_x_pack_kernel(const float4* __restrict__ x, float4* __restrict__ stage, int B, int Lv,
+                                 int D, int Lw, int P, int r) {
+  const int dv = D / 4;
+  const long long total = static_cast<long long>(P) * B * Lw * dv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % dv;
+  long long t = idx / dv;
+  const int l = t % Lw;
+  t /= Lw;
+  const int b = t % B;
+  stage[idx] = x[(static_cast<long long>(b) * Lv + r * Lw + l) * dv + c];
+}
+__global__ void sp_x_unpack_kernel(const float4* __restrict__ stage, float4* __restrict__ x, int B, int Lv,
+                                   int D, int Lw, int P, int r) {
+  const int dv = D / 4;
+  const long long total = static_cast<long long>(P) * B * Lw * dv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % dv;
+  long long t = idx / dv;
+  const int l = t % Lw;
+  t /= Lw;
+  const int b = t % B;
+  const int i = t / B;
+  if (i == r) return;
+  x[(static_cast<long long>(b) * Lv + i * Lw + l) * dv + c] = stage[idx];
+}
+
 }  // namespace
 
 int launch_ln_modulate2(const LnRows& r0, const LnRows* r1, int mod_bs, int B, int D, float eps,
@@ -440,5 +546,54 @@ int launch_key_bias(const float* ctx_mask, int Lc, float* key_bias, int* tile_de
   note_launch();
   return 0;
 }
+
+// ---- Ulysses staging copies ------------------------------------------------------------
+#define DV_SP_LAUNCH(kernel, total, ...)                                                  \
+  do {                                                                                    \
+    const long long _n = (total);                                                         \
+    if (_n > 0) {                                                                         \
+      kernel<<<static_cast<unsigned>((_n + 255) / 256), 256, 0, stream>>>(__VA_ARGS__);   \
+      DV_CHECK_CUDA(cudaGetLastError());                                                  \
+      note_launch();                                                                      \
+    }                                                                                     \
+  } while (0)
+
+int launch_sp_qkv_pack(const void* qkv, void* stage, int B, int L, int D, int row0, int Lw, int P,
+                       int Hc, cudaStream_t stream) {
+  DV_SP_LAUNCH(sp_qkv_pack_kernel, static_cast<long long>(P) * B * Lw * 3 * (Hc / 8),
+               reinterpret_cast<const uint4*>(qkv), reinterpret_cast<uint4*>(stage), B, L, D, row0, Lw, P, Hc);
+  return 0;
+}
+int launch_sp_qkv_unpack(const void* stage, void* qkv, int B, int L, int D, int Lc, int Lw, int P,
+                         int Hc, int r, cudaStream_t stream) {
+  DV_SP_LAUNCH(sp_qkv_unpack_kernel, static_cast<long long>(P) * B * Lw * 3 * (Hc / 8),
+               reinterpret_cast<const uint4*>(stage), reinterpret_cast<uint4*>(qkv), B, L, D, Lc, Lw, P, Hc, r);
+  return 0;
+}
+int launch_sp_attn_pack(const void* attn, void* stage, int B, int L, int D, int Lc, int Lw, int P,
+                        int Hc, int r, cudaStream_t stream) {
+  DV_SP_LAUNCH(sp_attn_pack_kernel, static_cast<long long>(P) * B * (Lc + Lw) * (Hc / 8),
+               reinterpret_cast<const uint4*>(attn), reinterpret_cast<uint4*>(stage), B, L, D, Lc, Lw, P, Hc, r);
+  return 0;
+}
+int launch_sp_attn_unpack(const void* stage, void* attn, int B, int L, int D, int Lc, int Lw, int P,
+                          int Hc, int r, cudaStream_t stream) {
+  DV_SP_LAUNCH(sp_attn_unpack_kernel, static_cast<long long>(P) * B * (Lc + Lw) * (Hc / 8),
+               reinterpret_cast<const uint4*>(stage), reinterpret_cast<uint4*>(attn), B, L, D, Lc, Lw, P, Hc, r);
+  return 0;
+}
+int launch_sp_x_pack(const float* x, void* stage, int B, int Lv, int D, int Lw, int P, int r,
+                     cudaStream_t stream) {
+  DV_SP_LAUNCH(sp_x_pack_kernel, static_cast<long long>(P) * B * Lw * (D / 4),
+               reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(stage), B, Lv, D, Lw, P, r);
+  return 0;
+}
+int launch_sp_x_unpack(const void* stage, float* x, int B, int Lv, int D, int Lw, int P, int r,
+                       cudaStream_t stream) {
+  DV_SP_LAUNCH(sp_x_unpack_kernel, static_cast<long long>(P) * B * Lw * (D / 4),
+               reinterpret_cast<const float4*>(stage), reinterpret_cast<float4*>(x), B, Lv, D, Lw, P, r);
+  return 0;
+}
+#undef DV_SP_LAUNCH
 
 }  // namespace dv

@@ -9,7 +9,7 @@ namespace dv {
 // tile_dead: [B][Lpad/128] "tile holds a dead key" flags from launch_key_bias, or nullptr
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
                      const int* tile_dead, int B, int L, int Lpad, int H, cudaStream_t stream,
-                     double flops = 0.0);
+                     double flops = 0.0, int head0 = 0, int n_heads = 0);
 
 // ---- MMDiT elementwise (elementwise.cu) -----------------------------------------------
 // out_bf16[b][l][:] = LN(x[b][l][:]) * (1 + scale[b][:]) + shift[b][:]   (eps inside sqrt)
@@ -79,5 +79,19 @@ int launch_block_noise(const float* z, void* out, int planes, int h, int w, floa
 int launch_gn_apply(const __nv_bfloat16* x, const double* acc, int replicas, long long replica_stride,
                     const float* gamma, const float* beta, __nv_bfloat16* y, int frames, int HW, int C,
                     int G, float eps, int silu_on, cudaStream_t stream);
+
+// ---- Ulysses sequence parallelism: staging copies around the all-to-all (elementwise.cu) ----
+int launch_sp_qkv_pack(const void* qkv, void* stage, int B, int L, int D, int row0, int Lw, int P,
+                       int Hc, cudaStream_t stream);
+int launch_sp_qkv_unpack(const void* stage, void* qkv, int B, int L, int D, int Lc, int Lw, int P,
+                         int Hc, int r, cudaStream_t stream);
+int launch_sp_attn_pack(const void* attn, void* stage, int B, int L, int D, int Lc, int Lw, int P,
+                        int Hc, int r, cudaStream_t stream);
+int launch_sp_attn_unpack(const void* stage, void* attn, int B, int L, int D, int Lc, int Lw, int P,
+                          int Hc, int r, cudaStream_t stream);
+int launch_sp_x_pack(const float* x, void* stage, int B, int Lv, int D, int Lw, int P, int r,
+                     cudaStream_t stream);
+int launch_sp_x_unpack(const void* stage, float* x, int B, int Lv, int D, int Lw, int P, int r,
+                       cudaStream_t stream);
 
 }  // namespace dv

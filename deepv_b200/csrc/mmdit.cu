@@ -54,6 +54,12 @@ struct dv_mmdit_plan {
   float *tfeat = nullptr, *g1 = nullptr, *g3 = nullptr, *temb = nullptr, *mod = nullptr;
   __nv_bfloat16 *xn = nullptr, *cn = nullptr, *qkv = nullptr, *attn = nullptr, *ffh = nullptr, *ffh_c = nullptr;
   __nv_bfloat16 *patch_a = nullptr, *hist_a = nullptr, *enc_bf = nullptr, *xo = nullptr;
+  // Ulysses sequence parallelism (dv_mmdit_plan_set_sp): this rank owns the video rows
+  // [sp_rank * Lv / sp_world, ...) and the heads [sp_rank * H / sp_world, ...)
+  int sp_rank = 0, sp_world = 1;
+  dv_exchange_fn sp_exchange = nullptr;
+  void* sp_user = nullptr;
+  void *sp_send = nullptr, *sp_recv = nullptr;  // staging buffers of the all-to-all
 };
 
 namespace {
@@ -329,6 +335,39 @@ extern "C" void dv_mmdit_plan_destroy(dv_mmdit_plan* p) {
   delete p;
 }
 
+extern "C" int dv_mmdit_plan_set_sp(dv_mmdit_plan* p, int sp_rank, int sp_world, dv_exchange_fn fn,
+                                    void* user) {
+  DV_REQUIRE(p, "dv_mmdit_plan_set_sp: null plan");
+  DV_REQUIRE(sp_world >= 1 && sp_rank >= 0 && sp_rank < sp_world, "dv_mmdit_plan_set_sp: rank %d of %d",
+             sp_rank, sp_world);
+  const int H = p->m->cfg.num_heads;
+  DV_REQUIRE(H % sp_world == 0, "dv_mmdit_plan_set_sp: %d heads do not split over %d ranks", H, sp_world);
+  DV_REQUIRE(p->Lv % sp_world == 0, "dv_mmdit_plan_set_sp: %d video tokens do not split over %d ranks",
+             p->Lv, sp_world);
+  DV_REQUIRE(sp_world == 1 || fn != nullptr, "dv_mmdit_plan_set_sp: exchange function missing");
+  if (sp_world > 1 && p->sp_send == nullptr) {
+    const int D = p->m->D;
+    const long long Lw = p->Lv / sp_world;
+    // the largest exchange: q|k|v of my rows (bf16), the attention rows (bf16), the fp32 stream
+    long long bytes = static_cast<long long>(p->B) * Lw * 3 * D * 2;
+    const long long b2 = static_cast<long long>(sp_world) * p->B * (p->Lc + Lw) * (D / sp_world) * 2;
+    const long long b3 = static_cast<long long>(sp_world) * p->B * Lw * D * 4;
+    bytes = bytes > b2 ? bytes : b2;
+    bytes = bytes > b3 ? bytes : b3;
+    char *s0 = nullptr, *s1 = nullptr;
+    int rc = dev_alloc(p, &s0, bytes);
+    if (rc == 0) rc = dev_alloc(p, &s1, bytes);
+    if (rc) return rc;
+    p->sp_send = s0;
+    p->sp_recv = s1;
+  }
+  p->sp_rank = sp_rank;
+  p->sp_world = sp_world;
+  p->sp_exchange = fn;
+  p->sp_user = user;
+  return DV_OK;
+}
+
 extern "C" long long dv_mmdit_plan_workspace_bytes(const dv_mmdit_plan* p) { return p ? p->bytes : 0; }
 extern "C" double dv_mmdit_plan_flops(const dv_mmdit_plan* p) { return p ? p->flops : 0.0; }
 
@@ -412,6 +451,19 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
 
   const long long xs = static_cast<long long>(Lv) * D, cs = static_cast<long long>(Lc) * D;
   const long long js = static_cast<long long>(L) * D;  // joint (attention output) batch stride
+  // Ulysses: this rank's window of the video rows (the whole stream when sp_world == 1); every
+  // per-token step below runs on the window, the buffers keep their full-sequence layout
+  const int P = p->sp_world, R = p->sp_rank;
+  const int Lw = Lv / P, v0 = R * Lw;
+  const int Hc = D / P;  // attention columns (heads * 64) per rank
+  float* xw = p->x + static_cast<long long>(v0) * D;
+  __nv_bfloat16* xnw = p->xn + static_cast<long long>(v0) * D;
+  __nv_bfloat16* ffhw = p->ffh + static_cast<long long>(v0) * 4 * D;
+  auto exchange = [&](long long bytes_per_peer) -> int {
+    int erc = p->sp_exchange(p->sp_user, p->sp_send, p->sp_recv, bytes_per_peer, st);
+    if (erc != 0 && last_error()[0] == 0) set_error("dv_mmdit_forward: exchange callback failed (%d)", erc);
+    return erc;
+  };
   // ---- transformer blocks ------------------------------------------------------------------
   // Every step of a joint block is ONE launch covering the video and the context stream
   // (the reference runs them as separate modules, mmdit.py:385-433).
@@ -422,7 +474,7 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
     // norm1 / norm1_context: chunk order shift, scale, gate (msa), shift, scale, gate (mlp);
     // last block: AdaLayerNormContinuous on the context, chunk order scale, shift (mmdit.py:513)
     {
-      LnRows rx = {p->x, xs, p->xn, xs, mx + 0 * D, mx + 1 * D, Lv};
+      LnRows rx = {xw, xs, xnw, xs, mx + 0 * D, mx + 1 * D, Lw};
       LnRows rcx = {p->c, cs, p->cn, cs, last ? mc + 1 * D : mc + 0 * D, last ? mc + 0 * D : mc + 1 * D, Lc};
       DV_RUN(launch_ln_modulate2(rx, &rcx, MR, B, D, 1e-6f, st));
     }
@@ -431,30 +483,43 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
       GemmDesc dq[2];
       for (int s = 0; s < 2; ++s) {
         const bool vid = (s == 0);
-        GemmDesc d = dense_desc(vid ? p->xn : p->cn, vid ? xs : cs, D,
+        GemmDesc d = dense_desc(vid ? xnw : p->cn, vid ? xs : cs, D,
                                 vid ? m->p_w_qkv_x[i] : m->p_w_qkv_c[i], 3 * D,
-                                vid ? m->p_b_qkv_x[i] : m->p_b_qkv_c[i], B, vid ? Lv : Lc, 3 * D, D);
+                                vid ? m->p_b_qkv_x[i] : m->p_b_qkv_c[i], B, vid ? Lw : Lc, 3 * D, D);
         d.mode = EPI_QKV;
         d.out = p->qkv;
         d.out_batch_stride = static_cast<long long>(L) * 3 * D;
         d.ldo = 3 * D;
-        d.out_row_offset = vid ? Lc : 0;
+        d.out_row_offset = vid ? Lc + v0 : 0;
         d.qk_norm_w = vid ? m->p_qk_norm_x[i] : m->p_qk_norm_c[i];
         d.rope_cs = m->rope_cs;
-        d.frame_id = vid ? p->frame_x : p->frame_c;
+        d.frame_id = vid ? p->frame_x + v0 : p->frame_c;
         d.heads_dim = D;
         dq[s] = d;
       }
       DV_RUN(launch_gemm_pair(dq[0], &dq[1], st));
     }
+    if (P > 1) {
+      // my rows, every rank's heads  ->  every rank's rows, my heads
+      DV_RUN(launch_sp_qkv_pack(p->qkv, p->sp_send, B, L, D, Lc + v0, Lw, P, Hc, st));
+      DV_RUN(exchange(static_cast<long long>(B) * Lw * 3 * Hc * 2));
+      DV_RUN(launch_sp_qkv_unpack(p->sp_recv, p->qkv, B, L, D, Lc, Lw, P, Hc, R, st));
+    }
     DV_RUN(launch_attention(p->qkv, p->attn, p->kv_end, p->key_bias, p->tile_dead, B, L, p->Lpad,
-                            m->cfg.num_heads, st, p->attn_flops_layer));
+                            m->cfg.num_heads, st, p->attn_flops_layer / P, R * (m->cfg.num_heads / P),
+                            m->cfg.num_heads / P));
+    if (P > 1) {
+      // all context rows + rank j's video rows of my heads -> rank j; back come the other heads
+      DV_RUN(launch_sp_attn_pack(p->attn, p->sp_send, B, L, D, Lc, Lw, P, Hc, R, st));
+      DV_RUN(exchange(static_cast<long long>(B) * (Lc + Lw) * Hc * 2));
+      DV_RUN(launch_sp_attn_unpack(p->sp_recv, p->attn, B, L, D, Lc, Lw, P, Hc, R, st));
+    }
     // x += gate_msa * to_out(attn);  c += c_gate_msa * to_add_out(attn_c)  (not in the last block)
     {
-      GemmDesc dx = dense_desc(p->attn + static_cast<long long>(Lc) * D, js, D, m->p_w_out_x[i], D,
-                               m->p_b_out_x[i], B, Lv, D, D);
+      GemmDesc dx = dense_desc(p->attn + static_cast<long long>(Lc + v0) * D, js, D, m->p_w_out_x[i], D,
+                               m->p_b_out_x[i], B, Lw, D, D);
       dx.mode = EPI_RESID_GATE;
-      dx.out = p->x;
+      dx.out = xw;
       dx.out_batch_stride = xs;
       dx.ldo = D;
       dx.gate = mx + 2 * D;
@@ -470,25 +535,26 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
     }
     // feed-forward, both streams: LN + modulate, W1 + GELU, W2 + gated residual
     {
-      LnRows rx = {p->x, xs, p->xn, xs, mx + 3 * D, mx + 4 * D, Lv};
+      LnRows rx = {xw, xs, xnw, xs, mx + 3 * D, mx + 4 * D, Lw};
       LnRows rcx = {p->c, cs, p->cn, cs, mc + 3 * D, mc + 4 * D, Lc};
       DV_RUN(launch_ln_modulate2(rx, last ? nullptr : &rcx, MR, B, D, 1e-6f, st));
       GemmDesc d1[2], d2[2];
       for (int s = 0; s < 2; ++s) {
         const bool vid = (s == 0);
         const float* mm = vid ? mx : mc;
-        float* res = vid ? p->x : p->c;
-        __nv_bfloat16* nrm = vid ? p->xn : p->cn;
-        __nv_bfloat16* hid = vid ? p->ffh : p->ffh_c;
+        float* res = vid ? xw : p->c;
+        __nv_bfloat16* nrm = vid ? xnw : p->cn;
+        __nv_bfloat16* hid = vid ? ffhw : p->ffh_c;
         const long long rs = vid ? xs : cs;
-        const int Ls = vid ? Lv : Lc;
+        const int Ls = vid ? Lw : Lc;
+        const long long hs = static_cast<long long>(vid ? Lv : Lc) * 4 * D;  // hidden batch stride
         d1[s] = dense_desc(nrm, rs, D, vid ? m->p_w_ff1_x[i] : m->p_w_ff1_c[i], 4 * D,
                            vid ? m->p_b_ff1_x[i] : m->p_b_ff1_c[i], B, Ls, 4 * D, D);
         d1[s].mode = EPI_GELU;
         d1[s].out = hid;
-        d1[s].out_batch_stride = static_cast<long long>(Ls) * 4 * D;
+        d1[s].out_batch_stride = hs;
         d1[s].ldo = 4 * D;
-        d2[s] = dense_desc(hid, static_cast<long long>(Ls) * 4 * D, 4 * D,
+        d2[s] = dense_desc(hid, hs, 4 * D,
                            vid ? m->p_w_ff2_x[i] : m->p_w_ff2_c[i], D,
                            vid ? m->p_b_ff2_x[i] : m->p_b_ff2_c[i], B, Ls, D, 4 * D);
         d2[s].mode = EPI_RESID_GATE;
@@ -503,6 +569,12 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
     }
   }
 
+  if (P > 1) {
+    // every rank runs the (cheap) output head on the full video stream: all-gather the windows
+    DV_RUN(launch_sp_x_pack(p->x, p->sp_send, B, Lv, D, Lw, P, R, st));
+    DV_RUN(exchange(static_cast<long long>(B) * Lw * D * 4));
+    DV_RUN(launch_sp_x_unpack(p->sp_recv, p->x, B, Lv, D, Lw, P, R, st));
+  }
   // ---- head: norm_out (scale, shift) + proj_out + unpatchify, noisy clip only ---------------
   {
     const ClipInfo& lc = p->clips.back();

@@ -135,6 +135,34 @@ class B200MMDiT:
         self._weights = w
         check(self.lib.dv_mmdit_create(C.byref(c), C.byref(w), C.byref(self._handle)), "dv_mmdit_create")
 
+    # -- Ulysses sequence parallelism (no reference counterpart; BASELINE.json north_star) --------
+    def set_sequence_parallel(self, sp_rank: int, sp_world: int, exchange=None, user=None):
+        """Shard the video tokens of every forward over `sp_world` ranks (this one is `sp_rank`).
+        `exchange` is the equal-block all-to-all the forward calls around every attention: either
+        a `parallel.NcclExchange` (NCCL inside the library, no Python in the loop) or a Python
+        callable `(send_ptr, recv_ptr, bytes_per_peer, stream_ptr) -> int` (tests)."""
+        if sp_world > 1 and exchange is None:
+            raise _lib.DeepVError("set_sequence_parallel: an exchange is required for sp_world > 1")
+        self._sp = (int(sp_rank), int(sp_world))
+        self._sp_keep = exchange
+        if exchange is None:
+            self._sp_fn, self._sp_user = None, None
+        elif hasattr(exchange, "fn_ptr"):
+            self._sp_fn, self._sp_user = exchange.fn_ptr, exchange.user_ptr
+        else:
+            proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p)
+
+            def tramp(_user, send, recv, nbytes, stream):
+                try:
+                    return int(exchange(send, recv, nbytes, stream) or 0)
+                except Exception as e:  # noqa: BLE001 - must not unwind through C
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            self._sp_cb = proto(tramp)
+            self._sp_fn, self._sp_user = C.cast(self._sp_cb, C.c_void_p), None
+        # applied lazily per plan (a setting may not divide the token count of every cached layout)
+
     # -- plans -------------------------------------------------------------------------------------
     def _plan(self, B: int, clip_dims: tuple, text_len: int, hist: Optional[tuple], hist_ds: int):
         key = (B, clip_dims, text_len, hist, hist_ds)
@@ -149,6 +177,16 @@ class B200MMDiT:
                   "dv_mmdit_plan_create")
             p = h.value
             self._plans[key] = p
+        sp = getattr(self, "_sp", (0, 1))
+        applied = getattr(self, "_plan_sp", None)
+        if applied is None:
+            applied = self._plan_sp = {}
+        want = (sp[0], sp[1], id(getattr(self, "_sp_keep", None)))
+        if applied.get(p, (0, 1, id(None))) != want:
+            fn = getattr(self, "_sp_fn", None) if sp[1] > 1 else None
+            user = getattr(self, "_sp_user", None) if sp[1] > 1 else None
+            check(self.lib.dv_mmdit_plan_set_sp(p, sp[0], sp[1], fn, user), "dv_mmdit_plan_set_sp")
+            applied[p] = want
         return p
 
     def plan_flops(self, B, clip_dims, text_len=77, hist=None, hist_ds=2) -> float:

@@ -23,6 +23,65 @@ import torch
 import torch.distributed as dist
 
 
+class NcclExchange:
+    """The equal-block all-to-all of Ulysses sequence parallelism, run by NCCL INSIDE
+    libdeepv_b200.so (csrc/comm.cu): `fn_ptr` / `user_ptr` are handed to dv_mmdit_plan_set_sp, so a
+    sequence-parallel forward stays one C call.  The communicator is created from a unique id that
+    rank 0 of `group` makes and torch.distributed broadcasts."""
+
+    def __init__(self, group=None, device=None):
+        import ctypes as C
+
+        from . import _lib
+        lib = _lib.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        path = self._nccl_path()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            _lib.check(lib.dv_comm_unique_id(path, C.cast(buf, C.c_void_p)), "dv_comm_unique_id")
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        backend = dist.get_backend(group)
+        carrier = ident.to(device) if backend == "nccl" else ident
+        dist.broadcast(carrier, src=src, group=group)
+        raw = bytes(carrier.cpu().numpy().tobytes())
+        handle = C.c_void_p()
+        _lib.check(lib.dv_comm_create(path, raw, rank, world, C.byref(handle)), "dv_comm_create")
+        self._lib, self._handle = lib, handle
+        self.rank, self.world = rank, world
+        self.fn_ptr = C.cast(lib.dv_comm_exchange, C.c_void_p)
+        self.user_ptr = handle
+
+    @staticmethod
+    def _nccl_path():
+        import glob
+        import os
+        try:
+            import nvidia  # the wheel torch depends on
+            for base in nvidia.__path__:
+                hits = glob.glob(os.path.join(base, "nccl", "lib", "libnccl.so.2"))
+                if hits:
+                    return hits[0].encode()
+        except Exception:
+            pass
+        return b""
+
+    def close(self):
+        if self._handle:
+            self._lib.dv_comm_destroy(self._handle)
+            self._handle = None
+
+
+def sp_ranks(world: int, n_branch: int):
+    """How a rollout group of `world` ranks splits into CFG branches x sequence-parallel ranks:
+    returns (n_branch_groups, sp_world) with n_branch_groups * sp_world == world, or (1, world)
+    when the branches do not divide the group."""
+    if n_branch > 1 and world % n_branch == 0:
+        return n_branch, world // n_branch
+    return 1, world
+
+
 def branch_of_rank(rank: int, n_branch: int) -> int:
     return rank % n_branch
 
@@ -53,6 +112,7 @@ class Shard:
     rank: int
     world: int
     group: object = None
+    sp_layouts: object = None   # n_branch -> (branch groups, sp_world, NcclExchange | None), see setup_sp
 
     @staticmethod
     def current(group=None) -> "Shard":
@@ -86,8 +146,47 @@ class Shard:
     def active(self) -> bool:
         return self.world > 1
 
-    # ---- CFG branches -----------------------------------------------------------------------
+    # ---- CFG branches x Ulysses sequence parallelism --------------------------------------------
+    def setup_sp(self, device, branch_counts=(1, 2, 3)) -> None:
+        """Create the sequence-parallel sub-groups (and their in-library NCCL communicators) for
+        every CFG batch size the rollout uses.  A rollout group of G ranks runs `nb` branch groups
+        of `sp = G / nb` ranks each (sp_ranks()); ranks [b*sp, (b+1)*sp) of the group hold branch b.
+        Collective over the WHOLE world (torch.distributed.new_group)."""
+        self.sp_layouts = {}
+        if not self.active:
+            return
+        me, world_all = dist.get_rank(), dist.get_world_size()
+        n_rollouts = world_all // self.world
+        made = {}
+        for nb in branch_counts:
+            g_nb, sp = sp_ranks(self.world, nb)
+            if sp == 1:
+                self.sp_layouts[nb] = (g_nb, 1, None)
+                continue
+            if (g_nb, sp) not in made:
+                mine = None
+                for ro in range(n_rollouts):
+                    for b in range(g_nb):
+                        ranks = [ro * self.world + b * sp + i for i in range(sp)]
+                        grp = dist.new_group(ranks)
+                        if me in ranks:
+                            mine = grp
+                made[(g_nb, sp)] = NcclExchange(mine, device)
+            self.sp_layouts[nb] = (g_nb, sp, made[(g_nb, sp)])
+
+    def layout(self, n_branch: int):
+        """(branch groups, sp_world, exchange) for a CFG batch of n_branch.  Without setup_sp():
+        branch r % n_branch on rank r, no sequence parallelism (extra ranks duplicate a branch)."""
+        if self.sp_layouts and n_branch in self.sp_layouts:
+            return self.sp_layouts[n_branch]
+        if self.active and n_branch > 1 and self.world >= n_branch:
+            return (n_branch, 1, None)
+        return (1, 1, None)
+
     def my_branch(self, n_branch: int) -> int:
+        g_nb, sp, _ = self.layout(n_branch)
+        if self.sp_layouts and n_branch in self.sp_layouts:
+            return (self.rank // sp) if g_nb > 1 else 0
         return branch_of_rank(self.rank, n_branch)
 
     def gather_branches(self, pred_local: torch.Tensor, n_branch: int) -> torch.Tensor:
@@ -95,9 +194,10 @@ class Shard:
         (uncond, text[, text+history]) on every rank."""
         if not self.active:
             return pred_local
+        _, sp, _ = self.layout(n_branch)
         bufs = [torch.empty_like(pred_local) for _ in range(self.world)]
         dist.all_gather(bufs, pred_local.contiguous(), group=self.group)
-        return torch.cat([bufs[r] for r in branch_sources(self.world, n_branch)], dim=0)
+        return torch.cat([bufs[b * sp] for b in range(n_branch)], dim=0)
 
     # ---- VAE tiles -------------------------------------------------------------------------------
     def my_items(self, n_items: int) -> List[int]:

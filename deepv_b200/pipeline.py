@@ -87,7 +87,15 @@ class B200Pipeline:
         enc = prompt_embeds.to(self.device)
         enc_mask = prompt_attention_mask.to(self.device)
         pooled = pooled_prompt_embeds.to(self.device)
-        sharded = shard is not None and shard.active and n_branch > 1
+        sharded = False
+        if shard is not None and shard.active:
+            # rollout group = branch groups x Ulysses ranks (parallel.Shard.setup_sp)
+            g_nb, sp_world, exchange = shard.layout(n_branch)
+            sharded = g_nb > 1
+            if hasattr(self.model, "set_sequence_parallel"):
+                self.model.set_sequence_parallel(shard.rank % sp_world, sp_world, exchange)
+        elif getattr(self.model, "_sp", (0, 1))[1] > 1:
+            self.model.set_sequence_parallel(0, 1, None)   # back to the single-rank forward
         if sharded:
             if latents.shape[0] != 1:
                 raise _lib.DeepVError("CFG-branch sharding expects one sample per rollout")

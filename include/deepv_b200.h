@@ -161,6 +161,31 @@ int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, int io_dtyp
                      void* out_dev, int out_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Ulysses sequence parallelism over the ranks of one rollout group (reference: none — the
+ * reference is single-GPU; BASELINE.json north_star / SURVEY.md §8e.2).  The video tokens of a
+ * forward are sharded over sp_world ranks (each runs LN / projections / MLP on its rows; the
+ * <= 269 context tokens are replicated); around every attention the ranks exchange "my tokens,
+ * your heads" for "all tokens, my heads" with an equal-block all-to-all, and the fp32 video
+ * stream is all-gathered once before the output head, so that every rank returns the full
+ * prediction.  The exchange is a callback: block j of send_dev goes to rank j, block i of
+ * recv_dev comes from rank i, enqueued on `stream`.  dv_comm_* is the NCCL implementation of it
+ * (libnccl.so.2 is resolved with dlopen; the communicator is built from a unique id that the
+ * host broadcasts over its own process group).
+ * ------------------------------------------------------------------------------------------ */
+typedef int (*dv_exchange_fn)(void* user, const void* send_dev, void* recv_dev,
+                              long long bytes_per_peer, void* stream);
+/* Lv %% sp_world == 0 and num_heads %% sp_world == 0 are required; sp_world = 1 switches it off. */
+int dv_mmdit_plan_set_sp(dv_mmdit_plan* p, int sp_rank, int sp_world, dv_exchange_fn fn, void* user);
+
+typedef struct dv_comm dv_comm;
+int dv_comm_unique_id(const char* nccl_path, void* id128);   /* rank 0: 128-byte id to broadcast */
+int dv_comm_create(const char* nccl_path, const void* id128, int rank, int world, dv_comm** out);
+void dv_comm_destroy(dv_comm* c);
+/* a dv_exchange_fn; user = dv_comm* */
+int dv_comm_exchange(void* user, const void* send_dev, void* recv_dev, long long bytes_per_peer,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Causal video VAE decoder
  * ------------------------------------------------------------------------------------------ */
 typedef struct dv_vae dv_vae;

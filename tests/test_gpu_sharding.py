@@ -51,3 +51,66 @@ def test_tile_granular_decode_equals_fused_decode():
     torch.cuda.synchronize()
     for a, b in zip(fused, sharded):
         assert torch.equal(a, b)
+
+
+def test_ulysses_two_virtual_ranks_match_single_rank():
+    """Ulysses sequence parallelism (csrc/mmdit.cu + the staging kernels) with two virtual ranks on
+    ONE device: two models run the same forward in two threads, each on its own stream, and the
+    all-to-all callback swaps the staged blocks between them.  Both must reproduce the unsharded
+    forward (same kernels on a row window; split-K factors may re-associate sums)."""
+    import ctypes as C
+    import threading
+
+    from deepv_b200.mmdit import B200MMDiT
+    cfg, W = weights.mmdit_weights(dict(num_layers=2), seed=1)
+    inp = cases.mmdit_inputs(cases.MMDIT_CASES["two_block_b2"])
+    dev = "cuda"
+
+    def call(model):
+        return model(sample=[[c.to(dev) for c in inp["clips"]]], timestep_ratio=inp["t"].to(dev),
+                     encoder_hidden_states=inp["enc"].to(dev), encoder_attention_mask=inp["mask"].to(dev),
+                     pooled_projections=inp["pooled"].to(dev))[0]
+
+    ref = call(B200MMDiT(W, cfg, out_dtype=torch.float32))
+    torch.cuda.synchronize()
+
+    P = 2
+    models = [B200MMDiT(W, cfg, out_dtype=torch.float32) for _ in range(P)]
+    barrier = threading.Barrier(P)
+    posted = [None] * P
+
+    def make_exchange(r):
+        def exchange(send, recv, nbytes, stream):
+            torch.cuda.current_stream().synchronize()          # my staged blocks are complete
+            posted[r] = (send, recv, nbytes)
+            barrier.wait()
+            for i in range(P):                                 # block r of rank i's send -> block i of my recv
+                src = posted[i][0] + r * nbytes
+                rc = cudart.cudaMemcpy(C.c_void_p(recv + i * nbytes), C.c_void_p(src), C.c_size_t(nbytes), 3)
+                assert rc == 0, rc
+            barrier.wait()
+            return 0
+        return exchange
+
+    cudart = C.CDLL("libcudart.so.12")
+    outs, errs = [None] * P, []
+
+    def worker(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                models[r].set_sequence_parallel(r, P, make_exchange(r))
+                outs[r] = call(models[r])
+                torch.cuda.current_stream().synchronize()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errs, errs
+    for r in range(P):
+        err = ((outs[r] - ref).abs().max() / ref.abs().max()).item()
+        assert err <= 5e-3, (r, err)
