@@ -58,6 +58,10 @@ struct AttnArgs {
   const int* tile_dead;           // [B][Lpad/128]: tile holds a dead key (nullptr: assume yes)
   int L, Lpad, H, B;              // H = heads in the qkv / out rows
   int head0;                      // first head this launch handles (Ulysses: a rank's head slice)
+  // Ulysses over peer memory: context rows (< peer_Lc) go to every rank's buffer, video row q to
+  // out_peer[(q - peer_Lc) / peer_Lw]; n_peers == 0: everything to `out`
+  __nv_bfloat16* out_peer[8];
+  int n_peers, peer_Lc, peer_Lw;
   float scale_log2;               // head_dim^-0.5 * log2(e)
 };
 
@@ -361,16 +365,29 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
       }
       const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
       if (row_ok) {
-        uint4* d4 = reinterpret_cast<uint4*>(a.out + (static_cast<long long>(b) * a.L + qi) * HD +
-                                             head * kD);
+        uint4 q[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          uint4 q;
-          q.x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-          q.y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-          q.z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-          q.w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-          d4[i] = q;
+          q[i].x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+          q[i].y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+          q[i].z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+          q[i].w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        }
+        const long long off = (static_cast<long long>(b) * a.L + qi) * HD + head * kD;
+        if (a.n_peers == 0) {
+          uint4* d4 = reinterpret_cast<uint4*>(a.out + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = q[i];
+        } else if (qi >= a.peer_Lc) {  // a video row: straight into its owner's buffer (NVLink store)
+          uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[(qi - a.peer_Lc) / a.peer_Lw] + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = q[i];
+        } else {                       // a context row: every rank continues the replicated stream
+          for (int p = 0; p < a.n_peers; ++p) {
+            uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[p] + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d4[i] = q[i];
+          }
         }
       }
     }
@@ -389,7 +406,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
                      const int* tile_dead, int B, int L, int Lpad, int H, cudaStream_t stream,
-                     double flops, int head0, int n_heads) {
+                     double flops, int head0, int n_heads, void* const* out_peers, int n_peers,
+                     int peer_Lc, int peer_Lw) {
   if (n_heads <= 0) n_heads = H;
   DV_REQUIRE(head0 >= 0 && head0 + n_heads <= H, "attention: heads [%d, %d) of %d", head0, head0 + n_heads, H);
   DV_REQUIRE(Lpad % 128 == 0 && Lpad >= L, "attention: Lpad=%d must be a multiple of 128 >= L=%d",
@@ -410,6 +428,12 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   a.H = H;
   a.B = B;
   a.head0 = head0;
+  DV_REQUIRE(n_peers >= 0 && n_peers <= 8, "attention: %d peers", n_peers);
+  a.n_peers = out_peers ? n_peers : 0;
+  a.peer_Lc = peer_Lc;
+  a.peer_Lw = peer_Lw > 0 ? peer_Lw : 1;
+  for (int i = 0; i < 8; ++i)
+    a.out_peer[i] = (out_peers && i < n_peers) ? reinterpret_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {

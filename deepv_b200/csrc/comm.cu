@@ -27,6 +27,7 @@ typedef int (*FnCommDestroy)(NcclComm);
 typedef int (*FnGroup)(void);
 typedef int (*FnSendRecv)(const void*, size_t, int /*ncclDataType_t*/, int, NcclComm, cudaStream_t);
 typedef const char* (*FnErrStr)(int);
+typedef int (*FnAllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 
 struct NcclApi {
   void* h = nullptr;
@@ -37,6 +38,7 @@ struct NcclApi {
   FnSendRecv send = nullptr;
   int (*recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   FnErrStr err = nullptr;
+  FnAllReduce all_reduce = nullptr;
 };
 
 NcclApi g_nccl;
@@ -58,8 +60,9 @@ int load_nccl(const char* path) {
   g_nccl.send = reinterpret_cast<FnSendRecv>(dlsym(h, "ncclSend"));
   g_nccl.recv = reinterpret_cast<decltype(g_nccl.recv)>(dlsym(h, "ncclRecv"));
   g_nccl.err = reinterpret_cast<FnErrStr>(dlsym(h, "ncclGetErrorString"));
+  g_nccl.all_reduce = reinterpret_cast<FnAllReduce>(dlsym(h, "ncclAllReduce"));
   if (!g_nccl.get_id || !g_nccl.init || !g_nccl.destroy || !g_nccl.group_start || !g_nccl.group_end ||
-      !g_nccl.send || !g_nccl.recv) {
+      !g_nccl.send || !g_nccl.recv || !g_nccl.all_reduce) {
     set_error("dv_comm: libnccl.so.2 lacks a required symbol");
     return DV_ERR_INVALID;
   }
@@ -81,6 +84,7 @@ int load_nccl(const char* path) {
 struct dv_comm {
   NcclComm comm = nullptr;
   int rank = 0, world = 1;
+  int* token = nullptr;  // device word all-reduced by the barrier form of the exchange
 };
 
 extern "C" int dv_comm_unique_id(const char* nccl_path, void* id128) {
@@ -109,12 +113,18 @@ extern "C" int dv_comm_create(const char* nccl_path, const void* id128, int rank
     delete c;
     return DV_ERR_CUDA;
   }
+  if (cudaMalloc(&c->token, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->token, 0, 2 * sizeof(int)) != cudaSuccess) {
+    set_error("dv_comm_create: cannot allocate the barrier word");
+    delete c;
+    return DV_ERR_CUDA;
+  }
   *out = c;
   return DV_OK;
 }
 
 extern "C" void dv_comm_destroy(dv_comm* c) {
   if (!c) return;
+  if (c->token) cudaFree(c->token);
   if (c->comm && g_nccl.destroy) g_nccl.destroy(c->comm);
   delete c;
 }
@@ -123,8 +133,15 @@ extern "C" void dv_comm_destroy(dv_comm* c) {
 extern "C" int dv_comm_exchange(void* user, const void* send_dev, void* recv_dev,
                                 long long bytes_per_peer, void* stream) {
   dv_comm* c = reinterpret_cast<dv_comm*>(user);
-  DV_REQUIRE(c && c->comm && send_dev && recv_dev && bytes_per_peer >= 0, "dv_comm_exchange: bad argument");
+  DV_REQUIRE(c && c->comm && bytes_per_peer >= 0, "dv_comm_exchange: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bytes_per_peer == 0) {
+    // barrier form (peer-memory Ulysses: the payload already went over NVLink as plain stores):
+    // a one-word all-reduce orders every rank's preceding kernels before every rank's following ones
+    DV_NCCL(g_nccl.all_reduce(c->token, c->token + 1, 1, 2 /*ncclInt32*/, 0 /*ncclSum*/, c->comm, st));
+    return DV_OK;
+  }
+  DV_REQUIRE(send_dev && recv_dev, "dv_comm_exchange: null buffer");
   const char* s = reinterpret_cast<const char*>(send_dev);
   char* r = reinterpret_cast<char*>(recv_dev);
   DV_NCCL(g_nccl.group_start());

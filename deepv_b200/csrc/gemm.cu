@@ -327,7 +327,9 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
         v[2 * i + 1] = t.y * x0 + t.x * x1;
       }
     }
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out) +
+    void* base = d.out;
+    if (d.peer_cols > 0) base = d.out_peer[(n % d.heads_dim) / d.peer_cols];  // the rank that owns this head
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(base) +
                          static_cast<long long>(r.b) * d.out_batch_stride +
                          static_cast<long long>(r.m + d.out_row_offset) * d.ldo + n;
     store_bf16x32(out, v);

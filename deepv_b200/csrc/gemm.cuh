@@ -66,6 +66,10 @@ struct GemmDesc {
   const float* rope_cs;        // [frames][32][2] (cos, sin)
   const int* frame_id;         // [M]
   int heads_dim;               // = 1536 (q|k|v block width)
+  // Ulysses over peer memory: the 64-column head starting at column n of the q, k or v block is
+  // stored into out_peer[(n % heads_dim) / peer_cols] (same layout on every rank) instead of `out`
+  void* out_peer[8];           // null-filled = off
+  int peer_cols;               // attention columns (heads * 64) per rank
   // UNPATCH: out bf16 [B][C][1][2*gh][2*gw]
   int up_gh, up_gw, up_C;
   int out_f32;                 // UNPATCH: store fp32 instead of bf16

@@ -9,7 +9,8 @@ namespace dv {
 // tile_dead: [B][Lpad/128] "tile holds a dead key" flags from launch_key_bias, or nullptr
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
                      const int* tile_dead, int B, int L, int Lpad, int H, cudaStream_t stream,
-                     double flops = 0.0, int head0 = 0, int n_heads = 0);
+                     double flops = 0.0, int head0 = 0, int n_heads = 0, void* const* out_peers = nullptr,
+                     int n_peers = 0, int peer_Lc = 0, int peer_Lw = 0);
 
 // ---- MMDiT elementwise (elementwise.cu) -----------------------------------------------
 // out_bf16[b][l][:] = LN(x[b][l][:]) * (1 + scale[b][:]) + shift[b][:]   (eps inside sqrt)

@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "../../include/deepv_b200.h"
+#include <cstring>
+
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -60,6 +62,12 @@ struct dv_mmdit_plan {
   dv_exchange_fn sp_exchange = nullptr;
   void* sp_user = nullptr;
   void *sp_send = nullptr, *sp_recv = nullptr;  // staging buffers of the all-to-all
+  // peer-memory variant: every rank's qkv / attn buffer (own entry = own buffer); when set, the
+  // QKV and attention epilogues store straight into the owner's buffer over NVLink and the
+  // exchange callback is only used as a barrier (bytes_per_peer == 0)
+  void* qkv_peer[8] = {nullptr};
+  void* attn_peer[8] = {nullptr};
+  bool peers_set = false;
 };
 
 namespace {
@@ -368,6 +376,49 @@ extern "C" int dv_mmdit_plan_set_sp(dv_mmdit_plan* p, int sp_rank, int sp_world,
   return DV_OK;
 }
 
+extern "C" int dv_mmdit_plan_buffers(dv_mmdit_plan* p, void** qkv_dev, void** attn_dev) {
+  DV_REQUIRE(p && qkv_dev && attn_dev, "dv_mmdit_plan_buffers: null argument");
+  *qkv_dev = p->qkv;
+  *attn_dev = p->attn;
+  return DV_OK;
+}
+
+extern "C" int dv_mmdit_plan_set_sp_peers(dv_mmdit_plan* p, void* const* qkv_ptrs, void* const* attn_ptrs) {
+  DV_REQUIRE(p, "dv_mmdit_plan_set_sp_peers: null plan");
+  if (qkv_ptrs == nullptr || attn_ptrs == nullptr) {
+    p->peers_set = false;
+    return DV_OK;
+  }
+  DV_REQUIRE(p->sp_world > 1 && p->sp_world <= 8, "dv_mmdit_plan_set_sp_peers: call dv_mmdit_plan_set_sp first (sp_world=%d)",
+             p->sp_world);
+  for (int i = 0; i < p->sp_world; ++i) {
+    DV_REQUIRE(qkv_ptrs[i] && attn_ptrs[i], "dv_mmdit_plan_set_sp_peers: null pointer for rank %d", i);
+    p->qkv_peer[i] = qkv_ptrs[i];
+    p->attn_peer[i] = attn_ptrs[i];
+  }
+  DV_REQUIRE(p->qkv_peer[p->sp_rank] == p->qkv && p->attn_peer[p->sp_rank] == p->attn,
+             "dv_mmdit_plan_set_sp_peers: entry %d must be this plan's own buffers", p->sp_rank);
+  p->peers_set = true;
+  return DV_OK;
+}
+
+extern "C" int dv_ipc_get_handle(const void* dev_ptr, void* handle64) {
+  DV_REQUIRE(dev_ptr && handle64, "dv_ipc_get_handle: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  DV_CHECK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+  memcpy(handle64, &h, sizeof(h));
+  return DV_OK;
+}
+
+extern "C" int dv_ipc_open_handle(const void* handle64, void** dev_ptr) {
+  DV_REQUIRE(handle64 && dev_ptr, "dv_ipc_open_handle: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  DV_CHECK_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DV_OK;
+}
+
 extern "C" long long dv_mmdit_plan_workspace_bytes(const dv_mmdit_plan* p) { return p ? p->bytes : 0; }
 extern "C" double dv_mmdit_plan_flops(const dv_mmdit_plan* p) { return p ? p->flops : 0.0; }
 
@@ -495,11 +546,18 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
         d.rope_cs = m->rope_cs;
         d.frame_id = vid ? p->frame_x + v0 : p->frame_c;
         d.heads_dim = D;
+        if (vid && P > 1 && p->peers_set) {  // each head straight into the buffer of the rank that owns it
+          for (int j = 0; j < P; ++j) d.out_peer[j] = p->qkv_peer[j];
+          d.peer_cols = Hc;
+        }
         dq[s] = d;
       }
       DV_RUN(launch_gemm_pair(dq[0], &dq[1], st));
     }
-    if (P > 1) {
+    const bool peer = P > 1 && p->peers_set;
+    if (peer) {
+      DV_RUN(exchange(0));  // barrier: every rank's q|k|v stores have landed
+    } else if (P > 1) {
       // my rows, every rank's heads  ->  every rank's rows, my heads
       DV_RUN(launch_sp_qkv_pack(p->qkv, p->sp_send, B, L, D, Lc + v0, Lw, P, Hc, st));
       DV_RUN(exchange(static_cast<long long>(B) * Lw * 3 * Hc * 2));
@@ -507,8 +565,10 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
     }
     DV_RUN(launch_attention(p->qkv, p->attn, p->kv_end, p->key_bias, p->tile_dead, B, L, p->Lpad,
                             m->cfg.num_heads, st, p->attn_flops_layer / P, R * (m->cfg.num_heads / P),
-                            m->cfg.num_heads / P));
-    if (P > 1) {
+                            m->cfg.num_heads / P, peer ? p->attn_peer : nullptr, peer ? P : 0, Lc, Lw));
+    if (peer) {
+      DV_RUN(exchange(0));  // barrier: every rank's attention rows have landed
+    } else if (P > 1) {
       // all context rows + rank j's video rows of my heads -> rank j; back come the other heads
       DV_RUN(launch_sp_attn_pack(p->attn, p->sp_send, B, L, D, Lc, Lw, P, Hc, R, st));
       DV_RUN(exchange(static_cast<long long>(B) * (Lc + Lw) * Hc * 2));

@@ -186,6 +186,18 @@ class B200MMDiT:
             fn = getattr(self, "_sp_fn", None) if sp[1] > 1 else None
             user = getattr(self, "_sp_user", None) if sp[1] > 1 else None
             check(self.lib.dv_mmdit_plan_set_sp(p, sp[0], sp[1], fn, user), "dv_mmdit_plan_set_sp")
+            keep = getattr(self, "_sp_keep", None)
+            if sp[1] > 1 and callable(getattr(keep, "peer_pointers", None)):
+                # peer-memory exchange: every rank of the group maps the others' qkv / attention buffers
+                # (collective: all ranks of the SP group create their plans in the same order)
+                q, a = C.c_void_p(), C.c_void_p()
+                check(self.lib.dv_mmdit_plan_buffers(p, C.byref(q), C.byref(a)), "dv_mmdit_plan_buffers")
+                qs, as_ = keep.peer_pointers(key, q.value, a.value)
+                qa = (C.c_void_p * sp[1])(*qs)
+                aa = (C.c_void_p * sp[1])(*as_)
+                check(self.lib.dv_mmdit_plan_set_sp_peers(p, qa, aa), "dv_mmdit_plan_set_sp_peers")
+            else:
+                check(self.lib.dv_mmdit_plan_set_sp_peers(p, None, None), "dv_mmdit_plan_set_sp_peers")
             applied[p] = want
         return p
 

@@ -29,8 +29,11 @@ class NcclExchange:
     sequence-parallel forward stays one C call.  The communicator is created from a unique id that
     rank 0 of `group` makes and torch.distributed broadcasts."""
 
-    def __init__(self, group=None, device=None):
+    def __init__(self, group=None, device=None, peer_memory=True):
         import ctypes as C
+        self.group, self.device = group, device
+        if not peer_memory:
+            self.peer_pointers = None   # (instance attribute shadows the method: staged all-to-all)
 
         from . import _lib
         lib = _lib.load()
@@ -52,6 +55,35 @@ class NcclExchange:
         self.rank, self.world = rank, world
         self.fn_ptr = C.cast(lib.dv_comm_exchange, C.c_void_p)
         self.user_ptr = handle
+
+    def peer_pointers(self, _key, qkv_ptr: int, attn_ptr: int):
+        """Map every rank's qkv / attention buffers into this process (CUDA IPC): the forward then
+        stores q|k|v heads and attention rows straight into their owner's buffer over NVLink and
+        uses the NCCL exchange only as a barrier.  Collective over the group."""
+        import ctypes as C
+
+        from . import _lib
+        lib = self._lib
+        mine = (C.c_char * 128)()
+        _lib.check(lib.dv_ipc_get_handle(qkv_ptr, C.cast(mine, C.c_void_p)), "dv_ipc_get_handle")
+        _lib.check(lib.dv_ipc_get_handle(attn_ptr, C.cast(C.byref(mine, 64), C.c_void_p)), "dv_ipc_get_handle")
+        t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone()
+        on_dev = dist.get_backend(self.group) == "nccl"
+        t = t.to(self.device) if on_dev else t
+        bufs = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(bufs, t, group=self.group)
+        qs, as_ = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                qs.append(qkv_ptr)
+                as_.append(attn_ptr)
+                continue
+            raw = bytes(bufs[r].cpu().numpy().tobytes())
+            for off, lst in ((0, qs), (64, as_)):
+                ptr = C.c_void_p()
+                _lib.check(lib.dv_ipc_open_handle(raw[off:off + 64], C.byref(ptr)), "dv_ipc_open_handle")
+                lst.append(ptr.value)
+        return qs, as_
 
     @staticmethod
     def _nccl_path():
@@ -147,7 +179,7 @@ class Shard:
         return self.world > 1
 
     # ---- CFG branches x Ulysses sequence parallelism --------------------------------------------
-    def setup_sp(self, device, branch_counts=(1, 2, 3)) -> None:
+    def setup_sp(self, device, branch_counts=(1, 2, 3), peer_memory=None) -> None:
         """Create the sequence-parallel sub-groups (and their in-library NCCL communicators) for
         every CFG batch size the rollout uses.  A rollout group of G ranks runs `nb` branch groups
         of `sp = G / nb` ranks each (sp_ranks()); ranks [b*sp, (b+1)*sp) of the group hold branch b.
@@ -155,6 +187,9 @@ class Shard:
         self.sp_layouts = {}
         if not self.active:
             return
+        if peer_memory is None:   # DV_SP_STAGED=1: pack -> NCCL all-to-all -> unpack instead of peer stores
+            import os
+            peer_memory = os.environ.get("DV_SP_STAGED", "") == ""
         me, world_all = dist.get_rank(), dist.get_world_size()
         n_rollouts = world_all // self.world
         made = {}
@@ -171,7 +206,7 @@ class Shard:
                         grp = dist.new_group(ranks)
                         if me in ranks:
                             mine = grp
-                made[(g_nb, sp)] = NcclExchange(mine, device)
+                made[(g_nb, sp)] = NcclExchange(mine, device, peer_memory=peer_memory)
             self.sp_layouts[nb] = (g_nb, sp, made[(g_nb, sp)])
 
     def layout(self, n_branch: int):

@@ -177,6 +177,19 @@ typedef int (*dv_exchange_fn)(void* user, const void* send_dev, void* recv_dev,
 /* Lv %% sp_world == 0 and num_heads %% sp_world == 0 are required; sp_world = 1 switches it off. */
 int dv_mmdit_plan_set_sp(dv_mmdit_plan* p, int sp_rank, int sp_world, dv_exchange_fn fn, void* user);
 
+/* Peer-memory variant of the exchange (the transfer fused into the producing kernels): when every
+ * rank's qkv / attention buffers are mapped here (CUDA IPC between the processes of one box, or
+ * plain pointers inside one process), the QKV-projection epilogue stores each head straight into
+ * the buffer of the rank that owns it and the attention epilogue stores each output row into its
+ * owner's buffer — NVLink stores issued tile by tile while the tensor pipe keeps working — and the
+ * exchange callback is only called as a barrier (bytes_per_peer == 0, null buffers).
+ * qkv_ptrs / attn_ptrs: sp_world device pointers each, entry sp_rank = this plan's own buffers
+ * (dv_mmdit_plan_buffers); NULL switches back to the staged all-to-all.                          */
+int dv_mmdit_plan_buffers(dv_mmdit_plan* p, void** qkv_dev, void** attn_dev);
+int dv_mmdit_plan_set_sp_peers(dv_mmdit_plan* p, void* const* qkv_ptrs, void* const* attn_ptrs);
+int dv_ipc_get_handle(const void* dev_ptr, void* handle64);      /* cudaIpcGetMemHandle  */
+int dv_ipc_open_handle(const void* handle64, void** dev_ptr);    /* cudaIpcOpenMemHandle */
+
 typedef struct dv_comm dv_comm;
 int dv_comm_unique_id(const char* nccl_path, void* id128);   /* rank 0: 128-byte id to broadcast */
 int dv_comm_create(const char* nccl_path, const void* id128, int rank, int world, dv_comm** out);

@@ -53,7 +53,8 @@ def test_tile_granular_decode_equals_fused_decode():
         assert torch.equal(a, b)
 
 
-def test_ulysses_two_virtual_ranks_match_single_rank():
+@pytest.mark.parametrize("peer_memory", [False, True])
+def test_ulysses_two_virtual_ranks_match_single_rank(peer_memory):
     """Ulysses sequence parallelism (csrc/mmdit.cu + the staging kernels) with two virtual ranks on
     ONE device: two models run the same forward in two threads, each on its own stream, and the
     all-to-all callback swaps the staged blocks between them.  Both must reproduce the unsharded
@@ -79,9 +80,34 @@ def test_ulysses_two_virtual_ranks_match_single_rank():
     barrier = threading.Barrier(P)
     posted = [None] * P
 
+    shared = {}
+    payload_calls = [0] * P
+
+    class PeerExchange:
+        """peer_memory=True: both 'ranks' live in this process, so their buffers are plain pointers;
+        the callback is then only ever called as a barrier (nbytes == 0)."""
+
+        def __init__(self, r, fn):
+            self.r, self.fn = r, fn
+
+        def __call__(self, send, recv, nbytes, stream):
+            return self.fn(send, recv, nbytes, stream)
+
+        def peer_pointers(self, key, q, a):
+            shared[(key, self.r)] = (q, a)
+            barrier.wait()
+            got = [shared[(key, i)] for i in range(P)]
+            barrier.wait()
+            return [g[0] for g in got], [g[1] for g in got]
+
     def make_exchange(r):
         def exchange(send, recv, nbytes, stream):
-            torch.cuda.current_stream().synchronize()          # my staged blocks are complete
+            torch.cuda.current_stream().synchronize()          # my staged blocks / peer stores are complete
+            if nbytes == 0:                                    # barrier form (peer-memory variant)
+                assert peer_memory
+                barrier.wait()
+                return 0
+            payload_calls[r] += 1                              # staged path, or the final fp32 all-gather
             posted[r] = (send, recv, nbytes)
             barrier.wait()
             for i in range(P):                                 # block r of rank i's send -> block i of my recv
@@ -98,7 +124,8 @@ def test_ulysses_two_virtual_ranks_match_single_rank():
     def worker(r):
         try:
             with torch.cuda.stream(torch.cuda.Stream()):
-                models[r].set_sequence_parallel(r, P, make_exchange(r))
+                ex = make_exchange(r)
+                models[r].set_sequence_parallel(r, P, PeerExchange(r, ex) if peer_memory else ex)
                 outs[r] = call(models[r])
                 torch.cuda.current_stream().synchronize()
         except Exception as e:  # noqa: BLE001
@@ -114,3 +141,5 @@ def test_ulysses_two_virtual_ranks_match_single_rank():
     for r in range(P):
         err = ((outs[r] - ref).abs().max() / ref.abs().max()).item()
         assert err <= 5e-3, (r, err)
+    # peer memory: q|k|v and attention rows travel as stores, only the all-gather of the stream is staged
+    assert payload_calls == ([1] * P if peer_memory else [2 * cfg["num_layers"] + 1] * P)
