@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace dv {
@@ -139,8 +141,64 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base, shape, strides, box): plans call the same GEMMs with the
+// same buffers thousands of times per step, so the encoded descriptors are memoised (an encode
+// through the driver costs ~1 us, a launch carries up to six of them).
+namespace {
+struct TmKey {
+  const void* base;
+  int rank, swz;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  bool operator==(const TmKey& o) const { return memcmp(this, &o, sizeof(TmKey)) == 0; }
+};
+struct TmHash {
+  size_t operator()(const TmKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return static_cast<size_t>(h);
+  }
+};
+static_assert(sizeof(TmKey) % 8 == 0, "TmKey is hashed as 64-bit words");
+std::mutex g_tm_mutex;
+std::unordered_map<TmKey, CUtensorMap, TmHash>* g_tm_cache = nullptr;
+}  // namespace
+
+static int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+  TmKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = rank;
+  key.swz = swizzle128;
+  for (int i = 0; i < rank && i < 5; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i + 1 < rank) key.strides[i] = strides_bytes[i];
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_tm_mutex);
+    if (!g_tm_cache) g_tm_cache = new std::unordered_map<TmKey, CUtensorMap, TmHash>();
+    auto it = g_tm_cache->find(key);
+    if (it != g_tm_cache->end()) {
+      memcpy(out, &it->second, sizeof(CUtensorMap));
+      return 0;
+    }
+  }
+  int rc = encode_tensor_map_bf16(out, base, rank, dims, strides_bytes, box, swizzle128);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(g_tm_mutex);
+  if (g_tm_cache->size() > (1u << 16)) g_tm_cache->clear();  // unbounded callers (sweeps): start over
+  (*g_tm_cache)[key] = *out;
+  return 0;
+}
+
+static int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
   EncodeTiledFn enc = get_encode();
   DV_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver / device?)");
   DV_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);

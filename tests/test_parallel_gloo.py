@@ -116,3 +116,21 @@ def test_rollout_groups_over_gloo_world4():
     ret = mgr.dict()
     mp.spawn(_worker_grouped, args=(world, port, ret), nprocs=world, join=True)
     assert [ret[r] for r in range(4)] == [0, 0, 1, 1]
+
+
+def test_rollout_group_layouts():
+    """A rollout group splits into CFG branch groups x Ulysses ranks (parallel.sp_ranks)."""
+    assert parallel.sp_ranks(2, 2) == (2, 1)     # a GPU pair: one branch each
+    assert parallel.sp_ranks(4, 2) == (2, 2)
+    assert parallel.sp_ranks(8, 2) == (2, 4)
+    assert parallel.sp_ranks(8, 3) == (1, 8)     # 3 branches do not divide 8: whole batch, 8-way Ulysses
+    assert parallel.sp_ranks(6, 3) == (3, 2)
+    assert parallel.sp_ranks(4, 1) == (1, 4)
+    # without setup_sp(): branch r % n on rank r, no sequence parallelism, extra ranks duplicate
+    sh = parallel.Shard(3, 4)
+    assert sh.layout(2) == (2, 1, None) and sh.my_branch(2) == 1
+    assert parallel.Shard(0, 1).layout(3) == (1, 1, None)
+    # with layouts: branch = rank // sp_world, Ulysses rank = rank % sp_world
+    sh = parallel.Shard(5, 8, sp_layouts={2: (2, 4, None), 3: (1, 8, None)})
+    assert sh.my_branch(2) == 1 and sh.layout(2)[1] == 4
+    assert sh.my_branch(3) == 0 and sh.layout(3)[1] == 8
