@@ -169,6 +169,58 @@ def mmdit_weights(cfg: dict | None = None, seed: int = 1):
     return cfg, make_weights(mmdit_shapes(cfg), seed, "mmdit")
 
 
-def vae_weights(cfg: dict | None = None, seed: int = 2):
+def vae_encoder_shapes(cfg: dict) -> Shapes:
+    """encoder.* + quant_conv (model/vae.py:630-665,823)."""
+    chans = list(cfg["encoder_block_out_channels"])
+    layers = cfg["encoder_layers_per_block"]
+    sp, tp = cfg["encoder_spatial_down_sample"], cfg["encoder_temporal_down_sample"]
+    zc = cfg["encoder_out_channels"]
+    s: Shapes = OrderedDict()
+
+    def conv(name, co, ci, k):
+        s[name + ".conv.weight"] = (co, ci, k, k, k)
+        s[name + ".conv.bias"] = (co,)
+
+    def norm(name, ch):
+        s[name + ".weight"] = (ch,)
+        s[name + ".bias"] = (ch,)
+
+    def resnet(name, ci, co):
+        norm(name + ".norm1", ci)
+        conv(name + ".conv1", co, ci, 3)
+        norm(name + ".norm2", co)
+        conv(name + ".conv2", co, co, 3)
+        if ci != co:
+            conv(name + ".conv_shortcut", co, ci, 1)
+
+    conv("encoder.conv_in", chans[0], cfg.get("encoder_in_channels", 3), 3)
+    prev = chans[0]
+    for i, co in enumerate(chans):
+        for j in range(layers[i]):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if sp[i]:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3)
+        if tp[i]:
+            conv(f"encoder.down_blocks.{i}.temporal_downsamplers.0.conv", co, co, 3)
+        prev = co
+    c0 = chans[-1]
+    norm("encoder.mid_block.attentions.0.group_norm", c0)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        s[f"encoder.mid_block.attentions.0.{n}.weight"] = (c0, c0)
+        s[f"encoder.mid_block.attentions.0.{n}.bias"] = (c0,)
+    resnet("encoder.mid_block.resnets.0", c0, c0)
+    resnet("encoder.mid_block.resnets.1", c0, c0)
+    norm("encoder.conv_norm_out", c0)
+    conv("encoder.conv_out", 2 * zc, c0, 3)
+    conv("quant_conv", 2 * zc, 2 * zc, 1)
+    return s
+
+
+def vae_weights(cfg: dict | None = None, seed: int = 2, encoder: bool = False):
+    """Decoder weights (+ the encoder's, drawn from an independent stream so that adding them does
+    not change the decoder values existing fixtures were made with)."""
     cfg = dict(VAE_DEFAULT, **(cfg or {}))
-    return cfg, make_weights(vae_decoder_shapes(cfg), seed, "vae")
+    W = make_weights(vae_decoder_shapes(cfg), seed, "vae")
+    if encoder:
+        W.update(make_weights(vae_encoder_shapes(cfg), seed + 1000, "vae"))
+    return cfg, W

@@ -179,3 +179,72 @@ def unnormalise_latents(lat: Tensor) -> Tensor:
 def decode_latent(W, cfg, lat: Tensor) -> Tensor:
     """pipeline.py:703-713 with save_memory=True."""
     return tiled_decode(W, cfg, unnormalise_latents(lat), 256, 1, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# Encode side (SURVEY.md §8 row f1): vae.py:630-689 (encoder), :844-883 (encode / tiled_encode as
+# the rollout calls it: `vae.encode(x)` with tiling on -> temporal_chunk=False, 256-px tiles every
+# 192 px, 8-latent blends, 24-latent crops), :599-615 (DiagonalGaussianDistribution).
+# ---------------------------------------------------------------------------------------------
+def strided_causal_conv(W, name: str, x: Tensor, stride=(1, 1, 1)) -> Tensor:
+    """CausalConv3d without the chunk cache (vae.py:229-231,251): zero pad (k-1) frames in front
+    and k//2 pixels around, then a VALID conv with the given stride."""
+    w, b = W[name + ".conv.weight"], W[name + ".conv.bias"]
+    k = w.shape[2]
+    sp = w.shape[3] // 2
+    return F.conv3d(F.pad(x, (sp, sp, sp, sp, k - 1, 0)), w, b, stride=stride)
+
+
+def encoder_forward(W, cfg: dict, x: Tensor) -> Tensor:
+    """CausalVaeEncoder.forward + quant_conv for one tile, temporal_chunk=False -> moments [b,2z,t,h,w]."""
+    g = cfg.get("encoder_norm_num_groups", 32)
+    chans = list(cfg["encoder_block_out_channels"])
+
+    def res(name, h):
+        return resnet(W, name, h, None, True, g)
+
+    h = strided_causal_conv(W, "encoder.conv_in", x)
+    for i in range(len(chans)):
+        for j in range(cfg["encoder_layers_per_block"][i]):
+            h = res(f"encoder.down_blocks.{i}.resnets.{j}", h)
+        if cfg["encoder_spatial_down_sample"][i]:
+            h = strided_causal_conv(W, f"encoder.down_blocks.{i}.downsamplers.0.conv", h, (1, 2, 2))
+        if cfg["encoder_temporal_down_sample"][i]:
+            h = strided_causal_conv(W, f"encoder.down_blocks.{i}.temporal_downsamplers.0.conv", h, (2, 1, 1))
+    h = res("encoder.mid_block.resnets.0", h)
+    h = mid_attention(W, "encoder.mid_block.attentions.0", h, g)
+    h = res("encoder.mid_block.resnets.1", h)
+    h = F.silu(frame_group_norm(W, "encoder.conv_norm_out", h, g))
+    h = strided_causal_conv(W, "encoder.conv_out", h)
+    return strided_causal_conv(W, "quant_conv", h)
+
+
+def tiled_encode(W, cfg, x: Tensor, tile_sample_min_size: int = 256, scale: int = 8) -> Tensor:
+    """vae.py:844-851,954-987 with temporal_chunk=False: moments of the whole frame."""
+    ts = tile_sample_min_size
+    tl = int(ts / scale)
+    if not (x.shape[-1] > ts or x.shape[-2] > ts):
+        return encoder_forward(W, cfg, x)
+    overlap = int(ts * 0.75)
+    extent = int(tl * 0.25)
+    limit = tl - extent
+    rows: List[List[Tensor]] = []
+    for i in range(0, x.shape[3], overlap):
+        rows.append([encoder_forward(W, cfg, x[:, :, :, i:i + ts, j:j + ts]) for j in range(0, x.shape[4], overlap)])
+    out_rows = []
+    for i, row in enumerate(rows):
+        resl = []
+        for j, tile in enumerate(row):
+            if i > 0:
+                tile = _blend_v(rows[i - 1][j], tile, extent)
+            if j > 0:
+                tile = _blend_h(row[j - 1], tile, extent)
+            resl.append(tile[:, :, :, :limit, :limit])
+        out_rows.append(torch.cat(resl, dim=4))
+    return torch.cat(out_rows, dim=3)
+
+
+def gaussian_sample(moments: Tensor, noise: Tensor) -> Tensor:
+    """DiagonalGaussianDistribution(moments).sample() with the normal draw injected (vae.py:602-615)."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise

@@ -5,4 +5,4 @@ only enumerates parameter names/shapes and draws seeded normals), so that bench.
 does not have to import anything from oracle/.
 """
 from deepv_b200.synthetic import (MMDIT_DEFAULT, VAE_DEFAULT, make_weights, mmdit_shapes,  # noqa: F401
-                                  mmdit_weights, vae_decoder_shapes, vae_weights)
+                                  mmdit_weights, vae_decoder_shapes, vae_encoder_shapes, vae_weights)

@@ -78,3 +78,23 @@ def vae_digest(y):
                 rows=y.double().mean(dim=(1, 2, 4)).float(), cols=y.double().mean(dim=(1, 2, 3)).float(),
                 seam_h=y[:, :, :, 180:260:4, ::8].clone().float() if y.shape[3] > 260 else None,
                 seam_w=y[:, :, :, ::8, 180:260:4].clone().float() if y.shape[4] > 260 else None)
+
+
+# ---- VAE encode: moments of vae.encode(x) with tiling on (vae.py:844-883) ----
+VAE_ENC_CASES = {
+    # reduced widths keep the CPU reference fast; tile geometry (256-px tiles every 192 px, 8-latent
+    # blends) and the stride-2 causal convolutions are the real ones
+    "image_untiled": dict(cfg=dict(decoder_block_out_channels=(32, 32, 64, 64), encoder_block_out_channels=(32, 32, 64, 64),
+                                   decoder_layers_per_block=(1, 1, 1, 1), encoder_layers_per_block=(1, 2, 1, 1)),
+                          wseed=5, video=(1, 3, 1, 64, 96), seed=41),
+    "clip9_tiled_2x2": dict(cfg=dict(decoder_block_out_channels=(32, 32, 64, 64), encoder_block_out_channels=(32, 32, 64, 64),
+                                     decoder_layers_per_block=(1, 1, 1, 1), encoder_layers_per_block=(1, 1, 1, 1)),
+                            wseed=6, video=(1, 3, 9, 320, 272), seed=42),
+    "clip17_tiled_1x2": dict(cfg=dict(decoder_block_out_channels=(32, 32, 32, 32), encoder_block_out_channels=(32, 32, 32, 32),
+                                      decoder_layers_per_block=(1, 1, 1, 1), encoder_layers_per_block=(2, 1, 1, 1)),
+                             wseed=7, video=(1, 3, 17, 200, 328), seed=43),
+}
+
+
+def vae_video(case):
+    return torch.randn(*case["video"], generator=_g(case["seed"]))

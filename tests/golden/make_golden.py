@@ -90,6 +90,18 @@ def main():
         out[name] = cases.vae_digest(y)
         print(name, tuple(y.shape), float(y.abs().max()))
     torch.save(out, HERE / "vae_golden.pt")
+
+    # ---- VAE encode: moments (mean | logvar) of the tiled, un-chunked encode ---------------------------
+    out = {}
+    for name, case in cases.VAE_ENC_CASES.items():
+        cfg, W = weights.vae_weights(case["cfg"], seed=case["wseed"], encoder=True)
+        vae = va.CausalVideoVAE(**{k: cfg[k] for k in keys}).eval()
+        vae.load_state_dict(W, strict=True)
+        vae.enable_tiling()
+        m = vae.encode(cases.vae_video(case)).latent_dist.parameters
+        out[name] = m.clone().float()
+        print(name, tuple(m.shape), float(m.abs().max()))
+    torch.save(out, HERE / "vae_encode_golden.pt")
     for f in sorted(HERE.glob("*golden*")):
         print(f.name, os.path.getsize(f))
 

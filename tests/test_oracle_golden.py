@@ -95,6 +95,22 @@ def test_vae_oracle_matches_reference_golden(name):
         assert (d[k] - gold[k]).abs().max().item() <= 2e-5, k
 
 
+@pytest.mark.parametrize("name", list(cases.VAE_ENC_CASES))
+def test_vae_encode_oracle_matches_reference_golden(name):
+    gold = torch.load(G / "vae_encode_golden.pt")[name]
+    case = cases.VAE_ENC_CASES[name]
+    cfg, W = weights.vae_weights(case["cfg"], seed=case["wseed"], encoder=True)
+    with torch.no_grad():
+        m = vae_ref.tiled_encode(W, cfg, cases.vae_video(case))
+    assert m.shape == gold.shape
+    assert (m - gold).abs().max().item() <= 2e-5
+    # DiagonalGaussianDistribution.sample with the draw injected (vae.py:602-615)
+    noise = torch.randn(m.shape[0], m.shape[1] // 2, *m.shape[2:], generator=torch.Generator().manual_seed(9))
+    z = vae_ref.gaussian_sample(m, noise)
+    mean, logvar = m.chunk(2, dim=1)
+    assert torch.allclose(z, mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * noise)
+
+
 def test_cfg_combine_orders():
     p = torch.randn(3, 4, 5)
     u, t, h = p.chunk(3)
