@@ -79,6 +79,33 @@ extern "C" int dv_attention(const void* qkv_dev, void* out_dev, const int* kv_en
                           S(stream));
 }
 
+extern "C" int dv_conv3d_strided_cl(const void* x_dev, const void* w_dev, const float* bias_dev,
+                                    void* out_dev, int B, int T, int H, int W, int Cin, int Cout,
+                                    int w_rows, int sT, int sH, int sW, void* stream) {
+  DV_REQUIRE(x_dev && w_dev && out_dev, "dv_conv3d_strided_cl: null pointer");
+  GemmDesc d = {};
+  d.batch = B;
+  d.N = Cout;
+  d.A = x_dev;
+  d.a_mode = 1;
+  d.cT = T;
+  d.cH = H;
+  d.cW = W;
+  d.cC = Cin;
+  d.kt = d.kh = d.kw = 3;
+  d.sT = sT;
+  d.sH = sH;
+  d.sW = sW;
+  d.W = w_dev;
+  d.w_rows = w_rows;
+  d.bias = bias_dev;
+  d.mode = EPI_CONV;
+  d.out = out_dev;
+  d.conv_store = CONV_PLAIN;
+  d.out_C = Cout;
+  return launch_gemm(d, S(stream));
+}
+
 extern "C" int dv_conv3d_cl(const void* x_dev, const void* w_dev, const float* bias_dev,
                             const void* residual_dev, void* out_dev, int B, int T, int H, int W,
                             int Cin, int Cout, int w_rows, int ksize, int store, int drop_first,

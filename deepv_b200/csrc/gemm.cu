@@ -46,6 +46,7 @@ struct Problem {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmBh;  // CTA-pair mode: same matrix, 128-row box (each CTA loads half of N)
+  alignas(64) CUtensorMap tmAp[3];  // strided conv: the other input parities (tmA = parity 0), see setup_problem
   GemmDesc d;
   int m_tiles, n_tiles, k_blocks, tiles;
   int kb_per_split;      // split-K over a cluster of `splits` CTAs
@@ -53,6 +54,8 @@ struct Problem {
   int tiles_w, tiles_h;  // conv: M-tile grid inside one frame
   int c_blocks;          // conv: Cin / 64
   int swap;              // conv, Cout <= 128: weights are the M operand, 16x16 pixels the N operand
+  int oT, oH, oW;        // conv: output dims (input dims over the strides)
+  int sT, sH, sW;        // conv: strides (1 or 2)
 };
 
 // One launch runs up to two problems of the same epilogue mode (the video and the context stream
@@ -130,7 +133,7 @@ __device__ __forceinline__ RowCtx make_row(const Problem& a, const TileCoord& tc
     const int q = tc.m_tile % per_frame;
     r.ch = (q / a.tiles_w) * 8 + (row_in_tile >> 4);
     r.cw = (q % a.tiles_w) * 16 + (row_in_tile & 15);
-    r.ok = (r.ct < d.cT) && (r.ch < d.cH) && (r.cw < d.cW);
+    r.ok = (r.ct < a.oT) && (r.ch < a.oH) && (r.cw < a.oW);
   } else {
     r.ok = r.m < d.M;
   }
@@ -365,15 +368,15 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
           make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   } else if constexpr (MODE == EPI_CONV) {
     add_bias<W>(d.bias, n, v);
-    int ot = r.ct, oh = r.ch, ow = r.cw, oc = n, oH = d.cH, oW = d.cW;
+    int ot = r.ct, oh = r.ch, ow = r.cw, oc = n, oH = a.oH, oW = a.oW;
     if (d.conv_store == CONV_SHUFFLE_HW) {
       // packed weight rows are ordered (p1, p2, c): vae.py:382
       const int q = n / d.out_C;
       oc = n % d.out_C;
       oh = 2 * r.ch + (q >> 1);
       ow = 2 * r.cw + (q & 1);
-      oH = 2 * d.cH;
-      oW = 2 * d.cW;
+      oH = 2 * a.oH;
+      oW = 2 * a.oW;
     } else if (d.conv_store == CONV_INTERLEAVE_T) {
       // packed weight rows are ordered (p, c): vae.py:407-409
       const int p = n / d.out_C;
@@ -382,7 +385,7 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
       if (ot < 0) return;
     }
     const int oT =
-        (d.conv_store == CONV_INTERLEAVE_T) ? (2 * d.cT - (d.conv_drop_first ? 1 : 0)) : d.cT;
+        (d.conv_store == CONV_INTERLEAVE_T) ? (2 * a.oT - (d.conv_drop_first ? 1 : 0)) : a.oT;
     const long long off =
         (((static_cast<long long>(r.b) * oT + ot) * oH + oh) * oW + ow) * d.out_C + oc;
     if (r.ok) {
@@ -488,7 +491,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const Ti
   const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
   const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(d.residual);
-  const long long frame_off = (static_cast<long long>(tc.b) * d.cT + ct) * d.cH;
+  const long long frame_off = (static_cast<long long>(tc.b) * a.oT + ct) * a.oH;
   if (quarter * 32 >= d.N) return;  // warp-uniform: no live channel in this lane quarter
   float gsum = 0.f, gsq = 0.f;      // fused GroupNorm statistics of this thread's channel
   uint32_t buf[2][32];
@@ -501,8 +504,8 @@ __device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const Ti
 #pragma unroll
     for (int hr = 0; hr < 2; ++hr) {
       const int oh = h0 + cc * 2 + hr;
-      if (oh >= d.cH || !c_ok) continue;
-      const long long row_off = ((frame_off + oh) * d.cW + w0) * d.out_C + c;
+      if (oh >= a.oH || !c_ok) continue;
+      const long long row_off = ((frame_off + oh) * a.oW + w0) * d.out_C + c;
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(buf[ci & 1][hr * 16 + i]) + bias;
@@ -620,13 +623,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int dw = tap % d.kw;
             // causal in time (kt-1 frames of zero history), centred in space; TMA's
             // out-of-bounds zero fill is the padding
-            const int x = w0 + dw - d.kw / 2, y = h0 + dh - d.kh / 2, t = ct + dt - (d.kt - 1);
+            int x = w0 + dw - d.kw / 2, y = h0 + dh - d.kh / 2, t = ct + dt - (d.kt - 1);
+            const CUtensorMap* tma = &a.tmA;
+            if (a.sW == 2) {
+              // stride (1,2,2): input pixel 2*o + e, e in {-1,0,1}: parity (e & 1) selects one of four
+              // maps over the half-resolution grid, (e - parity) / 2 is the offset inside it
+              const int ew = dw - d.kw / 2, eh = dh - d.kh / 2;
+              const int pw = ew & 1, ph = eh & 1;
+              x = w0 + (ew - pw) / 2;
+              y = h0 + (eh - ph) / 2;
+              const int q = ph * 2 + pw;
+              if (q) tma = &a.tmAp[q - 1];
+            } else if (a.sT == 2) {
+              // stride (2,1,1), causal: input frame 2*o + e, e in {-2,-1,0}
+              const int et = dt - (d.kt - 1);
+              const int pt = et & 1;
+              t = ct + (et - pt) / 2;
+              if (pt) tma = &a.tmAp[0];
+            }
             if (a.swap) {
               // weights (<= 128 rows) feed the M side, a 16x16-pixel box the N side
               tma_load_2d(&a.tmB, &full_bar[stage], sa, kb * BK, 0);
-              tma_load_5d(&a.tmA, &full_bar[stage], sb, cb * 64, x, y, t, tc.b);
+              tma_load_5d(tma, &full_bar[stage], sb, cb * 64, x, y, t, tc.b);
             } else {
-              tma_load_5d(&a.tmA, &full_bar[stage], sa, cb * 64, x, y, t, tc.b);
+              tma_load_5d(tma, &full_bar[stage], sa, cb * 64, x, y, t, tc.b);
               tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
             }
           } else {
@@ -1119,9 +1139,22 @@ static int setup_problem(const GemmDesc& d, Problem& pr) {
     DV_REQUIRE(pr.swap || (d.N % 32 == 0 && d.out_C % 32 == 0),
                "conv: Cout=%d (stored channels %d) must be <= 128 with a plain store or multiples of 32",
                d.N, d.out_C);
-    pr.tiles_w = d.cW / 16;
-    pr.tiles_h = pr.swap ? (d.cH + 15) / 16 : d.cH / 8;
-    pr.m_tiles = d.cT * pr.tiles_w * pr.tiles_h;
+    pr.sT = d.sT > 1 ? d.sT : 1;
+    pr.sH = d.sH > 1 ? d.sH : 1;
+    pr.sW = d.sW > 1 ? d.sW : 1;
+    DV_REQUIRE((pr.sT == 1 && pr.sH == pr.sW && pr.sW <= 2) || (pr.sT == 2 && pr.sH == 1 && pr.sW == 1),
+               "conv: stride (%d,%d,%d) unsupported (only (1,1,1), (1,2,2), (2,1,1))", pr.sT, pr.sH, pr.sW);
+    DV_REQUIRE(pr.sT * pr.sH * pr.sW == 1 || (d.kt == 3 && d.conv_store == CONV_PLAIN),
+               "conv: strided convs are 3x3x3 with a plain store");
+    DV_REQUIRE(d.cH % pr.sH == 0 && d.cW % pr.sW == 0, "conv: H=%d W=%d not divisible by the stride", d.cH, d.cW);
+    pr.oT = (d.cT - 1) / pr.sT + 1;
+    pr.oH = d.cH / pr.sH;
+    pr.oW = d.cW / pr.sW;
+    DV_REQUIRE(pr.oW % 16 == 0 && pr.oH % 8 == 0, "conv: output H=%d W=%d must be multiples of 8/16", pr.oH,
+               pr.oW);
+    pr.tiles_w = pr.oW / 16;
+    pr.tiles_h = pr.swap ? (pr.oH + 15) / 16 : pr.oH / 8;
+    pr.m_tiles = pr.oT * pr.tiles_w * pr.tiles_h;
   } else {
     DV_REQUIRE(d.mode != EPI_CONV, "EPI_CONV needs the conv operand");
     DV_REQUIRE(d.K % 64 == 0, "gemm: K=%d must be a multiple of 64", d.K);
@@ -1130,6 +1163,8 @@ static int setup_problem(const GemmDesc& d, Problem& pr) {
     pr.c_blocks = 1;
     pr.tiles_w = pr.tiles_h = 1;
     pr.m_tiles = (d.M + BM - 1) / BM;
+    pr.oT = pr.oH = pr.oW = 0;
+    pr.sT = pr.sH = pr.sW = 1;
   }
   pr.k_blocks = K / BK;
   DV_REQUIRE(d.mode == EPI_UNPATCH || d.mode == EPI_CONV || d.N % 32 == 0,
@@ -1149,8 +1184,32 @@ static int setup_problem(const GemmDesc& d, Problem& pr) {
                            (uint64_t)d.cC * d.cW * d.cH * 2,
                            (uint64_t)d.cC * d.cW * d.cH * d.cT * 2};
     uint32_t box[5] = {64, 16, pr.swap ? 16u : 8u, 1, 1};
-    int rc = make_tensor_map_bf16(&pr.tmA, d.A, 5, dims, strides, box, 1);
-    if (rc) return rc;
+    const char* base = reinterpret_cast<const char*>(d.A);
+    const uint64_t px = (uint64_t)d.cC * 2, row = px * d.cW, frame = row * d.cH;
+    if (pr.sW == 2) {
+      // four maps over the half-resolution grid, one per (row parity, column parity)
+      dims[1] = d.cW / 2;
+      dims[2] = d.cH / 2;
+      strides[0] = 2 * px;
+      strides[1] = 2 * row;
+      for (int q = 0; q < 4; ++q) {
+        int rc = make_tensor_map_bf16(q ? &pr.tmAp[q - 1] : &pr.tmA, base + (q >> 1) * row + (q & 1) * px, 5,
+                                      dims, strides, box, 1);
+        if (rc) return rc;
+      }
+    } else if (pr.sT == 2) {
+      // two maps, one per frame parity (even frames: ceil(T/2), odd frames: floor(T/2))
+      strides[2] = 2 * frame;
+      for (int q = 0; q < 2; ++q) {
+        const int frames = q == 0 ? (d.cT + 1) / 2 : d.cT / 2;
+        dims[3] = frames > 0 ? frames : 1;  // (T = 1: the odd map is only ever addressed out of bounds)
+        int rc = make_tensor_map_bf16(q ? &pr.tmAp[0] : &pr.tmA, base + q * frame, 5, dims, strides, box, 1);
+        if (rc) return rc;
+      }
+    } else {
+      int rc = make_tensor_map_bf16(&pr.tmA, d.A, 5, dims, strides, box, 1);
+      if (rc) return rc;
+    }
   } else {
     uint64_t dims[3] = {(uint64_t)d.K, (uint64_t)d.M, (uint64_t)d.batch};
     uint64_t strides[2] = {(uint64_t)d.lda * 2, (uint64_t)d.a_batch_stride * 2};
@@ -1208,8 +1267,8 @@ static double plan_splits(long long tiles, int k_blocks, bool allow_split, int* 
   return best;
 }
 
-static double problem_flops(const GemmDesc& d, int K) {
-  const double rows = static_cast<double>(d.a_mode == 1 ? (double)d.cT * d.cH * d.cW : d.M) * d.batch;
+static double problem_flops(const GemmDesc& d, int K, const Problem& pr) {
+  const double rows = static_cast<double>(d.a_mode == 1 ? (double)pr.oT * pr.oH * pr.oW : d.M) * d.batch;
   return 2.0 * rows * d.N * K;
 }
 
@@ -1298,12 +1357,12 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
   }
 
   const int K0 = ka.p[0].k_blocks * BK;
-  double flops = problem_flops(d0, K0);
-  double rows = static_cast<double>(d0.a_mode == 1 ? (double)d0.cT * d0.cH * d0.cW : d0.M) * d0.batch;
+  double flops = problem_flops(d0, K0, ka.p[0]);
+  double rows = static_cast<double>(d0.a_mode == 1 ? (double)ka.p[0].oT * ka.p[0].oH * ka.p[0].oW : d0.M) * d0.batch;
   double bytes = 2.0 * (rows * K0 / (d0.a_mode == 1 ? d0.kt * d0.kh * d0.kw : 1) + (double)d0.N * K0 + rows * d0.N);
   if (d1 != nullptr) {
     const int K1 = ka.p[1].k_blocks * BK;
-    flops += problem_flops(*d1, K1);
+    flops += problem_flops(*d1, K1, ka.p[1]);
     bytes += 2.0 * ((double)d1->M * d1->batch * (K1 + d1->N) + (double)d1->N * K1);
   }
   char tag[56] = "";

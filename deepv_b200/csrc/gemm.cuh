@@ -45,6 +45,8 @@ struct GemmDesc {
   int a_mode;          // 0 dense, 1 conv
   int cT, cH, cW, cC;  // input dims (C multiple of 64)
   int kt, kh, kw;      // 3,3,3 or 1,1,1
+  int sT, sH, sW;      // conv strides: (1,1,1) [0 = 1], (1,2,2) or (2,1,1) (VAE encoder, vae.py:322,346);
+                       // output dims T' = (T-1)/sT + 1 (causal), H' = H/sH, W' = W/sW
   // ---- W operand -------------------------------------------------------------
   const void* W;       // bf16 [N_rows][K]
   int w_rows;          // rows present in memory (>= N)

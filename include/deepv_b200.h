@@ -86,6 +86,13 @@ int dv_attention(const void* qkv_dev, void* out_dev, const int* kv_end_dev,
 int dv_conv3d_cl(const void* x_dev, const void* w_dev, const float* bias_dev,
                  const void* residual_dev, void* out_dev, int B, int T, int H, int W, int Cin,
                  int Cout, int w_rows, int ksize, int store, int drop_first, void* stream);
+/* The strided causal convs of the VAE encoder (vae.py:322,346; CausalConv3d :229-231,251): 3x3x3,
+ * stride (1,2,2) or (2,1,1), zero padding 1 pixel around / 2 frames in front, then a VALID conv:
+ * out [B][(T-1)/sT+1][H/sH][W/sW][Cout] bf16.  The strides are realised by TMA tensor maps over the
+ * input parities (no im2col, no copies).                                                          */
+int dv_conv3d_strided_cl(const void* x_dev, const void* w_dev, const float* bias_dev, void* out_dev,
+                         int B, int T, int H, int W, int Cin, int Cout, int w_rows, int sT, int sH,
+                         int sW, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * MMDiT denoiser

@@ -148,3 +148,29 @@ def test_attention_large_scores_rescale_path(lib):
     _lib.check(lib.dv_attention(p(qkv), p(out), p(kvd), p(kb), B, L, 512, H, None))
     torch.cuda.synchronize()
     assert rel(out, _attn_ref(qkv, kv_end, kb, H)) <= 2e-2
+
+
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout,stride", [
+    (1, 3, 32, 64, 64, 256, (1, 2, 2)),     # spatial down-sample, wide output (regular tiles)
+    (1, 2, 64, 64, 128, 128, (1, 2, 2)),    # ... Cout <= 128: swapped-operand tiles
+    (1, 9, 16, 32, 64, 256, (2, 1, 1)),     # temporal down-sample: 9 -> 5 frames
+    (1, 1, 16, 32, 128, 128, (2, 1, 1)),    # a single image: 1 -> 1 frame (history frames all zero)
+    (2, 5, 32, 32, 64, 64, (2, 1, 1)),      # batch 2, 5 -> 3 frames
+])
+def test_strided_causal_conv3d(lib, B, T, H, W, Cin, Cout, stride):
+    """The encoder's down-sampling convs (vae.py:322,346 through CausalConv3d :229-231,251)."""
+    from deepv_b200 import _lib
+    torch.manual_seed(3)
+    x = (torch.randn(B, T, H, W, Cin, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(Cout, 27, Cin, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(max(Cout, 32), device="cuda")
+    sT, sH, sW = stride
+    oT, oH, oW = (T - 1) // sT + 1, H // sH, W // sW
+    out = torch.zeros(B, oT, oH, oW, Cout, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dv_conv3d_strided_cl(p(x), p(w), p(bias), p(out), B, T, H, W, Cin, Cout, Cout, sT, sH, sW, None))
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 4, 1, 2, 3)
+    wn = w.float().view(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3)
+    y = torch.nn.functional.conv3d(torch.nn.functional.pad(xn, (1, 1, 1, 1, 2, 0)), wn, bias[:Cout], stride=stride)
+    assert tuple(y.shape[2:]) == (oT, oH, oW)
+    assert rel(out, y.permute(0, 2, 3, 4, 1)) <= TOL
