@@ -52,6 +52,9 @@ class VAEConfig(C.Structure):
         ("latent_channels", C.c_int), ("out_channels", C.c_int),
         ("block_channels", C.c_int * 4), ("layers_per_block", C.c_int * 4),
         ("spatial_up", C.c_int * 4), ("temporal_up", C.c_int * 4), ("norm_groups", C.c_int),
+        ("enc_in_channels", C.c_int), ("enc_block_channels", C.c_int * 4),
+        ("enc_layers_per_block", C.c_int * 4), ("enc_spatial_down", C.c_int * 4),
+        ("enc_temporal_down", C.c_int * 4),
     ]
 
 
@@ -99,6 +102,12 @@ SIGNATURES = {
     "dv_vae_plan_destroy": (None, [_vp]),
     "dv_vae_plan_flops": (_d, [_vp]),
     "dv_vae_decode": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "dv_vae_enc_plan_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "dv_vae_enc_plan_destroy": (None, [_vp]),
+    "dv_vae_enc_plan_flops": (_d, [_vp]),
+    "dv_vae_enc_plan_latent_dims": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "dv_vae_encode": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "dv_gaussian_sample": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "dv_vae_plan_geometry": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dv_vae_plan_tile_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i)]),
     "dv_vae_plan_bind_tile": (_i, [_vp, _i, _vp]),

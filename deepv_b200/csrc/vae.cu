@@ -47,8 +47,9 @@ struct dv_vae {
 };
 
 struct TileOut {
-  __nv_bfloat16* px;  // [Tout][H][W][3]
+  __nv_bfloat16* px;  // [Tout][H][W][C] (decoder: C = 3 frames; encoder: C = 64, 2z moments used)
   int H, W;
+  int C = 3;
 };
 
 struct dv_vae_plan {
@@ -78,12 +79,13 @@ namespace {
 struct BlendArgs {
   const TileOut* tiles;
   int rows, cols, Tout, Hout, Wout, limit, extent;
+  int nch = 3;  // channels written (decoder: 3; encoder: 2z moments)
 };
 
 template <int DEPTH>
 __device__ float blended(const BlendArgs& a, int i, int j, int t, int y, int x, int c) {
   const TileOut& tl = a.tiles[i * a.cols + j];
-  float v = __bfloat162float(tl.px[((static_cast<long long>(t) * tl.H + y) * tl.W + x) * 3 + c]);
+  float v = __bfloat162float(tl.px[((static_cast<long long>(t) * tl.H + y) * tl.W + x) * tl.C + c]);
   if constexpr (DEPTH > 0) {
     if (i > 0) {  // blend_v with the (already blended) tile above, vae.py:942-946
       const TileOut& up = a.tiles[(i - 1) * a.cols + j];
@@ -111,8 +113,8 @@ __device__ float blended(const BlendArgs& a, int i, int j, int t, int y, int x, 
 
 template <typename T>
 __global__ void blend_kernel(BlendArgs a, T* __restrict__ out) {
-  // out: [3][Tout][Hout][Wout]; x fastest -> coalesced stores
-  const long long total = 3LL * a.Tout * a.Hout * a.Wout;
+  // out: [nch][Tout][Hout][Wout]; x fastest -> coalesced stores
+  const long long total = static_cast<long long>(a.nch) * a.Tout * a.Hout * a.Wout;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int X = idx % a.Wout;
@@ -176,12 +178,13 @@ struct Runner {
   // causal conv (vae.py:225-252) as implicit GEMM
   // `stats`: also accumulate the GroupNorm statistics of the output (its consumer is a norm)
   Act conv(const std::string& name, const Act& x, int cout, int ks, int store, int drop_first,
-           const __nv_bfloat16* residual, __nv_bfloat16* outbuf, int w_rows = -1, bool stats = false) {
+           const __nv_bfloat16* residual, __nv_bfloat16* outbuf, int w_rows = -1, bool stats = false,
+           int sT = 1, int sH = 1, int sW = 1) {
     Act y;
     y.p = outbuf;
-    y.T = x.T;
-    y.H = x.H;
-    y.W = x.W;
+    y.T = (x.T - 1) / sT + 1;  // causal: (kt-1) zero frames in front, then a VALID conv (vae.py:229-231)
+    y.H = x.H / sH;
+    y.W = x.W / sW;
     y.C = cout;
     if (store == CONV_SHUFFLE_HW) {
       y.H *= 2;
@@ -192,7 +195,7 @@ struct Runner {
       y.C = cout / 2;
     }
     note(y);
-    flops += 2.0 * x.T * x.H * x.W * cout * static_cast<double>(ks * ks * ks) * x.C;
+    flops += 2.0 * y.T * (x.H / sH) * (x.W / sW) * cout * static_cast<double>(ks * ks * ks) * x.C;
     const int G = pl->v->cfg.norm_groups;
     if (stats && y.C % G == 0 && (y.C / G == 4 || y.C / G == 8 || y.C / G == 16)) y.gn = new_gn_slot();
     if (dry || rc) return y;
@@ -210,6 +213,9 @@ struct Runner {
     d.cW = x.W;
     d.cC = x.C;
     d.kt = d.kh = d.kw = ks;
+    d.sT = sT;
+    d.sH = sH;
+    d.sW = sW;
     d.W = W(name + ".weight");
     d.w_rows = w_rows > 0 ? w_rows : cout;
     d.bias = reinterpret_cast<const float*>(W(name + ".bias"));
@@ -583,5 +589,244 @@ extern "C" int dv_vae_blend(dv_vae_plan* p, void* out_dev, int out_dtype, void* 
     blend_kernel<float><<<blocks, 256, 0, st>>>(a, reinterpret_cast<float*>(out_dev));
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
+  return DV_OK;
+}
+
+// =================================================================================================
+// Encoder.  Reuses the decoder's plan machinery (rotating NDHWC buffers,
+// GroupNorm accumulator ring, mid-block attention scratch, tile table + blend kernel).
+// =================================================================================================
+struct dv_vae_enc_plan {
+  dv_vae_plan base;            // base.T/h/w: input frames, PIXEL height/width; base.tile: tile size in pixels
+  int Tl = 0, lh = 0, lw = 0;  // latent dims of the whole clip
+  float* moments = nullptr;    // fp32 [2z][Tl][lh][lw] scratch when the caller does not want the moments
+};
+
+namespace {
+
+__global__ void gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                       void* __restrict__ out, long long n, int out_bf16) {
+  // moments: [mean (n) | logvar (n)]; DiagonalGaussianDistribution.sample (vae.py:602-615)
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lv = fminf(fmaxf(moments[n + i], -30.0f), 20.0f);
+  const float v = moments[i] + expf(0.5f * lv) * noise[i];
+  if (out_bf16)
+    reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16(v);
+  else
+    reinterpret_cast<float*>(out)[i] = v;
+}
+
+}  // namespace
+
+// encoder + quant_conv of one pixel tile (vae.py:671-689, :859-860)
+static int run_enc_tile(dv_vae_enc_plan* ep, const void* x, int x_bf16, int ti, int tj, cudaStream_t st,
+                        bool dry, double* flops, long long* max_elems) {
+  dv_vae_plan* p = &ep->base;
+  const dv_vae_config& c = p->v->cfg;
+  Runner r;
+  r.pl = p;
+  r.st = st;
+  r.dry = dry;
+  const int y0 = p->ys[ti], x0 = p->xs[tj];
+  const int th = std::min(p->tile, p->h - y0), tw = std::min(p->tile, p->w - x0);
+  if (th % 64 || tw % 128) {
+    set_error("vae encode: pixel tile %dx%d must be a multiple of 64x128", th, tw);
+    return DV_ERR_INVALID;
+  }
+  __nv_bfloat16** B = p->buf;
+  Act a{B[0], p->T, th, tw, 64};  // 3 image channels padded to one 64-channel TMA box
+  r.note(a);
+  if (!dry) {
+    cudaError_t e = cudaMemsetAsync(p->gn_acc, 0,
+                                    static_cast<size_t>(p->gn_slots + 1) * p->gn_slot_elems * sizeof(double), st);
+    if (e != cudaSuccess) {
+      set_error("vae encode: memset of the GroupNorm accumulators: %s", cudaGetErrorString(e));
+      return DV_ERR_CUDA;
+    }
+    r.rc = launch_latent_tile(x, x_bf16, B[0], c.enc_in_channels, p->T, p->h, p->w, y0, x0, th, tw, 64, st);
+  }
+  int cur = 0;
+  auto other = [&](int k) { return (cur + k) & 3; };
+  a = r.conv("encoder.conv_in.conv", a, c.enc_block_channels[0], 3, CONV_PLAIN, 0, nullptr, B[other(1)], -1, true);
+  cur = other(1);
+  for (int i = 0; i < 4; ++i) {
+    const int co = c.enc_block_channels[i];
+    for (int j = 0; j < c.enc_layers_per_block[i]; ++j) {
+      a = r.resnet("encoder.down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), a, co, other(1),
+                   other(2), other(3));
+      cur = other(3);
+    }
+    if (c.enc_spatial_down[i]) {
+      a = r.conv("encoder.down_blocks." + std::to_string(i) + ".downsamplers.0.conv.conv", a, co, 3, CONV_PLAIN, 0,
+                 nullptr, B[other(1)], -1, !c.enc_temporal_down[i], 1, 2, 2);
+      cur = other(1);
+    }
+    if (c.enc_temporal_down[i]) {
+      a = r.conv("encoder.down_blocks." + std::to_string(i) + ".temporal_downsamplers.0.conv.conv", a, co, 3,
+                 CONV_PLAIN, 0, nullptr, B[other(1)], -1, true, 2, 1, 1);
+      cur = other(1);
+    }
+  }
+  const int top = c.enc_block_channels[3];
+  a = r.resnet("encoder.mid_block.resnets.0", a, top, other(1), other(2), other(3));
+  cur = other(3);
+  a = r.attention("encoder.mid_block.attentions.0", a, other(1), other(3));
+  cur = other(3);
+  a = r.resnet("encoder.mid_block.resnets.1", a, top, other(1), other(2), other(3));
+  cur = other(3);
+  a = r.gn("encoder.conv_norm_out", a, true, B[other(1)]);
+  cur = other(1);
+  // conv_out (top -> 2z) and quant_conv (1x1x1), both padded to 64 channels so that they chain
+  a = r.conv("encoder.conv_out.conv", a, 64, 3, CONV_PLAIN, 0, nullptr, B[other(1)], 64);
+  cur = other(1);
+  TileOut& to = p->tiles[ti * p->cols + tj];
+  Act m = r.conv("quant_conv.conv", a, 64, 1, CONV_PLAIN, 0, nullptr, to.px, 64);
+  if (dry) {
+    to.H = m.H;
+    to.W = m.W;
+    to.C = 64;
+    p->Tout = m.T;
+  }
+  if (flops) *flops += r.flops;
+  if (max_elems && r.max_elems > *max_elems) *max_elems = r.max_elems;
+  return r.rc;
+}
+
+extern "C" void dv_vae_enc_plan_destroy(dv_vae_enc_plan* ep) {
+  if (!ep) return;
+  for (void* a : ep->base.allocs) cudaFree(a);
+  delete ep;
+}
+
+extern "C" int dv_vae_enc_plan_create(dv_vae* v, int T, int H, int W, int tile_px, dv_vae_enc_plan** out) {
+  DV_REQUIRE(v && out, "dv_vae_enc_plan_create: null argument");
+  DV_REQUIRE(v->cfg.enc_block_channels[0] > 0, "dv_vae_enc_plan_create: the encoder's weights were not loaded");
+  DV_REQUIRE(T >= 1 && H >= 64 && W >= 128 && tile_px >= 128, "dv_vae_enc_plan_create: T=%d H=%d W=%d tile=%d", T, H,
+             W, tile_px);
+  int downs = 0;
+  for (int i = 0; i < 4; ++i) downs += v->cfg.enc_spatial_down[i] ? 1 : 0;
+  DV_REQUIRE(downs == 3, "dv_vae_enc_plan_create: %d spatial down-samplings (3 supported: /8)", downs);
+  dv_vae_enc_plan* ep = new dv_vae_enc_plan();
+  dv_vae_plan* p = &ep->base;
+  p->v = v;
+  p->T = T;
+  p->h = H;
+  p->w = W;
+  p->tile = tile_px;
+  auto fail = [&](int rc) {
+    dv_vae_enc_plan_destroy(ep);
+    return rc;
+  };
+  // tile origins (vae.py:955,961-963): every 3/4 tile when the frame exceeds one tile
+  const bool tiled = (H > tile_px) || (W > tile_px);
+  if (tiled) {
+    const int stride = (tile_px * 3) / 4;
+    for (int y = 0; y < H; y += stride) p->ys.push_back(y);
+    for (int x = 0; x < W; x += stride) p->xs.push_back(x);
+  } else {
+    p->ys.assign(1, 0);
+    p->xs.assign(1, 0);
+    p->tile = H > W ? H : W;
+  }
+  p->rows = static_cast<int>(p->ys.size());
+  p->cols = static_cast<int>(p->xs.size());
+  p->tiles.resize(static_cast<size_t>(p->rows) * p->cols);
+  long long max_elems = 0;
+  for (int i = 0; i < p->rows; ++i)
+    for (int j = 0; j < p->cols; ++j) {
+      int rc = run_enc_tile(ep, nullptr, 0, i, j, 0, true, &p->flops, &max_elems);
+      if (rc) return fail(rc);
+    }
+  ep->Tl = p->Tout;
+  ep->lh = H / 8;
+  ep->lw = W / 8;
+  p->buf_elems = max_elems;
+  int rc = 0;
+  for (int k = 0; k < 4; ++k)
+    if ((rc = plan_alloc(p, &p->buf[k], max_elems)) != 0) return fail(rc);
+  const int top = v->cfg.enc_block_channels[3];
+  const long long pix = static_cast<long long>(p->tile / 8) * (p->tile / 8);
+  const int Tm = ep->Tl;  // the mid block runs at latent resolution
+  if ((rc = plan_alloc(p, &p->qk, static_cast<long long>(Tm) * pix * 3 * top)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->vt, static_cast<long long>(Tm) * pix * top)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->sc, static_cast<long long>(Tm) * pix * pix)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->pr, static_cast<long long>(Tm) * pix * pix)) != 0) return fail(rc);
+  const int max_frames = T + 8;
+  p->gn_replica_elems = max_frames * 64 * 2;
+  p->gn_slot_elems = dv_vae_plan::kGnReplicas * p->gn_replica_elems;
+  if ((rc = plan_alloc(p, &p->gn_acc, static_cast<long long>(p->gn_slots + 1) * p->gn_slot_elems)) != 0)
+    return fail(rc);
+  for (auto& to : p->tiles)
+    if ((rc = plan_alloc(p, &to.px, static_cast<long long>(p->Tout) * to.H * to.W * to.C)) != 0) return fail(rc);
+  if ((rc = plan_alloc(p, &p->tiles_dev, static_cast<long long>(p->tiles.size()))) != 0) return fail(rc);
+  const long long mom = 2LL * v->cfg.latent_channels * ep->Tl * ep->lh * ep->lw;
+  if ((rc = plan_alloc(p, &ep->moments, mom)) != 0) return fail(rc);
+  cudaError_t e = cudaMemcpy(p->tiles_dev, p->tiles.data(), p->tiles.size() * sizeof(TileOut), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("dv_vae_enc_plan_create: %s", cudaGetErrorString(e));
+    return fail(DV_ERR_CUDA);
+  }
+  *out = ep;
+  return DV_OK;
+}
+
+extern "C" double dv_vae_enc_plan_flops(const dv_vae_enc_plan* p) { return p ? p->base.flops : 0.0; }
+
+extern "C" int dv_vae_enc_plan_latent_dims(const dv_vae_enc_plan* p, int* t, int* h, int* w) {
+  DV_REQUIRE(p && t && h && w, "dv_vae_enc_plan_latent_dims: null argument");
+  *t = p->Tl;
+  *h = p->lh;
+  *w = p->lw;
+  return DV_OK;
+}
+
+extern "C" int dv_gaussian_sample(const float* moments_dev, const float* noise_dev, void* sample_dev,
+                                  long long n, int sample_dtype, void* stream) {
+  DV_REQUIRE(moments_dev && noise_dev && sample_dev && n > 0, "dv_gaussian_sample: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  gaussian_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      moments_dev, noise_dev, sample_dev, n, sample_dtype == DV_DTYPE_BF16);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return DV_OK;
+}
+
+extern "C" int dv_vae_encode(dv_vae_enc_plan* ep, const void* x_dev, int x_dtype, float* moments_dev,
+                             const float* noise_dev, void* sample_dev, int sample_dtype, void* stream) {
+  DV_REQUIRE(ep && x_dev, "dv_vae_encode: null argument");
+  DV_REQUIRE((noise_dev == nullptr) == (sample_dev == nullptr), "dv_vae_encode: noise and sample go together");
+  dv_vae_plan* p = &ep->base;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < p->rows; ++i)
+    for (int j = 0; j < p->cols; ++j) {
+      int rc = run_enc_tile(ep, x_dev, x_dtype == DV_DTYPE_BF16, i, j, st, false, nullptr, nullptr);
+      if (rc) return rc;
+    }
+  float* mom = moments_dev ? moments_dev : ep->moments;
+  // blend_v / blend_h + crop + concat of the moment tiles (vae.py:970-983)
+  BlendArgs a;
+  a.tiles = p->tiles_dev;
+  a.rows = p->rows;
+  a.cols = p->cols;
+  a.Tout = ep->Tl;
+  a.Hout = ep->lh;
+  a.Wout = ep->lw;
+  const int tl = p->tile / 8;
+  a.extent = tl / 4;          // blend_extent = tile_latent_min_size * 0.25
+  a.limit = tl - a.extent;    // row_limit
+  if (p->rows == 1 && p->cols == 1) a.limit = (a.Hout > a.Wout ? a.Hout : a.Wout) + 1;
+  a.nch = 2 * p->v->cfg.latent_channels;
+  const long long total = static_cast<long long>(a.nch) * a.Tout * a.Hout * a.Wout;
+  blend_kernel<float><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(a, mom);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  if (sample_dev != nullptr) {
+    const long long n = total / 2;
+    gaussian_sample_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+        mom, noise_dev, sample_dev, n, sample_dtype == DV_DTYPE_BF16);
+    DV_CHECK_CUDA(cudaGetLastError());
+    note_launch();
+  }
   return DV_OK;
 }

@@ -98,8 +98,97 @@ def pack_decoder_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Dict
     return out
 
 
+def pack_encoder_weights(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Dict[str, torch.Tensor]:
+    """The encoder's state dict (encoder.* + quant_conv, reference names) in the layout of
+    pack_decoder_weights: conv weights bf16 [Cout_rows][27 * Cin_pad] (conv_in's 3 input channels padded
+    to 64; conv_out and quant_conv padded to 64 rows / 64 input channels so that they chain), norm
+    affines and biases fp32, the mid-block attention's q|k|v fused."""
+    out: Dict[str, torch.Tensor] = {}
+
+    def pad_to(t, n, dim=0):
+        if t.shape[dim] >= n:
+            return t
+        pad = [0, 0] * (t.dim() - dim - 1) + [0, n - t.shape[dim]]
+        return F.pad(t, pad)
+
+    def conv(name, rows=None):
+        w = sd[name + ".weight"].float()
+        b = sd[name + ".bias"].float()
+        co, ci = w.shape[0], w.shape[1]
+        cip = (ci + 63) // 64 * 64
+        w = pad_to(w.permute(0, 2, 3, 4, 1), cip, dim=4).reshape(co, -1)
+        if rows is not None:
+            w = pad_to(w, rows, dim=0)
+        b = pad_to(b, max(32, (b.shape[0] + 31) // 32 * 32, rows or 0))
+        out[name + ".weight"] = w.to(device=device, dtype=torch.bfloat16).contiguous()
+        out[name + ".bias"] = b.to(device=device, dtype=torch.float32).contiguous()
+
+    def vec(name):
+        out[name] = sd[name].to(device=device, dtype=torch.float32).contiguous()
+
+    def resnet(name):
+        for n in ("norm1", "norm2"):
+            vec(f"{name}.{n}.weight")
+            vec(f"{name}.{n}.bias")
+        conv(name + ".conv1.conv")
+        conv(name + ".conv2.conv")
+        if name + ".conv_shortcut.conv.weight" in sd:
+            conv(name + ".conv_shortcut.conv")
+
+    chans = list(cfg["encoder_block_out_channels"])
+    conv("encoder.conv_in.conv")
+    for i in range(len(chans)):
+        for j in range(cfg["encoder_layers_per_block"][i]):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}")
+        if cfg["encoder_spatial_down_sample"][i]:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv.conv")
+        if cfg["encoder_temporal_down_sample"][i]:
+            conv(f"encoder.down_blocks.{i}.temporal_downsamplers.0.conv.conv")
+    a = "encoder.mid_block.attentions.0."
+    vec(a + "group_norm.weight")
+    vec(a + "group_norm.bias")
+    out[a + "to_qkv.weight"] = torch.cat([sd[a + "to_q.weight"], sd[a + "to_k.weight"], sd[a + "to_v.weight"]]) \
+        .to(device=device, dtype=torch.bfloat16).contiguous()
+    out[a + "to_qkv.bias"] = torch.cat([sd[a + "to_q.bias"], sd[a + "to_k.bias"], sd[a + "to_v.bias"]]) \
+        .to(device=device, dtype=torch.float32).contiguous()
+    out[a + "to_out.0.weight"] = sd[a + "to_out.0.weight"].to(device=device, dtype=torch.bfloat16).contiguous()
+    vec(a + "to_out.0.bias")
+    resnet("encoder.mid_block.resnets.0")
+    resnet("encoder.mid_block.resnets.1")
+    vec("encoder.conv_norm_out.weight")
+    vec("encoder.conv_norm_out.bias")
+    conv("encoder.conv_out.conv", rows=64)
+    conv("quant_conv.conv", rows=64)
+    return out
+
+
+class B200LatentDist:
+    """`DiagonalGaussianDistribution` of the reference (vae.py:599-628) over device moments."""
+
+    def __init__(self, lib, moments: torch.Tensor, dtype):
+        self._lib, self.parameters, self._dtype = lib, moments, dtype
+        self.mean, lv = torch.chunk(moments, 2, dim=1)
+        self.logvar = torch.clamp(lv, -30.0, 20.0)
+
+    def sample(self, generator=None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device, dtype=torch.float32)
+        return self.sample_with_noise(noise)
+
+    def sample_with_noise(self, noise: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.mean.shape, device=self.parameters.device, dtype=self._dtype)
+        noise = noise.to(device=self.parameters.device, dtype=torch.float32).contiguous()
+        check(self._lib.dv_gaussian_sample(self.parameters.data_ptr(), noise.data_ptr(), out.data_ptr(),
+                                           out.numel(), _lib.dtype_code(self._dtype), _lib.stream_ptr()),
+              "dv_gaussian_sample")
+        self._keep = noise
+        return out
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
 class B200VAE:
-    """Drop-in for the decode side of reference `CausalVideoVAE`."""
+    """Drop-in for reference `CausalVideoVAE`: decode, and encode when the encoder's weights are given."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], config: dict, device="cuda",
                  dtype=torch.bfloat16, reference_encoder=None):
@@ -112,6 +201,9 @@ class B200VAE:
         self.use_tiling = False
         self.reference_encoder = reference_encoder
         self._packed = pack_decoder_weights(state_dict, config, self.device)
+        self.has_encoder = "encoder.conv_in.conv.weight" in state_dict
+        if self.has_encoder:
+            self._packed.update(pack_encoder_weights(state_dict, config, self.device))
         self._names = [n.encode() for n in self._packed]
         refs = (TensorRef * len(self._packed))()
         for i, (n, t) in enumerate(self._packed.items()):
@@ -126,6 +218,13 @@ class B200VAE:
             c.spatial_up[i] = int(config["decoder_spatial_up_sample"][i])
             c.temporal_up[i] = int(config["decoder_temporal_up_sample"][i])
         c.norm_groups = config.get("decoder_norm_num_groups", 32)
+        if self.has_encoder:
+            c.enc_in_channels = config.get("encoder_in_channels", 3)
+            for i in range(4):
+                c.enc_block_channels[i] = config["encoder_block_out_channels"][i]
+                c.enc_layers_per_block[i] = config["encoder_layers_per_block"][i]
+                c.enc_spatial_down[i] = int(config["encoder_spatial_down_sample"][i])
+                c.enc_temporal_down[i] = int(config["encoder_temporal_down_sample"][i])
         self._handle = C.c_void_p()
         check(self.lib.dv_vae_create(C.byref(c), refs, len(self._packed), C.byref(self._handle)),
               "dv_vae_create")
@@ -230,16 +329,62 @@ class B200VAE:
         self._last = zs
         return outs
 
-    def encode(self, x, *a, **k):
-        if self.reference_encoder is None:
-            raise _lib.DeepVError("B200VAE.encode: the encoder is outside the hot path (SURVEY.md §8 "
-                                  "f1); pass reference_encoder= to delegate")
-        return self.reference_encoder.encode(x, *a, **k)
+    def encode(self, x, return_dict: bool = True, is_init_image=True, temporal_chunk=False, window_size=16,
+               tile_sample_min_size=256):
+        """Reference signature vae.py:844-847; the rollout calls `vae.encode(x).latent_dist.sample()`
+        (pipeline.py:250-251,569,574), i.e. the tiled, un-chunked encode.  x: [1,3,T,H,W] on the GPU."""
+        if not self.has_encoder:
+            if self.reference_encoder is None:
+                raise _lib.DeepVError("B200VAE.encode: no encoder weights were given (and no reference_encoder= "
+                                      "to delegate to)")
+            return self.reference_encoder.encode(x, return_dict, is_init_image, temporal_chunk, window_size,
+                                                 tile_sample_min_size)
+        if temporal_chunk:
+            raise _lib.DeepVError("B200VAE.encode: temporal_chunk=True (window cache) is not built; the rollout "
+                                  "never uses it for encoding")
+        _lib.require_cuda(x)
+        if x.shape[0] != 1:
+            parts = [self.encode(x[i:i + 1], True, is_init_image, False, window_size, tile_sample_min_size)
+                     .latent_dist.parameters for i in range(x.shape[0])]
+            return SimpleNamespace(latent_dist=B200LatentDist(self.lib, torch.cat(parts, dim=0), self.dtype))
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        _, _, T, H, W = x.shape
+        tile = int(tile_sample_min_size) if self.use_tiling else max(H, W)
+        key = ("enc", T, H, W, tile)
+        plan = self._enc_plans.get(key) if hasattr(self, "_enc_plans") else None
+        if plan is None:
+            if not hasattr(self, "_enc_plans"):
+                self._enc_plans = {}
+            hdl = C.c_void_p()
+            check(self.lib.dv_vae_enc_plan_create(self._handle, T, H, W, tile, C.byref(hdl)), "dv_vae_enc_plan_create")
+            plan = self._enc_plans[key] = hdl.value
+        t, h, w = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.dv_vae_enc_plan_latent_dims(plan, C.byref(t), C.byref(h), C.byref(w)))
+        zc = self.config["encoder_out_channels"]
+        moments = torch.empty((1, 2 * zc, t.value, h.value, w.value), device=x.device, dtype=torch.float32)
+        check(self.lib.dv_vae_encode(plan, x.data_ptr(), _lib.dtype_code(x.dtype), moments.data_ptr(), None, None, 0,
+                                     _lib.stream_ptr()), "dv_vae_encode")
+        self._last_enc = x
+        dist_ = B200LatentDist(self.lib, moments, self.dtype)
+        return SimpleNamespace(latent_dist=dist_) if return_dict else (dist_,)
+
+    def enc_plan_flops(self, T, H, W, tile=256) -> float:
+        hdl = C.c_void_p()
+        check(self.lib.dv_vae_enc_plan_create(self._handle, T, H, W, tile, C.byref(hdl)), "dv_vae_enc_plan_create")
+        f = self.lib.dv_vae_enc_plan_flops(hdl)
+        self.lib.dv_vae_enc_plan_destroy(hdl)
+        return f
 
     def close(self):
         for p in self._plans.values():
             self.lib.dv_vae_plan_destroy(p)
         self._plans.clear()
+        for p in getattr(self, "_enc_plans", {}).values():
+            self.lib.dv_vae_enc_plan_destroy(p)
+        if hasattr(self, "_enc_plans"):
+            self._enc_plans.clear()
         if self._handle:
             self.lib.dv_vae_destroy(self._handle)
             self._handle = C.c_void_p()

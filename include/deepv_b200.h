@@ -219,6 +219,12 @@ typedef struct {
   int spatial_up[4];          /* per up block (in decoder order): 1,1,1,0 */
   int temporal_up[4];         /* 1,1,1,0 */
   int norm_groups;            /* 32 */
+  /* encoder (all zero when only the decoder's weights are loaded) */
+  int enc_in_channels;        /* 3  */
+  int enc_block_channels[4];  /* encoder_block_out_channels, e.g. 128,256,512,512 */
+  int enc_layers_per_block[4];/* e.g. 2,2,2,2 */
+  int enc_spatial_down[4];    /* 1,1,1,0 */
+  int enc_temporal_down[4];   /* 1,1,1,0 */
 } dv_vae_config;
 
 /* Weights are passed as a flat name-ordered table built by the host side (see
@@ -256,6 +262,28 @@ int dv_vae_plan_bind_tile(dv_vae_plan* p, int tile, void* buf_dev);
 int dv_vae_decode_tiles(dv_vae_plan* p, const void* z_dev, int z_dtype,
                         unsigned long long tile_mask, void* stream);
 int dv_vae_blend(dv_vae_plan* p, void* out_dev, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Causal video VAE encoder (row f1): `vae.encode(x)` as the rollout calls it (pipeline.py:250-251,
+ * 569,574) -> CausalVideoVAE.encode with tiling on and temporal_chunk=False (vae.py:844-883,
+ * 954-987): 256-px tiles every 192 px, encoder + quant_conv per tile (vae.py:630-689), 8-latent
+ * linear blends, 24-latent crops, DiagonalGaussianDistribution (vae.py:599-615).
+ * A plan fixes the clip [1][3][T][H][W]; tiles must be multiples of 64 x 128 pixels.
+ *   x_dev        [1][3][T][H][W] (x_dtype)
+ *   moments_dev  fp32 [1][2z][T'][H/8][W/8] (mean | logvar), T' = three causal halvings of T; or NULL
+ *   noise_dev    fp32 [1][z][T'][H/8][W/8] standard-normal draw, or NULL (then no sample)
+ *   sample_dev   [1][z][T'][H/8][W/8] (sample_dtype) = mean + exp(0.5 clamp(logvar,-30,20)) noise; or NULL
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dv_vae_enc_plan dv_vae_enc_plan;
+int dv_vae_enc_plan_create(dv_vae* v, int T, int H, int W, int tile_px, dv_vae_enc_plan** out);
+void dv_vae_enc_plan_destroy(dv_vae_enc_plan* p);
+double dv_vae_enc_plan_flops(const dv_vae_enc_plan* p);
+int dv_vae_enc_plan_latent_dims(const dv_vae_enc_plan* p, int* t, int* h, int* w);
+/* DiagonalGaussianDistribution.sample (vae.py:602-615) on moments [mean (n) | logvar (n)] */
+int dv_gaussian_sample(const float* moments_dev, const float* noise_dev, void* sample_dev, long long n,
+                       int sample_dtype, void* stream);
+int dv_vae_encode(dv_vae_enc_plan* p, const void* x_dev, int x_dtype, float* moments_dev,
+                  const float* noise_dev, void* sample_dev, int sample_dtype, void* stream);
 
 #ifdef __cplusplus
 }

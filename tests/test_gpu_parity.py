@@ -240,3 +240,33 @@ def test_generate_one_unit_vs_oracle(dit2):
         print(f"unit stage {i}: latent max|a-b|/max|ref| = {e:.3e}")
         assert out[i].shape == ref[i].shape
         assert e <= 3e-2  # ~2% latent drift per unit for bf16 vs fp32
+
+
+# ---------------------------------------------------------------------------------------------
+# VAE encode
+@pytest.mark.parametrize("video", [(1, 3, 1, 64, 128), (1, 3, 9, 320, 320), (1, 3, 17, 384, 512)])
+def test_vae_tiled_encode_vs_oracle(video):
+    """`vae.encode(x)` with tiling on (vae.py:844-883,954-987): moments against the fp32 oracle
+    restatement (itself pinned to the real reference, tests/test_oracle_golden.py); tolerance as for
+    the denoiser: max|a-b| / max|ref| <= 2e-2 with bf16 activations."""
+    from deepv_b200.vae import B200VAE
+    over = dict(decoder_block_out_channels=(128, 128, 128, 128), encoder_block_out_channels=(128, 128, 256, 256),
+                decoder_layers_per_block=(1, 1, 1, 1), encoder_layers_per_block=(1, 2, 1, 1))
+    cfg, W = weights.vae_weights(over, seed=11, encoder=True)
+    v = B200VAE(W, cfg, dtype=torch.float32)
+    v.enable_tiling()
+    x = torch.randn(*video, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        ref = vae_ref.tiled_encode(W, cfg, x)
+    dist = v.encode(x.cuda()).latent_dist
+    torch.cuda.synchronize()
+    m = dist.parameters
+    assert m.shape == ref.shape
+    err = rel_max(m, ref)
+    print(f"vae encode {video}: moments max|a-b|/max|ref| = {err:.3e} (ref absmax {ref.abs().max():.2f})")
+    assert err <= 2e-2
+    # the sample with an injected draw: mean + exp(0.5 clamp(logvar)) * noise, bit-for-bit in fp32
+    noise = torch.randn(dist.mean.shape, generator=torch.Generator().manual_seed(13))
+    z = dist.sample_with_noise(noise.cuda())
+    want = vae_ref.gaussian_sample(m.cpu(), noise)
+    assert (z.cpu() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
