@@ -76,6 +76,7 @@ SIGNATURES = {
     "dv_cfg_euler_step": (_i, [_vp, _i, _vp, _vp, _ll, _f, _f, _d, _d, _i, _vp]),
     "dv_stage_renoise": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _i, _vp]),
     "dv_block_noise": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp]),
+    "dv_resize_half": (_i, [_vp, _vp, _ll, _i, _i, _f, _i, _vp]),
     "dv_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dv_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dv_conv3d_cl": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

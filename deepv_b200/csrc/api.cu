@@ -44,6 +44,12 @@ extern "C" int dv_stage_renoise(const void* lat_lo_dev, const void* noise_dev, v
                               dtype == DV_DTYPE_BF16, S(stream));
 }
 
+extern "C" int dv_resize_half(const void* in_dev, void* out_dev, long long planes, int H, int W, float scale,
+                              int dtype, void* stream) {
+  DV_REQUIRE(in_dev && out_dev && planes > 0, "dv_resize_half: bad argument");
+  return launch_resize_half(in_dev, out_dev, planes, H, W, scale, dtype == DV_DTYPE_BF16, S(stream));
+}
+
 extern "C" int dv_block_noise(const float* z_dev, void* out_dev, int planes, int h, int w,
                               float gamma, int dtype, void* stream) {
   DV_REQUIRE(z_dev && out_dev, "dv_block_noise: null pointer");

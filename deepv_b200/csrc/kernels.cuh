@@ -74,6 +74,10 @@ int launch_stage_renoise(const void* lat_lo, const void* noise, void* out, int p
 int launch_block_noise(const float* z, void* out, int planes, int h, int w, float gamma,
                        int is_bf16, cudaStream_t stream);
 
+// bilinear 1/2 down-sampling of [planes][H][W], ATen's rounding sequence (pipeline.py:226-240,554-557)
+int launch_resize_half(const void* in, void* out, long long planes, int H, int W, float scale, int is_bf16,
+                       cudaStream_t stream);
+
 // ---- VAE elementwise (vae_kernels.cu) ---------------------------------------------------
 // y = silu?( (x - mean) * rstd * gamma + beta ) over channels-last bf16 [frames][HW][C]
 // acc: `replicas` copies (stride in doubles) of [frames][G][2] fp64 (sum, sum of squares)

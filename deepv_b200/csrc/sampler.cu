@@ -200,4 +200,68 @@ int launch_block_noise(const float* z, void* out, int planes, int h, int w, floa
   return 0;
 }
 
+namespace {
+// ---------------------------------------------------------------------------------------
+// Bilinear down-sampling by exactly 2 (pipeline.py:226-240 get_pyramid_latent, :554-557 initial
+// noise pyramid; F.interpolate(mode='bilinear', align_corners=False)): source index 2*o + 0.5, both
+// lambdas 0.5, ATen's association  0.5*(0.5*a + 0.5*b) + 0.5*(0.5*c + 0.5*d)  in fp32 — every
+// scaling by 0.5 is exact, so the three additions below round exactly where ATen's do.  `scale`
+// is a separate multiply of the rounded result (the reference's `* 2` on the noise latents).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void resize_half_kernel(const T* __restrict__ in, T* __restrict__ out, long long planes, int H,
+                                   int W, float scale) {
+  const int oh = H / 2, ow = W / 2;
+  const long long total = planes * oh * ow;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int x = static_cast<int>(idx % ow);
+  const int y = static_cast<int>((idx / ow) % oh);
+  const long long pl = idx / (static_cast<long long>(ow) * oh);
+  const T* src = in + (pl * H + 2 * y) * W + 2 * x;
+  float a, b, c, d;
+  if constexpr (sizeof(T) == 2) {
+    a = __bfloat162float(src[0]);
+    b = __bfloat162float(src[1]);
+    c = __bfloat162float(src[W]);
+    d = __bfloat162float(src[W + 1]);
+  } else {
+    a = src[0];
+    b = src[1];
+    c = src[W];
+    d = src[W + 1];
+  }
+  const float top = __fmul_rn(0.5f, __fadd_rn(a, b));
+  const float bot = __fmul_rn(0.5f, __fadd_rn(c, d));
+  const float v = __fmul_rn(0.5f, __fadd_rn(top, bot));
+  if constexpr (sizeof(T) == 2) {
+    const __nv_bfloat16 r = __float2bfloat16(v);
+    out[idx] = scale == 1.0f ? r : __float2bfloat16(__fmul_rn(__bfloat162float(r), scale));
+  } else {
+    out[idx] = scale == 1.0f ? v : __fmul_rn(v, scale);
+  }
+}
+
+}  // namespace
+
+int launch_resize_half(const void* in, void* out, long long planes, int H, int W, float scale, int is_bf16,
+                       cudaStream_t stream) {
+  DV_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2, "resize_half: H=%d W=%d must be even", H, W);
+  const long long total = planes * (H / 2) * (W / 2);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (is_bf16)
+    resize_half_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                                 reinterpret_cast<__nv_bfloat16*>(out), planes, H, W,
+                                                                 scale);
+  else
+    resize_half_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(in),
+                                                          reinterpret_cast<float*>(out), planes, H, W, scale);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+namespace {
+}  // namespace
+
 }  // namespace dv

@@ -143,6 +143,34 @@ class B200Pipeline:
             intermed.append(latents)
         return intermed
 
+    # -- pipeline.py:226-240 / 554-557 --------------------------------------------------------------
+    def resize_half(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """F.interpolate(x, size=(h//2, w//2), mode='bilinear') (* scale) of [..., h, w] on the GPU,
+        bit-equal to ATen (dv_resize_half)."""
+        _lib.require_cuda(x)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        h, w = x.shape[-2], x.shape[-1]
+        out = torch.empty(x.shape[:-2] + (h // 2, w // 2), device=x.device, dtype=x.dtype)
+        check(self.lib.dv_resize_half(x.data_ptr(), out.data_ptr(), x.numel() // (h * w), h, w, float(scale),
+                                      _lib.dtype_code(x.dtype), _lib.stream_ptr()), "dv_resize_half")
+        return out
+
+    def get_pyramid_latent(self, x: torch.Tensor, stage_num: int) -> List[torch.Tensor]:
+        """pipeline.py:226-240: [x/2^stage_num, ..., x/2, x] (per-frame bilinear halvings)."""
+        out = [x]
+        for _ in range(stage_num):
+            x = self.resize_half(x)
+            out.append(x)
+        return list(reversed(out))
+
+    def noise_pyramid_base(self, latents: torch.Tensor) -> torch.Tensor:
+        """pipeline.py:554-557: the stage-0 noise = repeated (bilinear half) * 2 of the full-resolution draw."""
+        for _ in range(len(self.model_cfg["stages"]) - 1):
+            latents = self.resize_half(latents, 2.0)
+        return latents
+
     # -- pipeline.py:621-658 ------------------------------------------------------------------------
     def pyramid_conditions(self, generated: torch.Tensor, unit_index: int, firstframe_mask: bool,
                            n_branch: int) -> List[List[torch.Tensor]]:
@@ -150,15 +178,7 @@ class B200Pipeline:
         stage lower each, everything older than that at stage 0; oldest first."""
         nst = len(self.model_cfg["stages"])
         fpu = self.model_cfg["frame_per_unit"]
-        pyr = [generated]
-        x = generated
-        for _ in range(nst - 1):
-            b, c, t, h, w = x.shape
-            x2 = F.interpolate(x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w), size=(h // 2, w // 2),
-                               mode="bilinear")
-            x = x2.view(b, t, c, h // 2, w // 2).permute(0, 2, 1, 3, 4)
-            pyr.append(x)
-        pyr = list(reversed(pyr))
+        pyr = self.get_pyramid_latent(generated, nst - 1)
         rep = (lambda z: torch.cat([z] * n_branch)) if n_branch > 1 else (lambda z: z)
         out = []
         for i_s in range(nst):

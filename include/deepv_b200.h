@@ -65,6 +65,10 @@ int dv_stage_renoise(const void* lat_lo_dev, const void* noise_dev, void* out_de
                      int h, int w, double alpha, double beta, int dtype, void* stream);
 /* z_dev: iid N(0,1) fp32 [planes][h/2][w/2][4]; out_dev: [planes][h][w] with
  * cov(2x2 block) = (1+gamma) I - gamma 11^T                                                   */
+/* Bilinear down-sampling by 2 of [planes][H][W] (get_pyramid_latent pipeline.py:226-240; the initial
+ * noise pyramid pipeline.py:554-557 with scale = 2): bit-equal to F.interpolate(mode='bilinear').   */
+int dv_resize_half(const void* in_dev, void* out_dev, long long planes, int H, int W, float scale,
+                   int dtype, void* stream);
 int dv_block_noise(const float* z_dev, void* out_dev, int planes, int h, int w, float gamma,
                    int dtype, void* stream);
 

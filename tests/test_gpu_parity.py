@@ -270,3 +270,29 @@ def test_vae_tiled_encode_vs_oracle(video):
     z = dist.sample_with_noise(noise.cuda())
     want = vae_ref.gaussian_sample(m.cpu(), noise)
     assert (z.cpu() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------
+# pyramid resampling
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_resize_half_bit_exact_vs_aten(lib, dtype):
+    """get_pyramid_latent (pipeline.py:226-240) and the initial noise pyramid (:554-557): bilinear
+    halving (and `* 2`) bit-equal to F.interpolate on the same device."""
+    import ctypes as C
+
+    import torch.nn.functional as F
+
+    from deepv_b200 import _lib
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(2, 38, 3, 48, 64, generator=g) * 3).to(dtype).cuda()
+    b, c, t, h, w = x.shape
+    for scale in (1.0, 2.0):
+        out = torch.empty(b, c, t, h // 2, w // 2, device="cuda", dtype=dtype)
+        _lib.check(lib.dv_resize_half(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), b * c * t, h, w, scale,
+                                      _lib.dtype_code(dtype), None))
+        torch.cuda.synchronize()
+        ref = F.interpolate(x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w), size=(h // 2, w // 2), mode="bilinear")
+        ref = ref.view(b, t, c, h // 2, w // 2).permute(0, 2, 1, 3, 4)
+        if scale != 1.0:
+            ref = ref * scale
+        assert torch.equal(out, ref.contiguous()), (dtype, scale)
