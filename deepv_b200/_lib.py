@@ -114,6 +114,11 @@ SIGNATURES = {
     "dv_vae_plan_bind_tile": (_i, [_vp, _i, _vp]),
     "dv_vae_decode_tiles": (_i, [_vp, _vp, _i, C.c_ulonglong, _vp]),
     "dv_vae_blend": (_i, [_vp, _vp, _i, _vp]),
+    "dv_frames_requantise": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "dv_disparity_post": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dv_disparity_renorm": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
+    "dv_raymap_to_pose": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dv_camera_raymap": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
 }
 
 

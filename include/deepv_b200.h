@@ -289,6 +289,33 @@ int dv_gaussian_sample(const float* moments_dev, const float* noise_dev, void* s
 int dv_vae_encode(dv_vae_enc_plan* p, const void* x_dev, int x_dtype, float* moments_dev,
                   const float* noise_dev, void* sample_dev, int sample_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Rollout feedback on the device (row f3): what `InferencePipeline.generate` does on the host
+ * between two `generate_i2v` calls (pipeline.py:311-414), with no host synchronisation.
+ * Videos are [1][3][T][H][W]; poses are fp32 [n][4][4] row-major on the device.
+ * ------------------------------------------------------------------------------------------ */
+/* frames [t0, t0+n) -> uint8 (truncating, pipeline.py:341) -> ToTensor + Normalize(0.5, 0.5)
+ * (pipeline.py:564-567): out [1][3][n][H][W] (out_dtype); u8_dev (optional) [n][H][W][3], the PIL frames */
+int dv_frames_requantise(const void* frames_dev, int dtype, int T, int H, int W, int t0, int n,
+                         void* out_dev, int out_dtype, unsigned char* u8_dev, void* stream);
+/* pipeline.py:311-313: clamp(mean_c(raw) * 0.5 + 0.5, 0, 1)^2 / scale / 0.95 on 3 equal channels;
+ * scale_dev: device scalar of the previous iteration, NULL = 1 (first iteration); out fp32 */
+int dv_disparity_post(const void* raw_dev, int dtype, int T, int H, int W, const float* scale_dev,
+                      float* out_dev, void* stream);
+/* pipeline.py:346-350 (and :399-401 with clamp): if compute_scale, *scale_dev = 1 / max(disp[:, :, t0]);
+ * out [1][3][n][H][W] (out_dtype) = sqrt(disp * scale * 0.95) * 2 - 1 for frames [t0, t0+n) */
+int dv_disparity_renorm(const float* disp_dev, int T, int H, int W, int t0, int n, float* scale_dev,
+                        int compute_scale, int clamp, void* out_dev, int out_dtype, void* stream);
+/* pipeline.py:688-692 + raymap_to_trans_matrix :77-163 (append_first_reference, relative -> absolute):
+ * latents [1][C][T][h][w] (dtype) whose channels [c0, c0+6) hold the normalised ray map; frames 1..T-1
+ * are decoded.  trans3d_dev / trans2d_dev: fp32 [T][4][4] camera-to-world (frame 0 = identity) / intrinsics */
+int dv_raymap_to_pose(const void* latents_dev, int dtype, int C, int c0, int T, int h, int w, int ds,
+                      float* trans3d_dev, float* trans2d_dev, void* stream);
+/* get_raymap_from_camera_parameters(_batchversion) pipeline.py:29-75 for n cameras at H x W pixels:
+ * out [1][6][n][H/ds][W/ds] (out_dtype), (x - mean) / std applied when normalise (pipeline.py:300-301,258-259) */
+int dv_camera_raymap(const float* trans2d_dev, const float* trans3d_dev, int n, int H, int W, int ds,
+                     int normalise, void* out_dev, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,12 @@ ROLLOUT = dict(
     vae=dict(cfg=dict(decoder_block_out_channels=(32, 32, 64, 64), encoder_block_out_channels=(32, 32, 64, 64),
                       decoder_layers_per_block=(1, 1, 1, 1), encoder_layers_per_block=(1, 1, 1, 1)), wseed=8),
 )
+# the same rollout for the CUDA path: GroupNorm groups of >= 4 channels (128-wide VAE), 128x128 px
+ROLLOUT_GPU = dict(ROLLOUT, height=128, width=128, seed=81,
+                   vae=dict(cfg=dict(decoder_block_out_channels=(128, 128, 128, 128),
+                                     encoder_block_out_channels=(128, 128, 128, 128),
+                                     decoder_layers_per_block=(1, 1, 1, 1), encoder_layers_per_block=(1, 1, 1, 1)),
+                            wseed=9))
 ACTIONS = ("w", "a", "s", "d")
 
 
@@ -82,3 +88,51 @@ def digest_frames(v):
     """Compact, position-sensitive digest of a video [1,C,T,H,W]."""
     return dict(shape=tuple(v.shape), sub=v[:, :, ::4, ::8, ::8].clone().float(),
                 frame_mean=v.double().mean(dim=(1, 3, 4)).float(), frame_std=v.double().std(dim=(1, 3, 4)).float())
+
+
+class RecordingTape(NoiseTape):
+    """A tape that also keeps every draw, so a later run can replay a suffix of it (teacher forcing)."""
+
+    def __init__(self, seed):
+        super().__init__(seed)
+        self.draws = []
+
+    def randn(self, shape):
+        t = super().randn(shape)
+        self.draws.append(t)
+        return t
+
+    def block(self, bs, ch, temp, height, width, gamma):
+        t = super().block(bs, ch, temp, height, width, gamma)
+        self.draws.append(t)
+        return t
+
+
+class ReplayTape:
+    """Replays recorded draws from position `start`, checking the requested shapes."""
+
+    def __init__(self, draws, calls, start=0):
+        self.draws, self.expect, self.pos = draws, calls, start
+        self.calls = []
+
+    def _next(self, kind, shape):
+        want_kind, want_shape = self.expect[self.pos]
+        assert (kind, tuple(shape)) == (want_kind, tuple(want_shape)), (self.pos, kind, shape, want_kind, want_shape)
+        t = self.draws[self.pos]
+        self.pos += 1
+        self.calls.append((kind, tuple(shape)))
+        return t
+
+    def randn(self, shape):
+        return self._next("randn", shape)
+
+    def block(self, bs, ch, temp, height, width, gamma):
+        return self._next("block", (bs, ch, temp, height, width))
+
+
+def build_oracle_models(case=ROLLOUT):
+    from oracle import rollout_ref, scheduler_ref, weights
+    dcfg, DW = weights.mmdit_weights(case["dit"]["cfg"], seed=case["dit"]["wseed"])
+    vcfg, VW = weights.vae_weights(case["vae"]["cfg"], seed=case["vae"]["wseed"], encoder=True)
+    return rollout_ref.RolloutModels(dcfg, DW, vcfg, VW, scheduler_ref.pyramid_tables(**cases.SCHEDULER_KW),
+                                     text_embeds(case), dict(case["model_cfg"]))

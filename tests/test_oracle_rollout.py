@@ -13,17 +13,13 @@ from pathlib import Path
 import pytest
 import torch
 
-from oracle import rollout_ref, scheduler_ref, weights
-from tests.golden import cases, rollout_cases as rc
+from oracle import rollout_ref
+from tests.golden import rollout_cases as rc
 
 G = Path(__file__).resolve().parent / "golden"
 
 
-def build_models(case=rc.ROLLOUT):
-    dcfg, DW = weights.mmdit_weights(case["dit"]["cfg"], seed=case["dit"]["wseed"])
-    vcfg, VW = weights.vae_weights(case["vae"]["cfg"], seed=case["vae"]["wseed"], encoder=True)
-    return rollout_ref.RolloutModels(dcfg, DW, vcfg, VW, scheduler_ref.pyramid_tables(**cases.SCHEDULER_KW),
-                                     rc.text_embeds(case), dict(case["model_cfg"]))
+build_models = rc.build_oracle_models
 
 
 def close(a, b, tol, what):
