@@ -249,9 +249,12 @@ class B200Rollout:
 
     # -- pipeline.py:264-424 ------------------------------------------------------------------------
     @torch.no_grad()
-    def generate(self, batch_dict: Dict, noise=None, shard=None, trace: Optional[list] = None) -> Dict:
+    def generate(self, batch_dict: Dict, noise=None, shard=None, trace: Optional[list] = None,
+                 events: Optional[list] = None) -> Dict:
         """batch_dict: 'img' (PIL image, ndarray or uint8 tensor [H,W,3]), 'prompt' (sequence of action keys
-        or texts), 'prompt_type' ('action' | 'text').  Returns the reference's result dictionary."""
+        or texts), 'prompt_type' ('action' | 'text').  Returns the reference's result dictionary.
+        `events` (optional list) receives per iteration three CUDA events: start, after generate_i2v, after the
+        feedback — recorded on the current stream, nothing is synchronised here."""
         cfg = self.cfg
         units = cfg["max_temporal_length"]
         noise = noise or DeviceNoise(self.pipe)
@@ -267,6 +270,9 @@ class B200Rollout:
         start_unit = 0
         for it in range(iters):
             motion = total[0:1] + total[start_unit + 1:start_unit + units]                                # :296
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if events is not None else None
+            if ev:
+                ev[0].record()
             image, disparity, t3, t2 = self.generate_i2v(
                 motion, use_table, frames, in_disp, in_ray, in_hist, temp=units,
                 num_inference_steps=cfg.get("num_inference_steps", 10), noise=noise, shard=shard)
@@ -274,8 +280,13 @@ class B200Rollout:
                 trace.append(dict(motion_prompt=motion, frames=frames, input_disparity=in_disp, input_raymap=in_ray,
                                   input_history=in_hist, images=image, disparity=disparity, trans3d=t3, trans2d=t2))
             start_unit += units - NUM_INPUT_UNIT
+            if ev:
+                ev[1].record()
             disp = state.absorb(it, image, disparity, t3, t2, motion)
             frames, in_disp, in_ray, in_hist = state.next_inputs(image, disp, noise)
+            if ev:
+                ev[2].record()
+                events.append(ev)
         return {"pred_img": torch.cat(state.images, dim=2), "pred_disparity": torch.cat(state.disparitys, dim=2),
                 "motion_prompt_list": state.prompts, "trans3d": torch.cat(state.trans3d, dim=1),
                 "trans2d": torch.cat(state.trans2d, dim=1)}
