@@ -88,7 +88,7 @@ template <int NB>
 __global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(
     const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
     const float* __restrict__ in, int in_stride, float* __restrict__ out, int out_stride, int N,
-    int K, int silu_in, int accumulate) {
+    int K, int silu_in, int accumulate, int row_blocks) {
   extern __shared__ float s_in[];  // [NB][K]
   for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
     const int b = i / K, k = i - b * K;
@@ -97,10 +97,12 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * kGemvWarps + warp) * kGemvRowsPerWarp;
   // four weight rows in flight per warp (4 x 16 B loads per lane and k-step): the kernel is pure
-  // weight streaming, so memory-level parallelism is what sets its bandwidth
+  // weight streaming, so memory-level parallelism is what sets its bandwidth.  CTAs are persistent
+  // over row blocks, so the activation staging above (and its bubble) is paid once per CTA.
   constexpr int R = 4;
+  for (int blk = blockIdx.x; blk < row_blocks; blk += gridDim.x) {
+  const int row0 = (blk * kGemvWarps + warp) * kGemvRowsPerWarp;
   for (int rr = 0; rr < kGemvRowsPerWarp; rr += R) {
     const int n0 = row0 + rr;
     if (n0 >= N) break;
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(
         }
       }
     }
+  }
   }
 }
 
@@ -448,19 +451,23 @@ int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int 
   DV_REQUIRE(B >= 1 && B <= 4, "gemv: batch %d not in [1,4]", B);
   DV_REQUIRE(K % 8 == 0, "gemv: K=%d must be a multiple of 8", K);
   const int rows_per_cta = kGemvWarps * kGemvRowsPerWarp;
-  const int blocks = (N + rows_per_cta - 1) / rows_per_cta;
+  const int row_blocks = (N + rows_per_cta - 1) / rows_per_cta;
   const size_t smem = static_cast<size_t>(B) * K * sizeof(float);
 #define DV_GEMV(NB)                                                                              \
   do {                                                                                           \
-    static bool attr = false;                                                                    \
-    if (!attr) {                                                                                 \
+    static int occ = 0;                                                                          \
+    if (!occ) {                                                                                  \
       DV_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<NB>,                                        \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
-      attr = true;                                                                               \
+      DV_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemv_kernel<NB>,         \
+                                                                  kGemvWarps * 32, smem));       \
+      if (occ < 1) occ = 1;                                                                      \
     }                                                                                            \
+    const int resident = sm_count() * occ; /* persistent: one wave of resident CTAs */           \
+    const int blocks = row_blocks < resident ? row_blocks : resident;                            \
     gemv_kernel<NB><<<blocks, kGemvWarps * 32, smem, stream>>>(W, bias, in, in_stride, out,      \
                                                                out_stride, N, K, silu_in,        \
-                                                               accumulate);                      \
+                                                               accumulate, row_blocks);          \
   } while (0)
   DV_REQUIRE(smem <= 96 * 1024, "gemv: B*K too large for smem staging");
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(N) * K * 2.0, stream, N > 100000 ? "gemv_adaln" : "gemv");

@@ -105,6 +105,12 @@ class B200Pipeline:
             if history is not None:
                 history, history_mask = history[mb:mb + 1], history_mask[mb:mb + 1]
         n_local = 1 if sharded else n_branch
+        if self.model_cfg.get("no_need_depth", False):
+            # pipeline.py:476-478 zeroes channels 16.. (disparity + ray map) of every clip fed to the denoiser;
+            # the condition clips never change inside a unit, so they are cleared once, in place like the reference
+            for st in past_conditions:
+                for c in st:
+                    c[:, 16:] = 0
         intermed = []
         for i_s in range(len(stages)):
             self.scheduler.set_timesteps(num_inference_steps[i_s], i_s, device=None)
@@ -126,6 +132,13 @@ class B200Pipeline:
                 latents = up
             for idx in range(len(timesteps)):
                 x_in = torch.cat([latents] * n_local) if n_local > 1 else latents
+                if self.model_cfg.get("no_need_depth", False):
+                    if n_branch == 1:
+                        latents[:, 16:] = 0      # without CFG the reference's model input IS `latents` (pipeline.py:468)
+                    else:
+                        if n_local == 1:
+                            x_in = x_in.clone()  # a branch-sharded rank: the reference cleared a torch.cat copy
+                        x_in[:, 16:] = 0
                 # pipeline.py:473 casts the timestep to the latent dtype; timestep_dtype=float32
                 # keeps it unrounded for comparisons against the fp32 oracle
                 tval = torch.tensor(float(timesteps[idx]), dtype=torch.float64)

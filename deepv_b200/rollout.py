@@ -185,6 +185,8 @@ class B200Rollout:
     def generate_i2v(self, motion_prompt, use_motion_prompt: bool = True, input_image: torch.Tensor = None,
                      input_disparity: Optional[torch.Tensor] = None, input_raymap: Optional[torch.Tensor] = None,
                      input_history: Optional[torch.Tensor] = None, temp: int = 8, num_inference_steps=5,
+                     guidance_scale: float = 4.0, video_guidance_scale: float = 3.5, min_guidance_scale: float = 1.1,
+                     use_linear_guidance: bool = False, alpha: float = 1.0,
                      noise=None, shard=None, return_latents: bool = False):
         """input_image: the input frames as [1,3,n,H,W] in [-1,1] on the device (`frames_from_uint8` /
         `requantise`); input_disparity [1,3,n,H,W]; input_raymap [1,6,n_lat,h,w] normalised;
@@ -196,6 +198,8 @@ class B200Rollout:
         if temp % fpu != 0:
             raise _lib.DeepVError("generate_i2v: temp must be a multiple of frame_per_unit")
         steps = [num_inference_steps] * nst if isinstance(num_inference_steps, int) else list(num_inference_steps)
+        pipe._guidance_scale, pipe._video_guidance_scale = guidance_scale, video_guidance_scale       # :548-549
+        ramp = [max(guidance_scale - alpha * t_, min_guidance_scale) for t_ in range(temp + 1)] if use_linear_guidance else None
         _lib.require_cuda(input_image)
         H, W = input_image.shape[-2], input_image.shape[-1]
         C = pipe.model.in_channels
@@ -218,6 +222,8 @@ class B200Rollout:
         start = 1 if first else (n_frames - 1) // 8 + 1                                                   # :587
         gamma = float(pipe.scheduler.config.gamma)
         for unit in range(start, num_units):
+            if ramp is not None:                                                                         # :592-594
+                pipe._guidance_scale = pipe._video_guidance_scale = ramp[unit]
             enc, mask, pooled = self.prompts.branches(motion_prompt[unit - int(first)], n_branch, use_motion_prompt)
             conds = pipe.pyramid_conditions(torch.cat(generated, dim=2), unit, first, n_branch)
             lat = lat_noise[:, :, unit * fpu:(unit + 1) * fpu].contiguous()
@@ -237,6 +243,8 @@ class B200Rollout:
         else:
             image = pipe.decode_latent(z_image)
             disparity = pipe.decode_latent(z_disparity)
+        if cfg.get("no_need_depth", False):
+            disparity = torch.zeros_like(disparity)                                                       # :696-697
         if return_latents:
             return image, disparity, trans3d, trans2d, lat
         return image, disparity, trans3d, trans2d
@@ -275,7 +283,8 @@ class B200Rollout:
                 ev[0].record()
             image, disparity, t3, t2 = self.generate_i2v(
                 motion, use_table, frames, in_disp, in_ray, in_hist, temp=units,
-                num_inference_steps=cfg.get("num_inference_steps", 10), noise=noise, shard=shard)
+                num_inference_steps=cfg.get("num_inference_steps", 10), guidance_scale=4.0, video_guidance_scale=3.5,
+                use_linear_guidance=False, alpha=1.0, min_guidance_scale=1.1, noise=noise, shard=shard)   # :302-309
             if trace is not None:
                 trace.append(dict(motion_prompt=motion, frames=frames, input_disparity=in_disp, input_raymap=in_ray,
                                   input_history=in_hist, images=image, disparity=disparity, trans3d=t3, trans2d=t2))
@@ -349,9 +358,13 @@ class _Feedback:
         T, H, W = images.shape[2], images.shape[3], images.shape[4]
         t0 = T - NUM_INPUT_IMAGE
         frames = ro.requantise(images, t0, NUM_INPUT_IMAGE)                                 # :339-344
-        scale = torch.empty(1, device=images.device, dtype=torch.float32)
-        in_disp = ro.disparity_renorm(disp, t0, NUM_INPUT_IMAGE, scale, True, False)        # :346-350
-        self.scale = scale
+        if ro.cfg.get("no_need_depth", False):                                              # :345-350 skipped
+            scale = self.scale if self.scale is not None else torch.ones(1, device=images.device, dtype=torch.float32)
+            in_disp = disp[:, :, t0:].to(ro.dtype).contiguous()
+        else:
+            scale = torch.empty(1, device=images.device, dtype=torch.float32)
+            in_disp = ro.disparity_renorm(disp, t0, NUM_INPUT_IMAGE, scale, True, False)    # :346-350
+            self.scale = scale
 
         cur = torch.cat(self.trans3d, dim=1)[:, -NUM_INPUT_UNIT:]                            # :352-358
         cur = torch.matmul(_inv(cur[:, 0]).unsqueeze(1), cur)

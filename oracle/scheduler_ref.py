@@ -105,7 +105,7 @@ def block_noise_cov(gamma: float) -> torch.Tensor:
 def generate_one_unit(model_fn: Callable, tables: Dict, latents: torch.Tensor,
                       past_conditions: List[List[torch.Tensor]], block_noise: List[torch.Tensor],
                       n_branch: int, steps: Sequence[int], w_text: float, w_hist: float,
-                      timestep_dtype=None):
+                      timestep_dtype=None, no_need_depth: bool = False):
     """pipeline.py:439-524 with injected block noise (SURVEY.md §7 vi).
 
     model_fn(clips, timestep[B]) -> [B, C, 1, h, w]; latents [1, C, 1, h0, w0];
@@ -124,9 +124,14 @@ def generate_one_unit(model_fn: Callable, tables: Dict, latents: torch.Tensor,
             latents = alpha * latents + beta * block_noise[i_s - 1].to(latents.dtype)
         for idx in range(steps[i_s]):
             x_in = torch.cat([latents] * n_branch)
+            clips = list(past_conditions[i_s])
+            if no_need_depth:                       # pipeline.py:476-478 (with CFG the model input is a copy)
+                clips = [c.clone() for c in clips]
+                for c in clips + [x_in]:
+                    c[:, 16:] *= 0
             tval = torch.tensor(timesteps[idx], dtype=torch.float64)
             tt = tval.expand(x_in.shape[0]).to(timestep_dtype or x_in.dtype)  # pipeline.py:473
-            pred = model_fn(list(past_conditions[i_s]) + [x_in], tt)
+            pred = model_fn(clips + [x_in], tt)
             guided = cfg_combine(pred, w_text, w_hist)
             latents = euler_step(latents, guided, float(sigmas[idx]), float(sigmas[idx + 1]))
         outs.append(latents)

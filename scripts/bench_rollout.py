@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--repeats", type=int, default=2)
     ap.add_argument("--cpu-feedback", action="store_true")
+    ap.add_argument("--profile-dump", default=None, help="per-launch CSV of one extra profiled rollout")
     args = ap.parse_args()
     import torch
     from deepv_b200 import _lib, synthetic as synth
@@ -74,6 +75,14 @@ def main():
         if rep > 0 and (best is None or total_ms < best["total_ms"]):
             best = rec
     assert torch.isfinite(res["pred_img"]).all()
+    if args.profile_dump:
+        lib.dv_profile_enable(1)
+        lib.dv_profile_reset()
+        ro.generate(batch)
+        torch.cuda.synchronize()
+        lib.dv_profile_enable(0)
+        _lib.check(lib.dv_profile_dump(args.profile_dump.encode()), "dv_profile_dump")
+        lib.dv_profile_reset()
     line = {"metric": "rollout_frames_per_second", "value": best["frames"] / (best["total_ms"] / 1e3), "unit": "frames/s",
             "iterations": args.iters, "frames": best["frames"], "total_ms": best["total_ms"], "host_wall_ms": best["wall_ms"],
             "generate_i2v_ms": best["i2v_ms"], "feedback_ms": best["feedback_ms"], "gpu_launches": best["launches"],

@@ -242,6 +242,45 @@ def test_generate_one_unit_vs_oracle(dit2):
         assert e <= 3e-2  # ~2% latent drift per unit for bf16 vs fp32
 
 
+def test_generate_one_unit_no_need_depth_vs_oracle(dit2):
+    """`model_cfg['no_need_depth']` (pipeline.py:476-478): channels 16.. of every clip are cleared before the
+    denoiser sees them; the oracle's version of the flag is pinned to the live reference on the CPU side."""
+    from deepv_b200.pipeline import B200Pipeline
+    from deepv_b200.scheduler import B200Scheduler
+    cfg, W, model = dit2
+    pipe = B200Pipeline(model, None, B200Scheduler(**cases.SCHEDULER_KW), model_cfg=dict(no_need_depth=True),
+                        torch_dtype=torch.float32)
+    g = torch.Generator().manual_seed(14)
+    lat = torch.randn(1, 38, 1, 8, 8, generator=g)
+    conds = [[torch.randn(2, 38, 1, 8 * 2 ** i, 8 * 2 ** i, generator=g)] for i in range(3)]
+    noise = [torch.randn(1, 38, 1, 16, 16, generator=g), torch.randn(1, 38, 1, 32, 32, generator=g)]
+    enc = torch.randn(2, 77, 4096, generator=g)
+    pooled = torch.randn(2, 2048, generator=g)
+    mask = torch.zeros(2, 77, dtype=torch.long)
+    mask[0, :1] = 1
+    mask[1, :9] = 1
+    tb = scheduler_ref.pyramid_tables(**cases.SCHEDULER_KW)
+
+    def model_fn(clips, tt):
+        return mmdit_ref.mmdit_forward(W, cfg, clips, tt.float(), enc, mask, pooled)
+
+    with torch.no_grad():
+        ref = scheduler_ref.generate_one_unit(model_fn, tb, lat, conds, noise, 2, [1, 2, 1], 3.5, 6.0,
+                                              timestep_dtype=torch.float32, no_need_depth=True)
+        plain = scheduler_ref.generate_one_unit(model_fn, tb, lat, conds, noise, 2, [1, 2, 1], 3.5, 6.0,
+                                                timestep_dtype=torch.float32)
+    lat_dev = lat.cuda()
+    out = pipe.generate_one_unit(lat_dev, None, [[c.cuda() for c in cl] for cl in conds], enc, mask, pooled,
+                                 [1, 2, 1], block_noise=noise, timestep_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert torch.equal(lat_dev.cpu(), lat)           # with CFG the caller's latents are left alone, as in the reference
+    for i in range(3):
+        e = rel_max(out[i], ref[i])
+        print(f"no_need_depth stage {i}: {e:.3e} (flag changes the result by {rel_max(plain[i], ref[i]):.2e})")
+        assert e <= 3e-2
+    assert rel_max(plain[2], ref[2]) > 5 * rel_max(out[2], ref[2])
+
+
 # ---------------------------------------------------------------------------------------------
 # VAE encode (SURVEY.md §8 row f1)
 @pytest.mark.parametrize("video", [(1, 3, 1, 64, 128), (1, 3, 9, 320, 320), (1, 3, 17, 384, 512)])

@@ -93,3 +93,40 @@ def test_rollout_result_matches_reference(rollout):
     digest_close(res["pred_disparity"], gold["pred_disparity"], 1e-3, "pred_disparity")
     close(res["trans3d"], gold["trans3d"], 3e-3, "trans3d")
     close(res["trans2d"], gold["trans2d"], 1e-3, "trans2d")
+
+
+def test_no_need_depth_unit_matches_live_reference():
+    """`model_cfg['no_need_depth']` (pipeline.py:476-478) through the real `generate_one_unit`, when the
+    reference tree is present (build container); the restatement must zero the same channels."""
+    from oracle import _shim, mmdit_ref, scheduler_ref
+    if not _shim.reference_available():
+        pytest.skip("reference tree not present")
+    from tests.golden.make_rollout_golden import build_reference_pipeline
+    torch.set_grad_enabled(False)
+    case = rc.ROLLOUT
+    tape = rc.NoiseTape(5)
+    _, pipe = build_reference_pipeline(case, tape)
+    pipe.model_cfg["no_need_depth"] = True
+    pipe._guidance_scale, pipe._video_guidance_scale = 4.0, 3.5
+    g = torch.Generator().manual_seed(9)
+    lat = torch.randn(1, 38, 1, 6, 8, generator=g)
+    conds = [[torch.randn(2, 38, 1, 6 * 2 ** i, 8 * 2 ** i, generator=g)] for i in range(3)]
+    te = rc.text_embeds(case)
+    enc = torch.cat([te["empty"]["prompt_embeds"], te["w"]["prompt_embeds"]])
+    pooled = torch.cat([te["empty"]["pooled_prompt_embeds"], te["w"]["pooled_prompt_embeds"]])
+    mask = torch.cat([te["empty"]["prompt_attention_mask"], te["w"]["prompt_attention_mask"]])
+    want = pipe.generate_one_unit(lat.clone(), None, [[c.clone() for c in st] for st in conds], enc, mask, pooled,
+                                  [1, 1, 1], 6, 8, 1, torch.device("cpu"), torch.float32)
+    m = build_models(case)
+    replay = rc.NoiseTape(5)
+
+    def model_fn(clips, tt):
+        return mmdit_ref.mmdit_forward(m.dit_W, m.dit_cfg, clips, tt.float(), enc, mask, pooled, pos_table=m.pos_table())
+
+    block = [replay.block(1, 38, 1, 12, 16, m.tables["gamma"]), replay.block(1, 38, 1, 24, 32, m.tables["gamma"])]
+    got = scheduler_ref.generate_one_unit(model_fn, m.tables, lat, conds, block, 2, [1, 1, 1], 3.5, 6.0,
+                                          no_need_depth=True)
+    for i in range(3):
+        close(got[i], want[i], 1e-5, f"no_need_depth stage {i}")
+    plain = scheduler_ref.generate_one_unit(model_fn, m.tables, lat, conds, block, 2, [1, 1, 1], 3.5, 6.0)
+    assert (plain[2] - got[2]).abs().max() > 1e-3          # the flag does change the result
