@@ -25,15 +25,32 @@ def main():
     ap.add_argument("--repeats", type=int, default=2)
     ap.add_argument("--cpu-feedback", action="store_true")
     ap.add_argument("--profile-dump", default=None, help="per-launch CSV of one extra profiled rollout")
+    ap.add_argument("--check", action="store_true", help="under torchrun: also run the rollout un-sharded on "
+                                                         "every rank and compare")
     args = ap.parse_args()
+    out_fd = os.dup(1)                 # keep the JSON line alone on stdout: NCCL / library chatter goes to stderr
+    os.dup2(2, 1)
     import torch
     from deepv_b200 import _lib, synthetic as synth
     from deepv_b200.mmdit import B200MMDiT
     from deepv_b200.pipeline import B200Pipeline
-    from deepv_b200.rollout import B200Rollout, PromptCache
+    from deepv_b200.rollout import B200Rollout, DeviceNoise, PromptCache
     from deepv_b200.scheduler import B200Scheduler
     from deepv_b200.vae import B200VAE
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    shard = None
+    dist = None
+    if world > 1:                      # one rollout group over all ranks: CFG branches x Ulysses, VAE tiles dealt out
+        import torch.distributed as dist
+        from deepv_b200.parallel import Shard
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        shard = Shard.grouped(world)
+        shard.setup_sp(dev)
     lib = _lib.load()
     dtype = torch.bfloat16
     cfg, W = synth.mmdit_weights(dict(num_layers=args.layers), seed=1)
@@ -61,17 +78,25 @@ def main():
         lib.dv_launch_count_reset()
         events = []
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        res = ro.generate(batch, events=events)
+        res = ro.generate(batch, events=events, shard=shard,
+                          noise=DeviceNoise(pipe, torch.Generator(device=dev).manual_seed(1234)))
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         launches = lib.dv_launch_count()
         i2v = [e[0].elapsed_time(e[1]) for e in events]
         fb = [e[1].elapsed_time(e[2]) for e in events]
         total_ms = events[0][0].elapsed_time(events[-1][2])
+        if world > 1:                                        # device time, max over ranks
+            t = torch.tensor([total_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = t.item()
         frames = res["pred_img"].shape[2]
         rec = dict(frames=frames, total_ms=total_ms, wall_ms=wall * 1e3, i2v_ms=i2v, feedback_ms=fb, launches=launches)
-        print(("warm-up " if rep == 0 else "timed   ") + json.dumps(rec), file=sys.stderr, flush=True)
+        if rank == 0:
+            print(("warm-up " if rep == 0 else "timed   ") + json.dumps(rec), file=sys.stderr, flush=True)
         if rep > 0 and (best is None or total_ms < best["total_ms"]):
             best = rec
     assert torch.isfinite(res["pred_img"]).all()
@@ -83,7 +108,29 @@ def main():
         lib.dv_profile_enable(0)
         _lib.check(lib.dv_profile_dump(args.profile_dump.encode()), "dv_profile_dump")
         lib.dv_profile_reset()
-    line = {"metric": "rollout_frames_per_second", "value": best["frames"] / (best["total_ms"] / 1e3), "unit": "frames/s",
+    check = None
+    if args.check and shard is not None:
+        trace = []
+        alone = ro.generate(batch, noise=DeviceNoise(pipe, torch.Generator(device=dev).manual_seed(1234)), trace=trace)
+        t1 = trace[1]                  # the second iteration again, from identical inputs, un-sharded and sharded
+        forced = []
+        for sh in (None, shard):
+            forced.append(ro.generate_i2v(t1["motion_prompt"], True, t1["frames"], t1["input_disparity"], t1["input_raymap"],
+                                          t1["input_history"], temp=8, num_inference_steps=args.steps, shard=sh,
+                                          noise=DeviceNoise(pipe, torch.Generator(device=dev).manual_seed(99))))
+        torch.cuda.synchronize()
+        import math
+        def psnr(a, b):
+            return 10 * math.log10(4.0 / max(((a.float() - b.float()) ** 2).mean().item(), 1e-20))
+        check = {"psnr_first_iteration_db": psnr(res["pred_img"][:, :, :57], alone["pred_img"][:, :, :57]),
+                 "psnr_all_frames_db": psnr(res["pred_img"], alone["pred_img"]),
+                 "psnr_second_iteration_same_inputs_db": psnr(forced[0][0], forced[1][0]),
+                 "psnr_second_iteration_disparity_same_inputs_db": psnr(forced[0][1], forced[1][1]),
+                 "note": "sharded vs un-sharded rollout on the same rank, same device draws; the second iteration "
+                         "free-runs from bf16-different first-iteration frames"}
+    if rank != 0:
+        return
+    line = {"metric": "rollout_frames_per_second", "n_gpus": world, "sharded_vs_alone": check, "value": best["frames"] / (best["total_ms"] / 1e3), "unit": "frames/s",
             "iterations": args.iters, "frames": best["frames"], "total_ms": best["total_ms"], "host_wall_ms": best["wall_ms"],
             "generate_i2v_ms": best["i2v_ms"], "feedback_ms": best["feedback_ms"], "gpu_launches": best["launches"],
             "dtype": "bf16", "data": "synthetic",
@@ -107,7 +154,7 @@ def main():
         line["cpu_feedback_ms"] = (time.perf_counter() - t0) * 1e3
         line["cpu_feedback_note"] = ("oracle arithmetic of the same feedback step on the host cores (no PIL, no D2H/H2D, "
                                      "history encode excluded)")
-    print(json.dumps(line), flush=True)
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
