@@ -1346,8 +1346,13 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
   // CTA pairs (cta_group::2) once every SM pair has a 256-row tile: ~570 cycles per k-block instead
   // of the ~850 a lone CTA gets when all SMs pull 48 KB per k-block through L2
   bool pair = false;
-  // (dense only: the implicit-GEMM convs measured the same with and without pairing)
-  if (ka.splits == 1 && d0.a_mode == 0 && d0.mode != EPI_UNPATCH) {
+  // Stride-1 implicit-GEMM convs with >= 256 output channels (not operand-swapped) pair as well: half of the
+  // weight tile per CTA takes the k-block from ~1000 to ~880 cycles (1170 -> 1300 TFLOP/s, A/B on one box:
+  // profiles/r01_exp_conv_pair.txt).  DV_CONV_NOPAIR=1 switches it off.
+  static const bool conv_nopair = getenv("DV_CONV_NOPAIR") != nullptr;
+  const bool conv_ok = !conv_nopair && d0.a_mode == 1 && d1 == nullptr && !ka.p[0].swap && d0.sT <= 1 &&
+                       d0.sH <= 1 && d0.sW <= 1;
+  if (ka.splits == 1 && (d0.a_mode == 0 || conv_ok) && d0.mode != EPI_UNPATCH) {
     const int nsm = sm_count();
     const double w1 = static_cast<double>((ka.total_tiles + nsm - 1) / nsm);
     const double w2 = static_cast<double>((ka.total_pair_tiles + nsm / 2 - 1) / (nsm / 2));
