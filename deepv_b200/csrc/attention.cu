@@ -140,10 +140,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // heaviest query tiles first: later frames see more keys
-  const int qt = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
+  // longest work first, chip-wide: the query tile is the slowest grid index and runs from the last tile (most
+  // key tiles under the frame-causal mask) to the first, so the short items fill the tail of the launch
+  const int qt = static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z);
   const int q0 = qt * kTile;
-  const int head = a.head0 + static_cast<int>(blockIdx.y);
-  const int b = blockIdx.z;
+  const int head = a.head0 + static_cast<int>(blockIdx.x);
+  const int b = blockIdx.y;
 
   // keys needed by this query tile (kv_end is non-decreasing in q)
   const int last_q = min(q0 + kTile, a.L) - 1;
@@ -441,7 +443,7 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
                                        kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((L + kTile - 1) / kTile, n_heads, B);
+  dim3 grid(n_heads, B, (L + kTile - 1) / kTile);
   char tag[56] = "";
   if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d", B, L, H);
   const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);

@@ -1356,7 +1356,7 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
     const int nsm = sm_count();
     const double w1 = static_cast<double>((ka.total_tiles + nsm - 1) / nsm);
     const double w2 = static_cast<double>((ka.total_pair_tiles + nsm / 2 - 1) / (nsm / 2));
-    pair = ka.total_tiles >= nsm && w2 * 0.75 < w1;
+    pair = ka.total_tiles >= nsm && w2 * 0.75 < w1;   // (pairing a 144-tile problem measured 0 / -8 %)
     static const char* ep = getenv("DV_GEMM_PAIR");
     if (ep) pair = atoi(ep) != 0 && ka.total_pair_tiles > 0;
   }
