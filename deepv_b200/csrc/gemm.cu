@@ -1307,6 +1307,11 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) { return launch_gemm_pai
 int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream) {
   static const bool no_split = getenv("DV_GEMM_NOSPLIT") != nullptr;
   static const bool no_group = getenv("DV_GEMM_NOGROUP") != nullptr;
+  if (d1 == nullptr && d0.a_mode == 1) {
+    // 3x3x3 stride-1 convs with <= 128 output channels: pixel tile + halo shared by nine taps (conv_halo.cu)
+    const int hrc = launch_conv_halo(d0, stream);
+    if (hrc <= 0) return hrc;
+  }
   KArgs ka;
   int rc = setup_problem(d0, ka.p[0]);
   if (rc) return rc;

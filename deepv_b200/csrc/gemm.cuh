@@ -93,5 +93,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream);
 // Two dense problems of the same epilogue mode in ONE launch (video + context stream of a joint
 // block); d1 may be null.  Falls back to two launches when wave quantisation makes that cheaper.
 int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream);
+// conv_halo.cu: 0 = launched, 1 = not a problem that kernel takes (use the generic path), < 0 = error
+int launch_conv_halo(const GemmDesc& d, cudaStream_t stream);
 
 }  // namespace dv

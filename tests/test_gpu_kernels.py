@@ -56,6 +56,15 @@ def test_gemm_rejects_bad_shapes(lib):
     (1, 3, 8, 16, 64, 128, 3, 2, 1),      # frame-interleave store, first frame dropped
     (1, 3, 8, 16, 64, 128, 3, 2, 0),
     (1, 1, 8, 16, 64, 64, 3, 0, 0),       # single frame: two zero history frames
+    # >= 148 tiles of 8x32 pixels with <= 128 output channels: the halo kernel (conv_halo.cu)
+    (1, 3, 128, 128, 128, 128, 3, 0, 0),
+    (1, 4, 88, 96, 256, 128, 3, 0, 0),    # H not a multiple of the 32-row tile, two channel blocks per tap
+    (2, 2, 72, 80, 64, 64, 3, 0, 0),      # batch 2, 64 of the 128 accumulator rows live
+    (1, 1, 256, 256, 128, 128, 3, 0, 0),  # single frame (all history out of bounds), one full image row per tile row
+    (1, 3, 96, 128, 128, 256, 3, 0, 0),   # halo kernel, two 128-channel chunks per pixel tile
+    (1, 2, 64, 128, 64, 512, 3, 1, 0),    # ... pixel-shuffle store
+    (1, 3, 128, 64, 128, 256, 3, 2, 1),   # ... frame-interleave store, first frame dropped
+    (1, 3, 128, 64, 128, 256, 3, 2, 0),
 ])
 def test_conv3d_channels_last(lib, B, T, H, W, Cin, Cout, ks, store, drop):
     from deepv_b200 import _lib
