@@ -433,14 +433,15 @@ def run_ours(args):
     gk_tf = kinds["gemm_dense"]["tflop"] + kinds["gemm_conv"]["tflop"]
     gk_n = kinds["gemm_dense"]["launches"] + kinds["gemm_conv"]["launches"]
     achieved = gk_tf / (gk_ms / 1e3) if gk_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN> (dense + implicit-GEMM conv3d, tcgen05/TMEM/TMA)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel / gemm_pair_kernel (dense) + conv_halo_kernel / implicit-GEMM conv3d (tcgen05/TMEM/TMA)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "frac_of_nominal_2250": achieved / 2250.0, "peak_source": peak_src, "traffic": None,
                 # `achieved` aggregates ~2200 launches of many shapes, so one per-launch DRAM figure does not
-                # exist; the largest single shape as captured by `ncu --set full` (profiles/r01_ncu_full_v3_summary.txt):
-                "traffic_sample": {"launch": "conv 128->128 3x3x3 @ [9][256][256] (20 launches/step)",
-                                   "dram_bytes": 286.1e6, "algorithmic_bytes": 302.9e6,
-                                   "source": "profiles/r01_ncu_full_v3_summary.txt"},
+                # exist; the largest single shape as captured by `ncu --set full` (profiles/r01_ncu_conv_halo_summary.txt):
+                "traffic_sample": {"launch": "conv_halo_kernel 128->128 3x3x3 @ [9][256][256] (20 launches/step)",
+                                   "dram_bytes": 285.0e6, "algorithmic_bytes": 302.9e6,
+                                   "tensor_pipe_active_pct": 84.4,
+                                   "source": "profiles/r01_ncu_conv_halo_summary.txt"},
                 "launches_per_step": gk_n, "avg_launch_us": gk_ms * 1e3 / gk_n if gk_n else None,
                 "kernel_share_of_step": gk_ms / prof_ms if prof_ms > 0 else None, "by_kind": kinds,
                 "how": "CUDA events on the launching stream around every launch of one extra profiled step"}
