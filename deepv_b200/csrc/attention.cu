@@ -23,6 +23,7 @@
 //               into TMEM.  Masking runs only on tiles that hold a frame boundary or dead keys.
 // Query tiles are issued heaviest-first (late frames see the most keys).
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -404,6 +405,286 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   }
 }
 
+// =====================================================================================================
+// EXPERIMENTAL (DV_ATTN_PIPE=1; off by default — DESIGN.md §7.1).  State at the end of round 1: passes the six
+// attention cases of tests/test_gpu_kernels.py on a B200 and runs the B2 / L1613 / 24-head micro-benchmark
+// (scripts/exp_attn.py, every tile on the masked path) in 93.6 us against 124.8 us for attn_kernel; the model-level
+// parity / sharding suites have not been run with it yet, which is why it is not the default.
+// one CTA per SM with TWO S buffers in tensor memory.  The MMA warp issues S_{j+1} = Q K_{j+1}^T before
+// O += P_j V_j, so the softmax warps find the next scores ready when they finish a tile and have the XU
+// pipe to themselves; the price is 512 TMEM columns (one CTA per SM) and a 4-stage K/V ring.
+//   TMEM: S0 [0,128)  S1 [128,256)  O [256,320)  l [320,336)  Q [336,368);  P_j aliases S_{j&1}[0,64)
+//   order on the tensor pipe: S0, S1, (P0V0, S2), (P1V1, S3), ...  — in order, so S_{j+2} may overwrite P_j
+//   lazy rescale of O / l (rare path) first waits for pv_done(j-1): P_{j-1} V_{j-1} has retired.
+// =====================================================================================================
+constexpr int kPipeStages = 4;
+constexpr uint32_t kPipeTmemCols = 512;
+constexpr uint32_t kPColS = 0, kPColO = 256, kPColL = 320, kPColQ = 336;
+constexpr int kPipeSmemBytes = kTileBytes + kPipeStages * 2 * kTileBytes + kOnesBytes + 256 + 1024;
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid_constant__ AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + kTileBytes;
+  uint8_t* sOnes = sKV + kPipeStages * 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes);
+  uint64_t* q_full = bars;
+  uint64_t* q_ready = bars + 1;
+  uint64_t* kv_full = bars + 2;                  // [kPipeStages]
+  uint64_t* kv_empty = kv_full + kPipeStages;    // [kPipeStages]
+  uint64_t* s_full = kv_empty + kPipeStages;     // [2]: S_j ready in buffer j & 1
+  uint64_t* p_full = s_full + 2;                 // [2]: P_j written over buffer j & 1 (128 arrivals)
+  uint64_t* pv_done = p_full + 2;                // P_j V_j retired (one phase per tile)
+  uint64_t* o_done = pv_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z);
+  const int q0 = qt * kTile;
+  const int head = a.head0 + static_cast<int>(blockIdx.x);
+  const int b = blockIdx.y;
+  const int last_q = min(q0 + kTile, a.L) - 1;
+  const int n_kv = (__ldg(a.kv_end + last_q) + kTile - 1) / kTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmQKV);
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 128);
+    for (int i = 0; i < kPipeStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(pv_done, 1);
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kPipeTmemCols>(tmem_slot);
+  for (int i = threadIdx.x; i < kOnesBytes / 4; i += kAttnThreads)
+    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int HD = a.H * kD;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_3d(&a.tmQKV, q_full, sQ, head * kD, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kPipeStages;
+        const uint32_t ph = (j / kPipeStages) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* sK = sKV + s * 2 * kTileBytes;
+        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
+        tma_load_3d(&a.tmQKV, &kv_full[s], sK, HD + head * kD, j * kTile, b);
+        tma_load_3d(&a.tmQKV, &kv_full[s], sK + kTileBytes, 2 * HD + head * kD, j * kTile, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_kv > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 0);
+      const uint32_t tO = tmem_base + kPColO, tL = tmem_base + kPColL, tQ = tmem_base + kPColQ;
+      const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
+      auto issue_s = [&](int j) {
+        mbar_wait(&kv_full[j % kPipeStages], (j / kPipeStages) & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + kPColS + (j & 1) * 128;
+        const uint32_t aK = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes);
+        const uint64_t dk = umma_desc_sw128(aK, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ts(tS, tQ + k * 8, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_ready, 0);
+      issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in TMEM (and O / l rescaled if the max grew)
+        tc_fence_after();
+        const uint32_t tP = tmem_base + kPColS + (j & 1) * 128;
+        const uint32_t aV = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes) + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k) {
+          const uint64_t dv = umma_desc_sw128(aV + k * 2048, 1024, 1024);
+          umma_bf16_ts(tO, tP + k * 8, dv, idesc_pv, (j | k) != 0);
+          umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[j % kPipeStages]);
+        umma_commit(pv_done);
+        if (j + 2 < n_kv) issue_s(j + 2);  // in order behind P_j V_j: S_{j+2} may overwrite P_j
+        if (j + 1 == n_kv) umma_commit(o_done);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int qi = q0 + r;
+    const bool row_ok = qi < a.L;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tO = tmem_base + kPColO + lane_addr;
+    const uint32_t tL = tmem_base + kPColL + lane_addr;
+    if (n_kv > 0) {
+      mbar_wait(q_full, 0);
+      {
+        uint32_t qr[32];
+        const uint8_t* row = sQ + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 t = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+          qr[4 * c + 0] = t.x;
+          qr[4 * c + 1] = t.y;
+          qr[4 * c + 2] = t.z;
+          qr[4 * c + 3] = t.w;
+        }
+        tmem_st_32x32(tmem_base + kPColQ + lane_addr, qr);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(q_ready);
+      }
+      const int kv_end = row_ok ? __ldg(a.kv_end + qi) : 0;
+      const int kv_end_min = __ldg(a.kv_end + q0);
+      const float* kb = a.key_bias + static_cast<long long>(b) * a.Lpad;
+      const float sc = a.scale_log2;
+      float m_ref = -INFINITY;
+      const int* dead_row = a.tile_dead ? a.tile_dead + b * (a.Lpad / kTile) : nullptr;
+      for (int j = 0; j < n_kv; ++j) {
+        const int k0 = j * kTile;
+        const uint32_t tS = tmem_base + kPColS + (j & 1) * 128 + lane_addr;
+        const bool need_mask = (k0 + kTile > kv_end_min) || (dead_row == nullptr) || (__ldg(dead_row + j) != 0);
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        float s[kTile];
+#pragma unroll
+        for (int c = 0; c < kTile / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tS + c * 32, raw);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(raw[i]);
+        }
+        tmem_ld_wait();
+        float m_tile = -INFINITY;
+        if (need_mask) {
+#pragma unroll
+          for (int i4 = 0; i4 < kTile / 4; ++i4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(kb + k0) + i4);
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * i4 + e;
+              float x = s[i] + bv[e];
+              x = (k0 + i < kv_end) ? x : -INFINITY;
+              s[i] = x;
+              m_tile = fmaxf(m_tile, x);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kTile; ++i) m_tile = fmaxf(m_tile, s[i]);
+        }
+        m_tile *= sc;
+        const bool had = m_ref > -INFINITY;
+        const bool grow = had ? (m_tile > m_ref + kRescaleThreshold) : (m_tile > -INFINITY);
+        const float m_new = grow ? m_tile : m_ref;
+        if (j > 0 && __any_sync(0xffffffffu, grow && had)) {
+          // O and l still receive P_{j-1} V_{j-1}: wait until it has retired before touching them
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          const float alpha = (grow && had) ? ex2(m_ref - m_new) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < kD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tO + c * 32, o);
+          }
+          const uint32_t lv = tmem_ld_1(tL);
+          tmem_ld_wait();
+          tmem_st_1(tL, __float_as_uint(__uint_as_float(lv) * alpha));
+          tmem_st_wait();
+        }
+        m_ref = m_new;
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x0 = fmaf(s[hlf * 64 + 2 * i], sc, neg_m);
+            const float x1 = fmaf(s[hlf * 64 + 2 * i + 1], sc, neg_m);
+            pk[i] = pack_bf16x2(ex2(x0), ex2(x1));
+          }
+          tmem_st_32x32(tS + hlf * 32, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[j & 1]);
+      }
+
+      mbar_wait(o_done, 0);
+      tc_fence_after();
+      const float l_run = __uint_as_float(tmem_ld_1(tL));
+      float o[kD];
+#pragma unroll
+      for (int c = 0; c < kD / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tO + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]);
+      }
+      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      if (row_ok) {
+        uint4 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          q[i].x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+          q[i].y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+          q[i].z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+          q[i].w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        }
+        const long long off = (static_cast<long long>(b) * a.L + qi) * HD + head * kD;
+        if (a.n_peers == 0) {
+          uint4* d4 = reinterpret_cast<uint4*>(a.out + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = q[i];
+        } else if (qi >= a.peer_Lc) {
+          uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[(qi - a.peer_Lc) / a.peer_Lw] + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = q[i];
+        } else {
+          for (int p = 0; p < a.n_peers; ++p) {
+            uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[p] + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d4[i] = q[i];
+          }
+        }
+      }
+    }
+  }
+
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kPipeTmemCols>(tmem_base);
+  }
+}
+
 }  // namespace
 
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
@@ -437,17 +718,23 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   for (int i = 0; i < 8; ++i)
     a.out_peer[i] = (out_peers && i < n_peers) ? reinterpret_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
+  static const bool pipe = getenv("DV_ATTN_PIPE") != nullptr;   // experimental double-buffered-S variant
   static bool attr_set = false;
   if (!attr_set) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemBytes));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kPipeSmemBytes));
     attr_set = true;
   }
   dim3 grid(n_heads, B, (L + kTile - 1) / kTile);
   char tag[56] = "";
-  if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d", B, L, H);
+  if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d%s", B, L, H, pipe ? " pipe" : "");
   const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);
-  DV_CHECK_CUDA(launch_pdl(attn_kernel, grid, dim3(kAttnThreads), kSmemBytes, stream, 1, a));
+  if (pipe)
+    DV_CHECK_CUDA(launch_pdl(attn_pipe_kernel, grid, dim3(kAttnThreads), kPipeSmemBytes, stream, 1, a));
+  else
+    DV_CHECK_CUDA(launch_pdl(attn_kernel, grid, dim3(kAttnThreads), kSmemBytes, stream, 1, a));
   prof_end(pid, stream);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
