@@ -68,6 +68,13 @@ struct dv_mmdit_plan {
   void* qkv_peer[8] = {nullptr};
   void* attn_peer[8] = {nullptr};
   bool peers_set = false;
+  // CUDA-graph replay of the forward (DV_MMDIT_GRAPH=1, experimental): the inputs are copied into
+  // plan-owned staging buffers so that one captured graph serves every call of this token layout
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_io_dtype = -1, graph_enc_dtype = -1, graph_out_dtype = -1;
+  std::vector<void*> stage_clips;
+  void *stage_enc = nullptr, *stage_hist = nullptr, *stage_out = nullptr;
+  float *stage_mask = nullptr, *stage_pooled = nullptr, *stage_t = nullptr;
 };
 
 namespace {
@@ -339,6 +346,7 @@ extern "C" int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const i
 
 extern "C" void dv_mmdit_plan_destroy(dv_mmdit_plan* p) {
   if (!p) return;
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   for (void* a : p->allocs) cudaFree(a);
   delete p;
 }
@@ -422,17 +430,10 @@ extern "C" int dv_ipc_open_handle(const void* handle64, void** dev_ptr) {
 extern "C" long long dv_mmdit_plan_workspace_bytes(const dv_mmdit_plan* p) { return p ? p->bytes : 0; }
 extern "C" double dv_mmdit_plan_flops(const dv_mmdit_plan* p) { return p ? p->flops : 0.0; }
 
-extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, int io_dtype,
-                                const void* enc_dev, int enc_dtype, const float* ctx_mask_dev,
-                                const float* pooled_dev, const float* timestep_dev,
-                                const void* history_dev, void* out_dev, int out_dtype,
-                                void* stream_v) {
-  DV_REQUIRE(p && clips_dev && enc_dev && ctx_mask_dev && pooled_dev && timestep_dev && out_dev,
-             "dv_mmdit_forward: null argument");
-  DV_REQUIRE((p->hist_tokens > 0) == (history_dev != nullptr),
-             "dv_mmdit_forward: history pointer does not match the plan (plan has %d history tokens)",
-             p->hist_tokens);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_dtype,
+                        const void* enc_dev, int enc_dtype, const float* ctx_mask_dev,
+                        const float* pooled_dev, const float* timestep_dev,
+                        const void* history_dev, void* out_dev, int out_dtype, cudaStream_t st) {
   dv_mmdit* m = p->m;
   const dv_mmdit_weights& w = m->w;
   const int B = p->B, D = m->D, Lv = p->Lv, Lc = p->Lc, L = p->L;
@@ -656,4 +657,104 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
   }
 #undef DV_RUN
   return DV_OK;
+}
+
+// One captured graph per plan (DV_MMDIT_GRAPH=1, experimental, off by default; not yet run on hardware):
+// every input is first copied into plan-owned staging buffers (a few MB of device-to-device copies), so the
+// ~170 launches of a forward replay as one graph launch whatever tensors the caller passes.  Not used with
+// sequence parallelism (host exchange callback) or while the per-launch profiler is on.
+static int forward_graph(dv_mmdit_plan* p, const void* const* clips_dev, int io_dtype, const void* enc_dev,
+                         int enc_dtype, const float* ctx_mask_dev, const float* pooled_dev,
+                         const float* timestep_dev, const void* history_dev, void* out_dev, int out_dtype,
+                         cudaStream_t st) {
+  dv_mmdit* m = p->m;
+  const int B = p->B, C = m->cfg.in_channels;
+  const size_t io_sz = io_dtype == DV_DTYPE_BF16 ? 2 : 4;
+  const size_t enc_sz = enc_dtype == DV_DTYPE_BF16 ? 2 : 4;
+  const size_t out_sz = out_dtype == DV_DTYPE_BF16 ? 2 : 4;
+  const ClipInfo& lc = p->clips.back();
+  const size_t enc_bytes = static_cast<size_t>(B) * p->text_len * m->cfg.joint_dim * enc_sz;
+  const size_t hist_bytes = static_cast<size_t>(B) * C * p->hist_h * p->hist_w * io_sz;
+  const size_t out_bytes = static_cast<size_t>(B) * C * lc.t * lc.h * lc.w * out_sz;
+  if (p->stage_t == nullptr || p->graph_io_dtype != io_dtype || p->graph_enc_dtype != enc_dtype ||
+      p->graph_out_dtype != out_dtype) {
+    // (re)build the staging buffers for these dtypes; fp32-sized so that a dtype change fits as well
+    if (p->stage_t == nullptr) {
+      int rc;
+      p->stage_clips.resize(p->clips.size());
+      for (size_t i = 0; i < p->clips.size(); ++i) {
+        const ClipInfo& ci = p->clips[i];
+        float* buf = nullptr;
+        if ((rc = dev_alloc(p, &buf, static_cast<long long>(B) * C * ci.t * ci.h * ci.w)) != 0) return rc;
+        p->stage_clips[i] = buf;
+      }
+      float* f = nullptr;
+      if ((rc = dev_alloc(p, &f, static_cast<long long>(B) * p->text_len * m->cfg.joint_dim)) != 0) return rc;
+      p->stage_enc = f;
+      if (p->hist_tokens) {
+        if ((rc = dev_alloc(p, &f, static_cast<long long>(B) * C * p->hist_h * p->hist_w)) != 0) return rc;
+        p->stage_hist = f;
+      }
+      if ((rc = dev_alloc(p, &f, static_cast<long long>(B) * C * lc.t * lc.h * lc.w)) != 0) return rc;
+      p->stage_out = f;
+      if ((rc = dev_alloc(p, &p->stage_mask, static_cast<long long>(B) * p->Lc)) != 0) return rc;
+      if ((rc = dev_alloc(p, &p->stage_pooled, static_cast<long long>(B) * m->cfg.pooled_dim)) != 0) return rc;
+      if ((rc = dev_alloc(p, &p->stage_t, B)) != 0) return rc;
+    }
+    if (p->graph_exec) {
+      cudaGraphExecDestroy(p->graph_exec);
+      p->graph_exec = nullptr;
+    }
+    p->graph_io_dtype = io_dtype;
+    p->graph_enc_dtype = enc_dtype;
+    p->graph_out_dtype = out_dtype;
+  }
+  for (size_t i = 0; i < p->clips.size(); ++i) {
+    const ClipInfo& ci = p->clips[i];
+    DV_CHECK_CUDA(cudaMemcpyAsync(p->stage_clips[i], clips_dev[i], static_cast<size_t>(B) * C * ci.t * ci.h * ci.w * io_sz,
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  DV_CHECK_CUDA(cudaMemcpyAsync(p->stage_enc, enc_dev, enc_bytes, cudaMemcpyDeviceToDevice, st));
+  if (p->hist_tokens) DV_CHECK_CUDA(cudaMemcpyAsync(p->stage_hist, history_dev, hist_bytes, cudaMemcpyDeviceToDevice, st));
+  DV_CHECK_CUDA(cudaMemcpyAsync(p->stage_mask, ctx_mask_dev, static_cast<size_t>(B) * p->Lc * 4, cudaMemcpyDeviceToDevice, st));
+  DV_CHECK_CUDA(cudaMemcpyAsync(p->stage_pooled, pooled_dev, static_cast<size_t>(B) * m->cfg.pooled_dim * 4,
+                                cudaMemcpyDeviceToDevice, st));
+  DV_CHECK_CUDA(cudaMemcpyAsync(p->stage_t, timestep_dev, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
+  if (p->graph_exec == nullptr) {
+    std::vector<const void*> cl(p->stage_clips.begin(), p->stage_clips.end());
+    DV_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int rc = forward_body(p, cl.data(), io_dtype, p->stage_enc, enc_dtype, p->stage_mask, p->stage_pooled,
+                                p->stage_t, p->hist_tokens ? p->stage_hist : nullptr, p->stage_out, out_dtype, st);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc != 0) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    DV_CHECK_CUDA(ce);
+    DV_CHECK_CUDA(cudaGraphInstantiate(&p->graph_exec, g, 0));
+    cudaGraphDestroy(g);
+  }
+  DV_CHECK_CUDA(cudaGraphLaunch(p->graph_exec, st));
+  DV_CHECK_CUDA(cudaMemcpyAsync(out_dev, p->stage_out, out_bytes, cudaMemcpyDeviceToDevice, st));
+  return DV_OK;
+}
+
+extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, int io_dtype,
+                                const void* enc_dev, int enc_dtype, const float* ctx_mask_dev,
+                                const float* pooled_dev, const float* timestep_dev,
+                                const void* history_dev, void* out_dev, int out_dtype,
+                                void* stream_v) {
+  DV_REQUIRE(p && clips_dev && enc_dev && ctx_mask_dev && pooled_dev && timestep_dev && out_dev,
+             "dv_mmdit_forward: null argument");
+  DV_REQUIRE((p->hist_tokens > 0) == (history_dev != nullptr),
+             "dv_mmdit_forward: history pointer does not match the plan (plan has %d history tokens)",
+             p->hist_tokens);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  static const bool use_graph = getenv("DV_MMDIT_GRAPH") != nullptr;
+  if (use_graph && p->sp_world == 1 && !prof_on())
+    return forward_graph(p, clips_dev, io_dtype, enc_dev, enc_dtype, ctx_mask_dev, pooled_dev, timestep_dev,
+                         history_dev, out_dev, out_dtype, st);
+  return forward_body(p, clips_dev, io_dtype, enc_dev, enc_dtype, ctx_mask_dev, pooled_dev, timestep_dev,
+                      history_dev, out_dev, out_dtype, st);
 }
