@@ -71,6 +71,8 @@ struct dv_mmdit_plan {
   // CUDA-graph replay of the forward (DV_MMDIT_GRAPH=1, experimental): the inputs are copied into
   // plan-owned staging buffers so that one captured graph serves every call of this token layout
   cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;  // capture happens on a plan-owned stream (the caller's may be the legacy one)
+  long long graph_launches = 0;       // kernels inside the captured forward (added to the launch counter per replay)
   int graph_io_dtype = -1, graph_enc_dtype = -1, graph_out_dtype = -1;
   std::vector<void*> stage_clips;
   void *stage_enc = nullptr, *stage_hist = nullptr, *stage_out = nullptr;
@@ -347,6 +349,7 @@ extern "C" int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const i
 extern "C" void dv_mmdit_plan_destroy(dv_mmdit_plan* p) {
   if (!p) return;
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   for (void* a : p->allocs) cudaFree(a);
   delete p;
 }
@@ -721,12 +724,19 @@ static int forward_graph(dv_mmdit_plan* p, const void* const* clips_dev, int io_
                                 cudaMemcpyDeviceToDevice, st));
   DV_CHECK_CUDA(cudaMemcpyAsync(p->stage_t, timestep_dev, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToDevice, st));
   if (p->graph_exec == nullptr) {
+    // capture on the plan's own stream: the caller's stream may be the legacy default stream, which cannot
+    // be captured; nothing executes during capture, so no ordering with `st` is needed here
+    if (p->cap_stream == nullptr) DV_CHECK_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
     std::vector<const void*> cl(p->stage_clips.begin(), p->stage_clips.end());
-    DV_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const long long before = launch_count();
+    DV_CHECK_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeRelaxed));
     const int rc = forward_body(p, cl.data(), io_dtype, p->stage_enc, enc_dtype, p->stage_mask, p->stage_pooled,
-                                p->stage_t, p->hist_tokens ? p->stage_hist : nullptr, p->stage_out, out_dtype, st);
+                                p->stage_t, p->hist_tokens ? p->stage_hist : nullptr, p->stage_out, out_dtype,
+                                p->cap_stream);
     cudaGraph_t g = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    const cudaError_t ce = cudaStreamEndCapture(p->cap_stream, &g);
+    p->graph_launches = launch_count() - before;
+    note_launch(static_cast<int>(-p->graph_launches));  // nothing ran yet: the replay below counts them
     if (rc != 0) {
       if (g) cudaGraphDestroy(g);
       return rc;
@@ -736,6 +746,7 @@ static int forward_graph(dv_mmdit_plan* p, const void* const* clips_dev, int io_
     cudaGraphDestroy(g);
   }
   DV_CHECK_CUDA(cudaGraphLaunch(p->graph_exec, st));
+  note_launch(static_cast<int>(p->graph_launches));
   DV_CHECK_CUDA(cudaMemcpyAsync(out_dev, p->stage_out, out_bytes, cudaMemcpyDeviceToDevice, st));
   return DV_OK;
 }

@@ -50,7 +50,15 @@ __global__ void requantise_kernel(const TI* __restrict__ in, int T, long long HW
   const int f = static_cast<int>((i / HW) % n);
   const int c = static_cast<int>(i / (HW * n));
   const float x = ldf(in, (static_cast<long long>(c) * T + t0 + f) * HW + p);
-  float v = __fadd_rn(__fmul_rn(x, 0.5f), 0.5f);
+  float v;
+  if constexpr (sizeof(TI) == 2) {
+    // the reference does `x * 0.5 + 0.5` in the decode dtype and only then `.to(float32)` (pipeline.py:341):
+    // for bf16 frames ATen rounds after each op, so the sum sits on the bf16 grid before `* 255`
+    v = __bfloat162float(__float2bfloat16_rn(__fmul_rn(x, 0.5f)));
+    v = __bfloat162float(__float2bfloat16_rn(__fadd_rn(v, 0.5f)));
+  } else {
+    v = __fadd_rn(__fmul_rn(x, 0.5f), 0.5f);
+  }
   v = fminf(fmaxf(v, 0.0f), 1.0f);
   const float q = truncf(__fmul_rn(v, 255.0f));
   if (u8) u8[(static_cast<long long>(f) * HW + p) * 3 + c] = static_cast<unsigned char>(q);

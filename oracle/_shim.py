@@ -22,7 +22,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DEEPV_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _find_reference() -> str:
+    """$DEEPV_REFERENCE_ROOT, else the mounted reference, else the git-ignored copy that
+    oracle/reference_loader.stage() puts under baseline/_ref/ so that it travels to the GPU box."""
+    env = os.environ.get("DEEPV_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(cand, "model", "mmdit.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:

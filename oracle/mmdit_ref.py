@@ -57,14 +57,14 @@ def cropped_pos(table: Tensor, size: int, h: int, w: int, ori_h: int, ori_w: int
 def timestep_features(t: Tensor, dim: int = 256) -> Tensor:
     """mmdit.py:645-683 with flip_sin_to_cos=True, downscale_freq_shift=0: [cos | sin]."""
     half = dim // 2
-    expo = -math.log(10000) * torch.arange(half, dtype=torch.float32) / half
+    expo = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     ang = t[:, None].float() * torch.exp(expo)[None]
     return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
 
 
 def rope_table(frame_ids: Tensor, head_dim: int) -> Tensor:
     """mmdit.py:999-1012: (cos, sin) of frame * 10000^(-2i/hd), fp64 -> fp32.  [L, hd/2, 2]"""
-    omega = 1.0 / (10000 ** (torch.arange(0, head_dim, 2, dtype=torch.float64) / head_dim))
+    omega = 1.0 / (10000 ** (torch.arange(0, head_dim, 2, dtype=torch.float64, device=frame_ids.device) / head_dim))
     ang = frame_ids.double()[:, None] * omega[None]
     return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float()
 
@@ -116,8 +116,10 @@ def mmdit_forward(W: Dict[str, Tensor], cfg: dict, clips: Sequence[Tensor], time
     D, P, NL = H * hd, cfg["patch_size"], cfg["num_layers"]
     S = cfg["pos_embed_max_size"]
     B = clips[-1].shape[0]
+    dev = clips[-1].device   # the checker may run on any device (CPU here, CUDA fp32 for full-size cases)
     if pos_table is None:
         pos_table = sincos_2d_table(D, S, cfg["sample_size"] // P)
+    pos_table = pos_table.to(dev)
 
     # conditioning vector (mmdit.py:747-753)
     temb = linear(W, "time_text_embed.timestep_embedder.linear_2",
@@ -149,15 +151,15 @@ def mmdit_forward(W: Dict[str, Tensor], cfg: dict, clips: Sequence[Tensor], time
         pos = cropped_pos(pos_table, S, gh, gw, gh_n, gw_n)
         tk = patch_tokens(W, "pos_embed.proj", clip.float(), P).view(B, t, gh * gw, D) + pos[None, None]
         toks.append(tk.reshape(B, t * gh * gw, D))
-        frames.append(torch.arange(f0, f0 + t).repeat_interleave(gh * gw))
+        frames.append(torch.arange(f0, f0 + t, device=dev).repeat_interleave(gh * gw))
         f0 += t
     x = torch.cat(toks, dim=1)
     Lv = x.shape[1]
-    frame_ids = torch.cat([torch.zeros(Lc, dtype=torch.long), torch.cat(frames)])
+    frame_ids = torch.cat([torch.zeros(Lc, dtype=torch.long, device=dev), torch.cat(frames)])
     cs = rope_table(frame_ids, hd)
 
     # attention mask: same sample id (0 = padded) AND frame(q) >= frame(k) (mmdit.py:1414-1434)
-    sid = torch.arange(1, B + 1)[:, None].expand(B, Lc + Lv).clone()
+    sid = torch.arange(1, B + 1, device=dev)[:, None].expand(B, Lc + Lv).clone()
     sid[:, :Lc][ctx_mask == 0] = 0
     mask = (sid[:, :, None] == sid[:, None, :]) & (frame_ids[None, :, None] >= frame_ids[None, None, :])
     mask = mask[:, None]

@@ -140,7 +140,7 @@ def raymap_to_pose(raymap: Tensor, vae_downsample: int = 8):
     x_dir = right - left
     y_dir = torch.linalg.cross(z_dir, x_dir, dim=-1)
     x_dir = torch.linalg.cross(y_dir, z_dir, dim=-1)
-    pose = torch.zeros(b, t, 4, 4)
+    pose = torch.zeros(b, t, 4, 4, device=raymap.device)
     pose[:, :, :3, 0] = x_dir / torch.norm(x_dir, dim=-1, keepdim=True)
     pose[:, :, :3, 1] = y_dir / torch.norm(y_dir, dim=-1, keepdim=True)
     pose[:, :, :3, 2] = z_dir / torch.norm(z_dir, dim=-1, keepdim=True)
@@ -148,7 +148,7 @@ def raymap_to_pose(raymap: Tensor, vae_downsample: int = 8):
     pose[:, :, 3, 3] = 1.0
 
     rescale = (w / w_real + h / h_real) / 2 * vae_downsample
-    intr = torch.zeros(b, t, 4, 4)
+    intr = torch.zeros(b, t, 4, 4, device=raymap.device)
     intr[:, :, 0, 0] = focal * rescale
     intr[:, :, 1, 1] = focal * rescale
     intr[:, :, 0, 2] = w / 2 * vae_downsample
@@ -156,7 +156,7 @@ def raymap_to_pose(raymap: Tensor, vae_downsample: int = 8):
     intr[:, :, 2, 2] = 1.0
     intr[:, :, 3, 3] = 1.0
 
-    pose = torch.cat([torch.eye(4).expand(b, 1, 4, 4), pose], dim=1).to(raymap)
+    pose = torch.cat([torch.eye(4, device=raymap.device).expand(b, 1, 4, 4), pose], dim=1).to(raymap)
     intr = torch.cat([intr[:, :1], intr], dim=1).to(raymap)
     for i in range(t):
         pose[:, i + 1] = torch.bmm(pose[:, i], pose[:, i + 1])
@@ -171,8 +171,8 @@ def camera_raymap(trans2d: Tensor, trans3d: Tensor, depth_shape, vae_downsample:
     for k2, k3 in zip(trans2d, trans3d):
         fu, fv = k2[:, 0, 0].view(-1, 1, 1), k2[:, 1, 1].view(-1, 1, 1)
         cu, cv = k2[:, 0, 2].view(-1, 1, 1), k2[:, 1, 2].view(-1, 1, 1)
-        u = torch.arange(W).view(1, 1, W).expand(k2.shape[0], H, W)
-        v = torch.arange(H).view(1, H, 1).expand(k2.shape[0], H, W)
+        u = torch.arange(W, device=k2.device).view(1, 1, W).expand(k2.shape[0], H, W)
+        v = torch.arange(H, device=k2.device).view(1, H, 1).expand(k2.shape[0], H, W)
         one = torch.ones_like(u)
         rays = torch.stack(((u - cu) / fu, (v - cv) / fv, one, one), dim=1).to(k3)      # [t,4,H,W]
         rays = F.avg_pool2d(rays, kernel_size=vae_downsample, stride=vae_downsample)
@@ -224,7 +224,7 @@ def generate_i2v(m: RolloutModels, motion_prompt: Sequence[str], frames_u8: Tens
         hlen = int((input_history.size(-1) / cfg["history_downsample_ratio"] / 2) *
                    (input_history.size(-2) / cfg["history_downsample_ratio"] / 2))
         history = torch.cat([input_history] * 3)
-        hmask = torch.cat([torch.zeros(2, hlen), torch.ones(1, hlen)])
+        hmask = torch.cat([torch.zeros(2, hlen), torch.ones(1, hlen)]).to(input_history.device)
     neg = m.text_embeds["empty"]
     start = 1 if first else (frames_u8.shape[0] - 1) // 8 + 1                            # :587
     for unit in range(start, num_units):

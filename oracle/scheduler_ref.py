@@ -130,7 +130,7 @@ def generate_one_unit(model_fn: Callable, tables: Dict, latents: torch.Tensor,
                 for c in clips + [x_in]:
                     c[:, 16:] *= 0
             tval = torch.tensor(timesteps[idx], dtype=torch.float64)
-            tt = tval.expand(x_in.shape[0]).to(timestep_dtype or x_in.dtype)  # pipeline.py:473
+            tt = tval.expand(x_in.shape[0]).to(device=x_in.device, dtype=timestep_dtype or x_in.dtype)  # pipeline.py:473
             pred = model_fn(clips + [x_in], tt)
             guided = cfg_combine(pred, w_text, w_hist)
             latents = euler_step(latents, guided, float(sigmas[idx]), float(sigmas[idx + 1]))

@@ -73,8 +73,9 @@ def test_requantise_bit_exact(gpu_rollout, dtype):
     v[0, 0, 7, 0, :8] = torch.tensor([-1.0, 1.0, 0.0, 1 / 255, 2 / 255 - 1, 0.999, -0.999, 0.5]).to(dtype)
     out, u8 = ro.requantise(v.cuda(), 5, 25, want_u8=True)
     torch.cuda.synchronize()
-    last = v.float()[0, :, 5:30].permute(1, 2, 3, 0)
-    want_u8 = (torch.clamp(last * 0.5 + 0.5, 0, 1) * 255).to(torch.uint8)
+    # the reference's op order (pipeline.py:341): `* 0.5 + 0.5` and the clamp in the decode dtype, THEN fp32
+    last = v[0, :, 5:30].permute(1, 2, 3, 0)
+    want_u8 = (torch.clamp(last * 0.5 + 0.5, 0, 1).to(torch.float32) * 255).to(torch.uint8)
     assert torch.equal(u8.cpu(), want_u8)
     assert torch.equal(out.cpu(), rollout_ref.frames_to_input(want_u8))
     assert torch.equal(ro.frames_from_uint8(want_u8).cpu(), rollout_ref.frames_to_input(want_u8))
