@@ -718,7 +718,10 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   for (int i = 0; i < 8; ++i)
     a.out_peer[i] = (out_peers && i < n_peers) ? reinterpret_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
-  static const bool pipe = getenv("DV_ATTN_PIPE") != nullptr;   // experimental double-buffered-S variant
+  // double-buffered-S kernel (one CTA per SM, QK^T of tile j+1 issued before PV of tile j) is the default since
+  // round 2: all GPU suites pass with it, attention time of a C2 step 16.8 -> 14.6 ms (profiles/r02a_summary.txt);
+  // DV_ATTN_PIPE=0 selects the round-1 kernel (two CTAs per SM, S overwritten by P)
+  static const bool pipe = !(getenv("DV_ATTN_PIPE") != nullptr && atoi(getenv("DV_ATTN_PIPE")) == 0);
   static bool attr_set = false;
   if (!attr_set) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -8,8 +8,14 @@ What shards on this path and the exchange step each sharding ne
   * VAE decode — the 6 spatial tiles x {rgb, disparity} of one iteration are independent
     (vae.py:994-1000): work items are dealt round-robin, every decoded tile is broadcast from its
     owner, and each rank blends (the blend needs all tiles, vae.py:1002-1011).
-Ulysses sequence parallelism around the attention is the next sharding (latency-bound at
-L <= 2237) and is not part of round 1.
+  * Ulysses sequence parallelism inside a branch: a branch group of `sp` ranks
+    shards the video tokens; around every attention heads <-> tokens are exchanged, either as
+    epilogue stores into the owning rank's buffers over NVLink (CUDA IPC peer memory, the default)
+    or as a staged NCCL all-to-all (`DV_SP_STAGED=1`); see csrc/mmdit.cu / csrc/comm.cu.
+PRECONDITION of all three: the latents (and therefore every random draw) are REPLICATED over the
+ranks of a rollout group.  `Shard.shared_seed()` broadcasts one seed so that each rank's device
+generator produces the same stream; `B200Rollout` uses it whenever it has to make its own noise
+source under a shard, and refuses an unseeded one.
 
 The functions that decide who does what are pure (tested on CPU); the exchange helpers work on
 any backend (NCCL on the GPUs, gloo in the CPU tests).
@@ -177,6 +183,28 @@ class Shard:
     @property
     def active(self) -> bool:
         return self.world > 1
+
+    # ---- replicated randomness ---------------------------------------------------------------------
+    def shared_seed(self, device=None) -> int:
+        """One 62-bit seed drawn by rank 0 of the group and broadcast: seeding a device generator with it on
+        every rank replicates all later draws (same device type, same draw order).  Collective over the group."""
+        t = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+        if not self.active:
+            return int(t.item())
+        if dist.get_backend(self.group) == "nccl":
+            t = t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        dist.broadcast(t, src=self._global(0), group=self.group)
+        return int(t.item())
+
+    def assert_replicated(self, x: torch.Tensor, what: str = "tensor") -> None:
+        """Debug check (DV_CHECK_REPLICAS=1 in B200Rollout): `x` is bit-identical on every rank of the group."""
+        if not self.active:
+            return
+        ref = x.detach().clone().contiguous()
+        dist.broadcast(ref, src=self._global(0), group=self.group)
+        if not torch.equal(ref, x):
+            raise RuntimeError(f"{what} differs between the ranks of a rollout group (rank {self.rank}): "
+                               "sharded rollouts need replicated latents / noise")
 
     # ---- CFG branches x Ulysses sequence parallelism --------------------------------------------
     def setup_sp(self, device, branch_counts=(1, 2, 3), peer_memory=None) -> None:

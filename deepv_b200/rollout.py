@@ -14,6 +14,7 @@ The heavy work is `B200Pipeline.generate_one_unit`, `B200VAE.encode` and `decode
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -23,6 +24,7 @@ from ._lib import check
 from .pipeline import B200Pipeline, VAE_SCALE, VAE_SHIFT, VAE_VIDEO_SCALE, VAE_VIDEO_SHIFT
 
 NUM_INPUT_IMAGE, NUM_INPUT_UNIT = 25, 4          # pipeline.py:269-270
+_CHECK_REPLICAS = bool(os.environ.get("DV_CHECK_REPLICAS"))   # debug: all-rank equality of every unit's latents
 
 
 class PromptCache:
@@ -83,6 +85,22 @@ class DeviceNoise:
         return self.pipe.sample_block_noise(bs, ch, temp, height, width, self.generator)
 
 
+def noise_for(pipe: B200Pipeline, noise, shard):
+    """The noise source of a rollout.  Un-sharded: whatever was given, else the device's global generator.
+    Sharded (rollout group > 1 rank): latents must stay replicated over the group (CFG branches of different
+    ranks are combined, Ulysses ranks exchange q/k/v of what must be the same input), so a default source is
+    seeded from ONE seed broadcast over the group, and an unseeded DeviceNoise is refused."""
+    if shard is None or not shard.active:
+        return noise or DeviceNoise(pipe)
+    if noise is None:
+        seed = shard.shared_seed(pipe.device)
+        return DeviceNoise(pipe, torch.Generator(device=pipe.device).manual_seed(seed))
+    if isinstance(noise, DeviceNoise) and noise.generator is None:
+        raise _lib.DeepVError("sharded rollout: DeviceNoise needs a generator seeded identically on every rank of the "
+                              "group (or pass noise=None to have one seeded from a broadcast seed)")
+    return noise
+
+
 def plan_prompts(prompts: Sequence[str], actual_unit: int):
     """pipeline.py:275-279: pad the prompt list with its last entry; number of iterations."""
     p = [str(x) for x in prompts]
@@ -107,10 +125,15 @@ class B200Rollout:
 
     def frames_from_uint8(self, frames_u8: torch.Tensor) -> torch.Tensor:
         """uint8 [n,H,W,3] (the PIL frames) -> ToTensor + Normalize(0.5, 0.5) -> [1,3,n,H,W] (pipeline.py:564-568).
-        Host frames are converted on the host, as torchvision does (ATen's CUDA division by a scalar multiplies
-        by the reciprocal and is 1 ulp off); only the first frame of a rollout ever takes this path."""
-        x = frames_u8.cpu().permute(3, 0, 1, 2).to(torch.float32).div(255)
-        return ((x - 0.5) / 0.5).unsqueeze(0).to(self.device, self.dtype).contiguous()
+        The 256 possible values are converted once on the host exactly as torchvision does (ATen's CUDA division
+        by a scalar multiplies by the reciprocal and is 1 ulp off) and gathered on the device, so a frame that is
+        already resident never goes back to the host."""
+        lut = getattr(self, "_u8_lut", None)
+        if lut is None:
+            q = torch.arange(256, dtype=torch.float32).div(255)
+            lut = self._u8_lut = ((q - 0.5) / 0.5).to(self.device, self.dtype)
+        idx = frames_u8.to(self.device, non_blocking=True).permute(3, 0, 1, 2).to(torch.int64)
+        return lut[idx].unsqueeze(0).contiguous()
 
     def requantise(self, images: torch.Tensor, t0: int, n: int, want_u8: bool = False):
         """Frames [t0, t0+n) of a decoded video as the next iteration's input frames (pipeline.py:339-344,564-568)."""
@@ -193,7 +216,7 @@ class B200Rollout:
         input_history [1,38,1,h,w].  Returns image, disparity (raw decodes), trans3d, trans2d."""
         pipe, cfg = self.pipe, self.cfg
         fpu, nst, ray = cfg["frame_per_unit"], len(cfg["stages"]), cfg["raymap_dim"]
-        noise = noise or DeviceNoise(pipe)
+        noise = noise_for(pipe, noise, shard)
         first = input_disparity is None
         if temp % fpu != 0:
             raise _lib.DeepVError("generate_i2v: temp must be a multiple of frame_per_unit")
@@ -231,6 +254,8 @@ class B200Rollout:
             block = [noise.block(1, C, fpu, h0 * 2 ** s, w0 * 2 ** s, gamma) for s in range(1, nst)]
             outs = pipe.generate_one_unit(lat, input_history, conds, enc, mask, pooled, steps, temp=fpu,
                                           is_first_frame=False, block_noise=block, shard=shard)
+            if _CHECK_REPLICAS and shard is not None and shard.active:
+                shard.assert_replicated(outs[-1], f"latent of unit {unit}")
             generated.append(outs[-1])
         if first:
             generated = generated[1:]                                                                     # :680-681
@@ -265,7 +290,7 @@ class B200Rollout:
         feedback — recorded on the current stream, nothing is synchronised here."""
         cfg = self.cfg
         units = cfg["max_temporal_length"]
-        noise = noise or DeviceNoise(self.pipe)
+        noise = noise_for(self.pipe, noise, shard)
         total, iters = plan_prompts(batch_dict["prompt"], units)
         use_table = batch_dict.get("prompt_type", "action") == "action"
         img = batch_dict["img"]

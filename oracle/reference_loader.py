@@ -57,10 +57,15 @@ def modules():
 
 
 def build_mmdit(cfg: dict, W: dict, device="cpu", dtype=torch.float32):
+    """The reference MMDiT with the given state dict.  Constructed on the meta device (its own random init of
+    2 B parameters costs ~1 min of CPU and is overwritten anyway) and the tensors of `W` are assigned, not copied;
+    the sincos table the constructor computes with numpy (mmdit.py:820-824) stays a real buffer."""
     mm, _, _, _ = modules()
-    dit = mm.MMDiT(**{k: cfg[k] for k in MMDIT_KEYS}).eval()
-    missing, unexpected = dit.load_state_dict(W, strict=False)
+    with torch.device("meta"):
+        dit = mm.MMDiT(**{k: cfg[k] for k in MMDIT_KEYS}).eval()
+    missing, unexpected = dit.load_state_dict(W, strict=False, assign=True)
     assert missing == ["pos_embed.pos_embed"] and not unexpected, (missing, unexpected)
+    assert not any(p.is_meta for p in dit.parameters()) and not any(b.is_meta for b in dit.buffers())
     dit.in_channels = cfg["in_channels"]     # diffusers' ModelMixin resolves this from .config (pipeline.py:551)
     return dit.to(device=device, dtype=dtype)
 

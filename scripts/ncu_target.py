@@ -55,6 +55,21 @@ if which in ("all", "gemm"):
     Wt = (torch.randn(1536, 6144, device="cuda") * 0.05).bfloat16()
     Cc = torch.empty(2, 77, 1536, device="cuda", dtype=torch.bfloat16)
     _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), None, p(Cc), 2, 77, 1536, 6144, 0, st))
+if which in ("all", "small"):
+    # stage-0 shapes (fewer tiles than SMs: cluster split-K): FF2 / out-proj / QKV-sized problems at M = 96 rows x B 2
+    for (Bt, M, N, K) in ((2, 96, 1536, 6144), (2, 96, 1536, 1536), (2, 96, 4608, 1536), (2, 384, 6144, 1536)):
+        A = (torch.randn(Bt, M, K, device="cuda") * 0.5).bfloat16()
+        Wt = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        Cc = torch.empty(Bt, M, N, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.dv_gemm_bf16(p(A), p(Wt), None, p(Cc), Bt, M, N, K, 0, st))
+if which in ("all", "conv57"):
+    # the dominant launch of a rollout: up3 resnet conv 128 -> 128 at 256x256 over the 57 frames of an iteration
+    B, T, H, W, Ci, Co = 1, 57, 256, 256, 128, 128
+    x = (torch.randn(B, T, H, W, Ci, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(Co, 27, Ci, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(Co, device="cuda")
+    out = torch.empty(B, T, H, W, Co, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.dv_conv3d_cl(p(x), p(w), p(bias), None, p(out), B, T, H, W, Ci, Co, Co, 3, 0, 0, st))
 if which in ("all", "attn"):
     B, L, H = 2, 1613, 24
     qkv = torch.randn(B, L, 3 * H * 64, device="cuda").bfloat16()

@@ -50,6 +50,20 @@ def _worker(rank, world, port, ret):
         sh.exchange_tiles(bufs)
         for i, (m, t) in enumerate(items):
             assert torch.equal(bufs[i], torch.full((3, 5), float(100 * m + t + 1))), (rank, i)
+        # ---- replicated randomness: one broadcast seed, identical generator streams on every rank
+        torch.manual_seed(1000 + rank)                 # ranks start from DIFFERENT global RNG states
+        seed = sh.shared_seed()
+        draws = torch.randn(5, generator=torch.Generator().manual_seed(seed))
+        alld = [torch.empty_like(draws) for _ in range(world)]
+        dist.all_gather(alld, draws)
+        assert all(torch.equal(d, alld[0]) for d in alld)
+        sh.assert_replicated(draws, "draws")
+        try:                                          # a tensor that differs per rank is caught on every rank but the source
+            sh.assert_replicated(torch.full((3,), float(rank)), "rank id")
+            caught = False
+        except RuntimeError:
+            caught = True
+        assert caught == (rank != 0)
         ret[rank] = len(mine)
     finally:
         dist.destroy_process_group()
@@ -134,3 +148,27 @@ def test_rollout_group_layouts():
     sh = parallel.Shard(5, 8, sp_layouts={2: (2, 4, None), 3: (1, 8, None)})
     assert sh.my_branch(2) == 1 and sh.layout(2)[1] == 4
     assert sh.my_branch(3) == 0 and sh.layout(3)[1] == 8
+
+
+def test_sharded_rollout_refuses_unseeded_noise():
+    """a rollout group must draw identical noise on every rank (rollout.noise_for)."""
+    from deepv_b200 import _lib
+    from deepv_b200.rollout import DeviceNoise, noise_for
+
+    class FakePipe:
+        device = torch.device("cpu")
+
+    class FakeShard:
+        active = True
+
+        def shared_seed(self, device=None):
+            return 1234
+
+    pipe = FakePipe()
+    with pytest.raises(_lib.DeepVError):
+        noise_for(pipe, DeviceNoise(pipe, None), FakeShard())
+    seeded = noise_for(pipe, None, FakeShard())
+    assert isinstance(seeded, DeviceNoise) and seeded.generator.initial_seed() == 1234
+    assert isinstance(noise_for(pipe, None, None), DeviceNoise)          # un-sharded: the global generator is fine
+    mine = DeviceNoise(pipe, torch.Generator().manual_seed(7))
+    assert noise_for(pipe, mine, FakeShard()) is mine
