@@ -66,6 +66,17 @@ def parse():
     return ap.parse_args()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else any library or the reference's own
+    modules print (NCCL banners, `print` in mmdit.py:1249) was redirected to stderr at start-up."""
+    out = _REAL_STDOUT or sys.__stdout__
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def frames_per_step(workload):
     return 8 if workload == "unit" else 57 + 32 * (ROLLOUT_ITERS - 1)
 
@@ -347,7 +358,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": rs.kind, "sample": rs.describe(mean)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def same_box_eager(args):
@@ -426,7 +437,8 @@ def roofline_from_profile(path, prof_ms, peaks):
                 e.update(tflops=round(tf, 1), note="fewer 128x256 tiles than SMs: bounded by streaming the weights once (bytes = "
                                                    "A + W + out of every launch), not by the tensor pipe")
         out[c] = e
-    (dc, dtag), d = max(tags.items(), key=lambda kv: kv[1]["ms"])
+    dom_class = max(classes.items(), key=lambda kv: kv[1]["ms"])[0]
+    (dc, dtag), d = max(((k, v) for k, v in tags.items() if k[0] == dom_class), key=lambda kv: kv[1]["ms"])
     per_launch_ms = d["ms"] / d["launches"]
     bound = out[dc]["bound"]
     traffic, traffic_src = None, None
@@ -448,8 +460,8 @@ def roofline_from_profile(path, prof_ms, peaks):
            "kernel_share_of_step": round(d["ms"] / prof_ms, 4) if prof_ms > 0 else None,
            "peak_source": src, "classes": out, "kernel_time_ms": round(total_ms, 2), "profiled_step_ms": round(prof_ms, 2),
            "how": "CUDA events on the launching stream around every launch of one extra profiled step (graph replay and "
-                  "programmatic-dependent-launch overlap are off while profiling); dominant kernel = the launch tag with the "
-                  "largest total time"}
+                  "programmatic-dependent-launch overlap are off while profiling); dominant kernel = the launch shape with the "
+                  "largest total time inside the kernel class with the largest share of the step"}
     return top
 
 
@@ -670,16 +682,16 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu, "same_box_eager": eager, "replicas": replicas,
                 "published_reference": {"value": 4.0, "unit": "frames/s", "hardware": "1x A800, full run.py pipeline",
                                         "source": "README.md:78", "comparable": False}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     # libraries (NCCL banners, ...) may write to fd 1: keep the real stdout for the ONE JSON line
-    _real_stdout = os.fdopen(os.dup(1), "w")
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    sys.stdout = _real_stdout
+    sys.stdout = sys.stderr
     a = parse()
     if a.impl == "reference":
         run_reference(a)

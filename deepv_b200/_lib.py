@@ -89,10 +89,11 @@ SIGNATURES = {
     "dv_mmdit_plan_flops": (_d, [_vp]),
     "dv_mmdit_forward": (_i, [_vp, _PP, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dv_mmdit_plan_set_sp": (_i, [_vp, _i, _i, _vp, _vp]),
-    "dv_mmdit_plan_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
-    "dv_mmdit_plan_set_sp_peers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "dv_mmdit_plan_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "dv_mmdit_plan_set_sp_peers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "dv_ipc_get_handle": (_i, [_vp, _vp]),
     "dv_ipc_open_handle": (_i, [_vp, C.POINTER(_vp)]),
+    "dv_ipc_close_handle": (_i, [_vp]),
     "dv_comm_unique_id": (_i, [C.c_char_p, _vp]),
     "dv_comm_create": (_i, [C.c_char_p, _vp, _i, _i, C.POINTER(_vp)]),
     "dv_comm_destroy": (None, [_vp]),

@@ -62,7 +62,7 @@ int load_nccl(const char* path) {
   g_nccl.err = reinterpret_cast<FnErrStr>(dlsym(h, "ncclGetErrorString"));
   g_nccl.all_reduce = reinterpret_cast<FnAllReduce>(dlsym(h, "ncclAllReduce"));
   if (!g_nccl.get_id || !g_nccl.init || !g_nccl.destroy || !g_nccl.group_start || !g_nccl.group_end ||
-      !g_nccl.send || !g_nccl.recv || !g_nccl.all_reduce) {
+      !g_nccl.send || !g_nccl.recv || !g_nccl.all_reduce || !g_nccl.err) {
     set_error("dv_comm: libnccl.so.2 lacks a required symbol");
     return DV_ERR_INVALID;
   }
@@ -115,7 +115,7 @@ extern "C" int dv_comm_create(const char* nccl_path, const void* id128, int rank
   }
   if (cudaMalloc(&c->token, 2 * sizeof(int)) != cudaSuccess || cudaMemset(c->token, 0, 2 * sizeof(int)) != cudaSuccess) {
     set_error("dv_comm_create: cannot allocate the barrier word");
-    delete c;
+    dv_comm_destroy(c);   // frees the word (if any) and the communicator
     return DV_ERR_CUDA;
   }
   *out = c;
@@ -145,12 +145,19 @@ extern "C" int dv_comm_exchange(void* user, const void* send_dev, void* recv_dev
   const char* s = reinterpret_cast<const char*>(send_dev);
   char* r = reinterpret_cast<char*>(recv_dev);
   DV_NCCL(g_nccl.group_start());
-  for (int p = 0; p < c->world; ++p) {
-    DV_NCCL(g_nccl.send(s + static_cast<size_t>(p) * bytes_per_peer, static_cast<size_t>(bytes_per_peer),
-                        0 /*ncclInt8*/, p, c->comm, st));
-    DV_NCCL(g_nccl.recv(r + static_cast<size_t>(p) * bytes_per_peer, static_cast<size_t>(bytes_per_peer), 0,
-                        p, c->comm, st));
+  int first_err = 0;   // the group is always closed, or later collectives would hang instead of failing
+  for (int p = 0; p < c->world && first_err == 0; ++p) {
+    first_err = g_nccl.send(s + static_cast<size_t>(p) * bytes_per_peer, static_cast<size_t>(bytes_per_peer),
+                            0 /*ncclInt8*/, p, c->comm, st);
+    if (first_err == 0)
+      first_err = g_nccl.recv(r + static_cast<size_t>(p) * bytes_per_peer, static_cast<size_t>(bytes_per_peer), 0,
+                              p, c->comm, st);
   }
-  DV_NCCL(g_nccl.group_end());
+  const int end_err = g_nccl.group_end();
+  if (first_err != 0 || end_err != 0) {
+    const int e = first_err != 0 ? first_err : end_err;
+    set_error("dv_comm_exchange: NCCL error %d (%s)", e, g_nccl.err(e));
+    return DV_ERR_CUDA;
+  }
   return DV_OK;
 }

@@ -400,7 +400,79 @@ __global__ void sp_x_unpack_kernel(const float4* __restrict__ stage, float4* __r
   x[(static_cast<long long>(b) * Lv + i * Lw + l) * dv + c] = stage[idx];
 }
 
+// ---- sequence parallelism over peer memory: barrier and all-gather without NCCL ---------------------------
+struct SpPeers {
+  void* p[8];
+};
+// One warp.  Lane j announces this rank's arrival (epoch e) in rank j's flag array and then waits until rank j's
+// arrival shows up in this rank's own array.  Epochs only grow, so a peer that is already one barrier ahead is
+// still seen as arrived.  The previous kernels of this stream have completed (the barrier is launched without the
+// programmatic-serialization attribute), i.e. their stores into the peers' buffers are performed before the
+// release store of the flag.  A peer that never arrives traps after 30 s instead of hanging the box.
+__global__ void sp_barrier_kernel(SpPeers flags, int* __restrict__ epoch, int rank, int P) {
+  __shared__ int e_sh;
+  if (threadIdx.x == 0) {
+    e_sh = *epoch + 1;
+    *epoch = e_sh;
+  }
+  __syncthreads();
+  const int e = e_sh;
+  const int j = threadIdx.x;
+  if (j < P) {
+    __threadfence_system();
+    int* dst = reinterpret_cast<int*>(flags.p[j]) + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(e) : "memory");
+    const int* src = reinterpret_cast<const int*>(flags.p[rank]) + j;
+    const uint64_t t0 = global_ns();
+    while (true) {
+      int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      if (v - e >= 0) break;
+      if (global_ns() - t0 > 30000000000ull) asm volatile("trap;");
+    }
+  }
+}
+// rows [row0, row0 + rows) of my fp32 stream -> the same rows of every peer's stream (plain stores over NVLink)
+__global__ void sp_x_share_kernel(SpPeers xs, int B, int Lv, int D, int row0, int rows, int rank, int P) {
+  const int dv = D / 4;
+  const long long per_peer = static_cast<long long>(B) * rows * dv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= per_peer * (P - 1)) return;
+  int j = static_cast<int>(idx / per_peer);
+  if (j >= rank) ++j;
+  long long t = idx % per_peer;
+  const int c = t % dv;
+  t /= dv;
+  const int l = t % rows;
+  const int b = static_cast<int>(t / rows);
+  const long long off = (static_cast<long long>(b) * Lv + row0 + l) * dv + c;
+  reinterpret_cast<float4*>(xs.p[j])[off] = reinterpret_cast<const float4*>(xs.p[rank])[off];
+}
+
 }  // namespace
+
+int launch_sp_barrier(void* const* flag_peers, int* epoch, int rank, int P, cudaStream_t stream) {
+  DV_REQUIRE(flag_peers && epoch && P >= 2 && P <= 8 && rank >= 0 && rank < P, "sp_barrier: bad argument");
+  SpPeers f;
+  for (int i = 0; i < 8; ++i) f.p[i] = i < P ? flag_peers[i] : nullptr;
+  sp_barrier_kernel<<<1, 32, 0, stream>>>(f, epoch, rank, P);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_sp_x_share(void* const* x_peers, int B, int Lv, int D, int row0, int rows, int rank, int P,
+                      cudaStream_t stream) {
+  DV_REQUIRE(x_peers && P >= 2 && P <= 8 && rank >= 0 && rank < P && D % 4 == 0, "sp_x_share: bad argument");
+  if (rows <= 0) return 0;
+  SpPeers x;
+  for (int i = 0; i < 8; ++i) x.p[i] = i < P ? x_peers[i] : nullptr;
+  const long long n = static_cast<long long>(P - 1) * B * rows * (D / 4);
+  sp_x_share_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, B, Lv, D, row0, rows, rank, P);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
 
 int launch_ln_modulate2(const LnRows& r0, const LnRows* r1, int mod_bs, int B, int D, float eps,
                         cudaStream_t stream) {

@@ -98,5 +98,10 @@ int launch_sp_x_pack(const float* x, void* stage, int B, int Lv, int D, int Lw, 
                      cudaStream_t stream);
 int launch_sp_x_unpack(const void* stage, float* x, int B, int Lv, int D, int Lw, int P, int r,
                        cudaStream_t stream);
+// peer-memory variant without NCCL: flag_peers[i] = rank i's int[8] arrival words, epoch = this rank's device-resident
+// barrier counter; x_peers[i] = rank i's fp32 stream [B][Lv][D]
+int launch_sp_barrier(void* const* flag_peers, int* epoch, int rank, int P, cudaStream_t stream);
+int launch_sp_x_share(void* const* x_peers, int B, int Lv, int D, int row0, int rows, int rank, int P,
+                      cudaStream_t stream);
 
 }  // namespace dv

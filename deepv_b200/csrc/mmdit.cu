@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/deepv_b200.h"
+#include <cstdlib>
 #include <cstring>
 
 #include "gemm.cuh"
@@ -68,6 +69,13 @@ struct dv_mmdit_plan {
   void* qkv_peer[8] = {nullptr};
   void* attn_peer[8] = {nullptr};
   bool peers_set = false;
+  // device-side barrier + all-gather of the stream over peer memory (no NCCL, no host callback in the forward, so
+  // a sequence-parallel forward can be replayed as a CUDA graph): every rank's fp32 stream and flag words mapped
+  void* x_peer[8] = {nullptr};
+  void* flag_peer[8] = {nullptr};
+  bool dev_barrier = false;
+  int* sp_flags = nullptr;   // [8] arrival epochs written by the peers (slot = source rank)
+  int* sp_epoch = nullptr;   // [1] this rank's barrier count (device resident: graph replays keep counting)
   // CUDA-graph replay of the forward (DV_MMDIT_GRAPH=1, experimental): the inputs are copied into
   // plan-owned staging buffers so that one captured graph serves every call of this token layout
   cudaGraphExec_t graph_exec = nullptr;
@@ -366,19 +374,30 @@ extern "C" int dv_mmdit_plan_set_sp(dv_mmdit_plan* p, int sp_rank, int sp_world,
   DV_REQUIRE(sp_world == 1 || fn != nullptr, "dv_mmdit_plan_set_sp: exchange function missing");
   if (sp_world > 1 && p->sp_send == nullptr) {
     const int D = p->m->D;
-    const long long Lw = p->Lv / sp_world;
-    // the largest exchange: q|k|v of my rows (bf16), the attention rows (bf16), the fp32 stream
-    long long bytes = static_cast<long long>(p->B) * Lw * 3 * D * 2;
-    const long long b2 = static_cast<long long>(sp_world) * p->B * (p->Lc + Lw) * (D / sp_world) * 2;
-    const long long b3 = static_cast<long long>(sp_world) * p->B * Lw * D * 4;
+    // sized for every sp_world >= 2 (a cached plan may be re-sharded): q|k|v of my rows (bf16), the attention rows
+    // of all context + my video rows (bf16), the fp32 stream
+    const long long half = (p->Lv + 1) / 2;
+    long long bytes = static_cast<long long>(p->B) * half * 3 * D * 2;
+    const long long b2 = static_cast<long long>(p->B) * (p->Lc + half) * D * 2;
+    const long long b3 = static_cast<long long>(p->B) * p->Lv * D * 4;
     bytes = bytes > b2 ? bytes : b2;
     bytes = bytes > b3 ? bytes : b3;
     char *s0 = nullptr, *s1 = nullptr;
     int rc = dev_alloc(p, &s0, bytes);
     if (rc == 0) rc = dev_alloc(p, &s1, bytes);
+    if (rc == 0) rc = dev_alloc(p, &p->sp_flags, 8);
+    if (rc == 0) rc = dev_alloc(p, &p->sp_epoch, 1);
     if (rc) return rc;
     p->sp_send = s0;
     p->sp_recv = s1;
+  }
+  if (sp_world != p->sp_world || sp_rank != p->sp_rank) {   // a different sharding: peers and the captured graph are stale
+    p->peers_set = false;
+    p->dev_barrier = false;
+    if (p->graph_exec) {
+      cudaGraphExecDestroy(p->graph_exec);
+      p->graph_exec = nullptr;
+    }
   }
   p->sp_rank = sp_rank;
   p->sp_world = sp_world;
@@ -387,15 +406,24 @@ extern "C" int dv_mmdit_plan_set_sp(dv_mmdit_plan* p, int sp_rank, int sp_world,
   return DV_OK;
 }
 
-extern "C" int dv_mmdit_plan_buffers(dv_mmdit_plan* p, void** qkv_dev, void** attn_dev) {
+extern "C" int dv_mmdit_plan_buffers(dv_mmdit_plan* p, void** qkv_dev, void** attn_dev, void** x_dev,
+                                     void** flags_dev) {
   DV_REQUIRE(p && qkv_dev && attn_dev, "dv_mmdit_plan_buffers: null argument");
   *qkv_dev = p->qkv;
   *attn_dev = p->attn;
+  if (x_dev) *x_dev = p->x;
+  if (flags_dev) *flags_dev = p->sp_flags;   // null before dv_mmdit_plan_set_sp(sp_world > 1)
   return DV_OK;
 }
 
-extern "C" int dv_mmdit_plan_set_sp_peers(dv_mmdit_plan* p, void* const* qkv_ptrs, void* const* attn_ptrs) {
+extern "C" int dv_mmdit_plan_set_sp_peers(dv_mmdit_plan* p, void* const* qkv_ptrs, void* const* attn_ptrs,
+                                          void* const* x_ptrs, void* const* flag_ptrs) {
   DV_REQUIRE(p, "dv_mmdit_plan_set_sp_peers: null plan");
+  if (p->graph_exec) {   // the captured forward holds the old pointers
+    cudaGraphExecDestroy(p->graph_exec);
+    p->graph_exec = nullptr;
+  }
+  p->dev_barrier = false;
   if (qkv_ptrs == nullptr || attn_ptrs == nullptr) {
     p->peers_set = false;
     return DV_OK;
@@ -410,6 +438,16 @@ extern "C" int dv_mmdit_plan_set_sp_peers(dv_mmdit_plan* p, void* const* qkv_ptr
   DV_REQUIRE(p->qkv_peer[p->sp_rank] == p->qkv && p->attn_peer[p->sp_rank] == p->attn,
              "dv_mmdit_plan_set_sp_peers: entry %d must be this plan's own buffers", p->sp_rank);
   p->peers_set = true;
+  if (x_ptrs != nullptr && flag_ptrs != nullptr) {
+    for (int i = 0; i < p->sp_world; ++i) {
+      DV_REQUIRE(x_ptrs[i] && flag_ptrs[i], "dv_mmdit_plan_set_sp_peers: null stream / flag pointer for rank %d", i);
+      p->x_peer[i] = x_ptrs[i];
+      p->flag_peer[i] = flag_ptrs[i];
+    }
+    DV_REQUIRE(p->x_peer[p->sp_rank] == p->x && p->flag_peer[p->sp_rank] == p->sp_flags,
+               "dv_mmdit_plan_set_sp_peers: entry %d must be this plan's own stream / flags", p->sp_rank);
+    p->dev_barrier = true;
+  }
   return DV_OK;
 }
 
@@ -427,6 +465,12 @@ extern "C" int dv_ipc_open_handle(const void* handle64, void** dev_ptr) {
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, sizeof(h));
   DV_CHECK_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DV_OK;
+}
+
+extern "C" int dv_ipc_close_handle(void* dev_ptr) {
+  DV_REQUIRE(dev_ptr, "dv_ipc_close_handle: null pointer");
+  DV_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
   return DV_OK;
 }
 
@@ -519,6 +563,13 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
     if (erc != 0 && last_error()[0] == 0) set_error("dv_mmdit_forward: exchange callback failed (%d)", erc);
     return erc;
   };
+  const bool peer = P > 1 && p->peers_set;
+  const bool devbar = peer && p->dev_barrier;
+  // barrier of the peer-memory variant: flag stores + polling on the device, or NCCL's one-word all-reduce
+  auto sp_sync = [&]() -> int {
+    if (devbar) return launch_sp_barrier(p->flag_peer, p->sp_epoch, R, P, st);
+    return exchange(0);
+  };
   // ---- transformer blocks ------------------------------------------------------------------
   // Every step of a joint block is ONE launch covering the video and the context stream
   // (the reference runs them as separate modules, mmdit.py:385-433).
@@ -558,9 +609,8 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
       }
       DV_RUN(launch_gemm_pair(dq[0], &dq[1], st));
     }
-    const bool peer = P > 1 && p->peers_set;
     if (peer) {
-      DV_RUN(exchange(0));  // barrier: every rank's q|k|v stores have landed
+      DV_RUN(sp_sync());  // barrier: every rank's q|k|v stores have landed
     } else if (P > 1) {
       // my rows, every rank's heads  ->  every rank's rows, my heads
       DV_RUN(launch_sp_qkv_pack(p->qkv, p->sp_send, B, L, D, Lc + v0, Lw, P, Hc, st));
@@ -571,7 +621,7 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
                             m->cfg.num_heads, st, p->attn_flops_layer / P, R * (m->cfg.num_heads / P),
                             m->cfg.num_heads / P, peer ? p->attn_peer : nullptr, peer ? P : 0, Lc, Lw));
     if (peer) {
-      DV_RUN(exchange(0));  // barrier: every rank's attention rows have landed
+      DV_RUN(sp_sync());  // barrier: every rank's attention rows have landed
     } else if (P > 1) {
       // all context rows + rank j's video rows of my heads -> rank j; back come the other heads
       DV_RUN(launch_sp_attn_pack(p->attn, p->sp_send, B, L, D, Lc, Lw, P, Hc, R, st));
@@ -634,10 +684,17 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
   }
 
   if (P > 1) {
-    // every rank runs the (cheap) output head on the full video stream: all-gather the windows
-    DV_RUN(launch_sp_x_pack(p->x, p->sp_send, B, Lv, D, Lw, P, R, st));
-    DV_RUN(exchange(static_cast<long long>(B) * Lw * D * 4));
-    DV_RUN(launch_sp_x_unpack(p->sp_recv, p->x, B, Lv, D, Lw, P, R, st));
+    // every rank runs the (cheap) output head itself: all-gather the rows of the noisy clip
+    if (devbar) {
+      const ClipInfo& lcl = p->clips.back();
+      const int lo = v0 > lcl.row0 ? v0 : lcl.row0, hi = v0 + Lw;
+      DV_RUN(launch_sp_x_share(p->x_peer, B, Lv, D, lo, hi > lo ? hi - lo : 0, R, P, st));
+      DV_RUN(sp_sync());
+    } else {
+      DV_RUN(launch_sp_x_pack(p->x, p->sp_send, B, Lv, D, Lw, P, R, st));
+      DV_RUN(exchange(static_cast<long long>(B) * Lw * D * 4));
+      DV_RUN(launch_sp_x_unpack(p->sp_recv, p->x, B, Lv, D, Lw, P, R, st));
+    }
   }
   // ---- head: norm_out (scale, shift) + proj_out + unpatchify, noisy clip only ---------------
   {
@@ -762,8 +819,14 @@ extern "C" int dv_mmdit_forward(dv_mmdit_plan* p, const void* const* clips_dev, 
              "dv_mmdit_forward: history pointer does not match the plan (plan has %d history tokens)",
              p->hist_tokens);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-  static const bool use_graph = getenv("DV_MMDIT_GRAPH") != nullptr;
-  if (use_graph && p->sp_world == 1 && !prof_on())
+  // CUDA-graph replay: DV_MMDIT_GRAPH=1 always (when possible), =0 never; default: for sequence-parallel forwards
+  // over peer memory (row windows make every launch latency-bound and the host issue rate the limit), not for
+  // single-rank forwards (GPU-bound: measured 172.2 vs 171.6 ms per C2 step, profiles/r02a_summary.txt)
+  static const char* genv = getenv("DV_MMDIT_GRAPH");
+  static const int gmode = genv ? (atoi(genv) != 0 ? 1 : 0) : -1;
+  const bool capturable = p->sp_world == 1 || (p->peers_set && p->dev_barrier);   // no host callback inside
+  const bool use_graph = gmode == 1 || (gmode == -1 && p->sp_world > 1);
+  if (use_graph && capturable && !prof_on())
     return forward_graph(p, clips_dev, io_dtype, enc_dev, enc_dtype, ctx_mask_dev, pooled_dev, timestep_dev,
                          history_dev, out_dev, out_dtype, st);
   return forward_body(p, clips_dev, io_dtype, enc_dev, enc_dtype, ctx_mask_dev, pooled_dev, timestep_dev,

@@ -188,16 +188,18 @@ class B200MMDiT:
             check(self.lib.dv_mmdit_plan_set_sp(p, sp[0], sp[1], fn, user), "dv_mmdit_plan_set_sp")
             keep = getattr(self, "_sp_keep", None)
             if sp[1] > 1 and callable(getattr(keep, "peer_pointers", None)):
-                # peer-memory exchange: every rank of the group maps the others' qkv / attention buffers
-                # (collective: all ranks of the SP group create their plans in the same order)
-                q, a = C.c_void_p(), C.c_void_p()
-                check(self.lib.dv_mmdit_plan_buffers(p, C.byref(q), C.byref(a)), "dv_mmdit_plan_buffers")
-                qs, as_ = keep.peer_pointers(key, q.value, a.value)
-                qa = (C.c_void_p * sp[1])(*qs)
-                aa = (C.c_void_p * sp[1])(*as_)
-                check(self.lib.dv_mmdit_plan_set_sp_peers(p, qa, aa), "dv_mmdit_plan_set_sp_peers")
+                # peer-memory exchange: every rank of the group maps the others' qkv / attention buffers, fp32 stream
+                # and barrier flag words (collective: all ranks of the SP group create their plans in the same order)
+                mine = [C.c_void_p() for _ in range(4)]
+                check(self.lib.dv_mmdit_plan_buffers(p, *[C.byref(m) for m in mine]), "dv_mmdit_plan_buffers")
+                lists = keep.peer_pointers(key, [m.value for m in mine])
+                arrs = [(C.c_void_p * sp[1])(*lst) for lst in lists]
+                if getattr(keep, "device_barrier", True) and len(arrs) == 4:
+                    check(self.lib.dv_mmdit_plan_set_sp_peers(p, *arrs), "dv_mmdit_plan_set_sp_peers")
+                else:   # NCCL (or the host callback) stays the barrier and carries the final all-gather
+                    check(self.lib.dv_mmdit_plan_set_sp_peers(p, arrs[0], arrs[1], None, None), "dv_mmdit_plan_set_sp_peers")
             else:
-                check(self.lib.dv_mmdit_plan_set_sp_peers(p, None, None), "dv_mmdit_plan_set_sp_peers")
+                check(self.lib.dv_mmdit_plan_set_sp_peers(p, None, None, None, None), "dv_mmdit_plan_set_sp_peers")
             applied[p] = want
         return p
 

@@ -22,6 +22,7 @@ any backend (NCCL on the GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Sequence, Tuple
 
@@ -61,35 +62,41 @@ class NcclExchange:
         self.rank, self.world = rank, world
         self.fn_ptr = C.cast(lib.dv_comm_exchange, C.c_void_p)
         self.user_ptr = handle
+        self._opened = []     # peers' buffers mapped through CUDA IPC (closed in close())
+        # DV_SP_NCCL_BARRIER=1: keep NCCL's one-word all-reduce as the barrier of the peer-memory variant
+        self.device_barrier = os.environ.get("DV_SP_NCCL_BARRIER", "") == ""
 
-    def peer_pointers(self, _key, qkv_ptr: int, attn_ptr: int):
-        """Map every rank's qkv / attention buffers into this process (CUDA IPC): the forward then
-        stores q|k|v heads and attention rows straight into their owner's buffer over NVLink and
-        uses the NCCL exchange only as a barrier.  Collective over the group."""
+    def peer_pointers(self, _key, ptrs):
+        """Map the listed device buffers of every rank into this process (CUDA IPC): `ptrs` = this rank's
+        [qkv, attention, fp32 stream, barrier flags]; returns one list per buffer with every rank's pointer
+        (own entry = own pointer).  The forward then stores q|k|v heads and attention rows straight into
+        their owner's buffer over NVLink and synchronises through the flag words.  Collective over the group."""
         import ctypes as C
 
         from . import _lib
         lib = self._lib
-        mine = (C.c_char * 128)()
-        _lib.check(lib.dv_ipc_get_handle(qkv_ptr, C.cast(mine, C.c_void_p)), "dv_ipc_get_handle")
-        _lib.check(lib.dv_ipc_get_handle(attn_ptr, C.cast(C.byref(mine, 64), C.c_void_p)), "dv_ipc_get_handle")
+        n = len(ptrs)
+        mine = (C.c_char * (64 * n))()
+        for i, ptr in enumerate(ptrs):
+            _lib.check(lib.dv_ipc_get_handle(ptr, C.cast(C.byref(mine, 64 * i), C.c_void_p)), "dv_ipc_get_handle")
         t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone()
         on_dev = dist.get_backend(self.group) == "nccl"
         t = t.to(self.device) if on_dev else t
         bufs = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(bufs, t, group=self.group)
-        qs, as_ = [], []
+        out = [[] for _ in range(n)]
         for r in range(self.world):
             if r == self.rank:
-                qs.append(qkv_ptr)
-                as_.append(attn_ptr)
+                for i in range(n):
+                    out[i].append(ptrs[i])
                 continue
             raw = bytes(bufs[r].cpu().numpy().tobytes())
-            for off, lst in ((0, qs), (64, as_)):
+            for i in range(n):
                 ptr = C.c_void_p()
-                _lib.check(lib.dv_ipc_open_handle(raw[off:off + 64], C.byref(ptr)), "dv_ipc_open_handle")
-                lst.append(ptr.value)
-        return qs, as_
+                _lib.check(lib.dv_ipc_open_handle(raw[64 * i:64 * (i + 1)], C.byref(ptr)), "dv_ipc_open_handle")
+                self._opened.append(ptr.value)
+                out[i].append(ptr.value)
+        return out
 
     @staticmethod
     def _nccl_path():
@@ -106,6 +113,15 @@ class NcclExchange:
         return b""
 
     def close(self):
+        """Unmap the peers' buffers and destroy the communicator.  Collective: every rank of the group must
+        have stopped issuing forwards first (the owners free the buffers when their plans are destroyed)."""
+        if self._opened:
+            if dist.is_initialized():
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+            for ptr in self._opened:
+                self._lib.dv_ipc_close_handle(ptr)
+            self._opened = []
         if self._handle:
             self._lib.dv_comm_destroy(self._handle)
             self._handle = None

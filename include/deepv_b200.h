@@ -195,11 +195,19 @@ int dv_mmdit_plan_set_sp(dv_mmdit_plan* p, int sp_rank, int sp_world, dv_exchang
  * owner's buffer — NVLink stores issued tile by tile while the tensor pipe keeps working — and the
  * exchange callback is only called as a barrier (bytes_per_peer == 0, null buffers).
  * qkv_ptrs / attn_ptrs: sp_world device pointers each, entry sp_rank = this plan's own buffers
- * (dv_mmdit_plan_buffers); NULL switches back to the staged all-to-all.                          */
-int dv_mmdit_plan_buffers(dv_mmdit_plan* p, void** qkv_dev, void** attn_dev);
-int dv_mmdit_plan_set_sp_peers(dv_mmdit_plan* p, void* const* qkv_ptrs, void* const* attn_ptrs);
+ * (dv_mmdit_plan_buffers); NULL switches back to the staged all-to-all.
+ * x_ptrs / flag_ptrs (optional, both or neither): every rank's fp32 video stream and int[8] arrival
+ * words.  With them the barrier is a one-warp kernel (release store of an epoch into every peer's
+ * flag word, acquire-polling of the own words) and the final all-gather of the stream is a peer-store
+ * kernel: the forward then contains no NCCL call and no host callback, and is replayed as a CUDA
+ * graph.  Without them the exchange callback serves as the barrier (bytes_per_peer == 0).
+ * x_dev / flags_dev of dv_mmdit_plan_buffers may be NULL; flags exist after dv_mmdit_plan_set_sp.   */
+int dv_mmdit_plan_buffers(dv_mmdit_plan* p, void** qkv_dev, void** attn_dev, void** x_dev, void** flags_dev);
+int dv_mmdit_plan_set_sp_peers(dv_mmdit_plan* p, void* const* qkv_ptrs, void* const* attn_ptrs,
+                               void* const* x_ptrs, void* const* flag_ptrs);
 int dv_ipc_get_handle(const void* dev_ptr, void* handle64);      /* cudaIpcGetMemHandle  */
 int dv_ipc_open_handle(const void* handle64, void** dev_ptr);    /* cudaIpcOpenMemHandle */
+int dv_ipc_close_handle(void* dev_ptr);                          /* cudaIpcCloseMemHandle (after the peers' plans are idle) */
 
 typedef struct dv_comm dv_comm;
 int dv_comm_unique_id(const char* nccl_path, void* id128);   /* rank 0: 128-byte id to broadcast */

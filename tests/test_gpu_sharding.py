@@ -53,12 +53,17 @@ def test_tile_granular_decode_equals_fused_decode():
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("peer_memory", [False, True])
-def test_ulysses_two_virtual_ranks_match_single_rank(peer_memory):
+@pytest.mark.parametrize("mode", ["staged", "peer_host_barrier", "peer_device_barrier"])
+def test_ulysses_two_virtual_ranks_match_single_rank(mode):
     """Ulysses sequence parallelism (csrc/mmdit.cu + the staging kernels) with two virtual ranks on
     ONE device: two models run the same forward in two threads, each on its own stream, and the
     all-to-all callback swaps the staged blocks between them.  Both must reproduce the unsharded
-    forward (same kernels on a row window; split-K factors may re-associate sums)."""
+    forward (same kernels on a row window; split-K factors may re-associate sums).
+      staged               pack -> exchange callback -> unpack around every attention
+      peer_host_barrier    epilogues store into the owner's buffers, the callback is only a barrier
+      peer_device_barrier  ... and the barrier / final all-gather are kernels too (flag words + peer stores): the
+                           callback is never called and the forward is replayed as a CUDA graph"""
+    peer_memory = mode != "staged"
     import ctypes as C
     import threading
 
@@ -93,12 +98,14 @@ def test_ulysses_two_virtual_ranks_match_single_rank(peer_memory):
         def __call__(self, send, recv, nbytes, stream):
             return self.fn(send, recv, nbytes, stream)
 
-        def peer_pointers(self, key, q, a):
-            shared[(key, self.r)] = (q, a)
+        device_barrier = mode == "peer_device_barrier"
+
+        def peer_pointers(self, key, ptrs):
+            shared[(key, self.r)] = list(ptrs)
             barrier.wait()
             got = [shared[(key, i)] for i in range(P)]
             barrier.wait()
-            return [g[0] for g in got], [g[1] for g in got]
+            return [[g[k] for g in got] for k in range(len(ptrs))]
 
     def make_exchange(r):
         def exchange(send, recv, nbytes, stream):
@@ -141,5 +148,24 @@ def test_ulysses_two_virtual_ranks_match_single_rank(peer_memory):
     for r in range(P):
         err = ((outs[r] - ref).abs().max() / ref.abs().max()).item()
         assert err <= 5e-3, (r, err)
-    # peer memory: q|k|v and attention rows travel as stores, only the all-gather of the stream is staged
-    assert payload_calls == ([1] * P if peer_memory else [2 * cfg["num_layers"] + 1] * P)
+    # peer memory: q|k|v and attention rows travel as stores; with the host barrier only the all-gather of the
+    # stream is staged, with the device barrier nothing is
+    want = {"staged": 2 * cfg["num_layers"] + 1, "peer_host_barrier": 1, "peer_device_barrier": 0}[mode]
+    assert payload_calls == [want] * P
+    if mode == "peer_device_barrier":
+        # a second forward replays the captured graph (epochs keep counting on the device)
+        def again(r):
+            try:
+                with torch.cuda.stream(torch.cuda.Stream()):
+                    outs[r] = call(models[r])
+                    torch.cuda.current_stream().synchronize()
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        threads = [threading.Thread(target=again, args=(r,)) for r in range(P)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=120)
+        assert not errs, errs
+        for r in range(P):
+            assert ((outs[r] - ref).abs().max() / ref.abs().max()).item() <= 5e-3
