@@ -63,6 +63,7 @@ class NcclExchange:
         self.fn_ptr = C.cast(lib.dv_comm_exchange, C.c_void_p)
         self.user_ptr = handle
         self._opened = []     # peers' buffers mapped through CUDA IPC (closed in close())
+        self._peer_cache = {}
         # DV_SP_NCCL_BARRIER=1: keep NCCL's one-word all-reduce as the barrier of the peer-memory variant
         self.device_barrier = os.environ.get("DV_SP_NCCL_BARRIER", "") == ""
 
@@ -76,6 +77,9 @@ class NcclExchange:
         from . import _lib
         lib = self._lib
         n = len(ptrs)
+        ck = (_key, tuple(ptrs))
+        if ck in self._peer_cache:      # the same plan re-sharded the same way: its peers are already mapped
+            return self._peer_cache[ck]  # (every rank of the group takes this branch together)
         mine = (C.c_char * (64 * n))()
         for i, ptr in enumerate(ptrs):
             _lib.check(lib.dv_ipc_get_handle(ptr, C.cast(C.byref(mine, 64 * i), C.c_void_p)), "dv_ipc_get_handle")
@@ -96,6 +100,7 @@ class NcclExchange:
                 _lib.check(lib.dv_ipc_open_handle(raw[64 * i:64 * (i + 1)], C.byref(ptr)), "dv_ipc_open_handle")
                 self._opened.append(ptr.value)
                 out[i].append(ptr.value)
+        self._peer_cache[ck] = out
         return out
 
     @staticmethod
@@ -122,6 +127,7 @@ class NcclExchange:
             for ptr in self._opened:
                 self._lib.dv_ipc_close_handle(ptr)
             self._opened = []
+            self._peer_cache = {}
         if self._handle:
             self._lib.dv_comm_destroy(self._handle)
             self._handle = None
