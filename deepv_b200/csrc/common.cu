@@ -165,16 +165,22 @@ std::mutex g_tm_mutex;
 std::unordered_map<TmKey, CUtensorMap, TmHash>* g_tm_cache = nullptr;
 }  // namespace
 
-static int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+static int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box, int swizzle, int f32);
 
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+  return make_tensor_map(out, base, 0, rank, dims, strides_bytes, box, swizzle128 ? 1 : 0);
+}
+
+// swizzle: 0 none, 1 = 128 B, 2 = 64 B; f32: 0 = bf16 elements, 1 = fp32 elements
+int make_tensor_map(CUtensorMap* out, const void* base, int f32, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
   TmKey key;
   memset(&key, 0, sizeof(key));
   key.base = base;
   key.rank = rank;
-  key.swz = swizzle128;
+  key.swz = swizzle | (f32 << 8);
   for (int i = 0; i < rank && i < 5; ++i) {
     key.dims[i] = dims[i];
     key.box[i] = box[i];
@@ -189,7 +195,7 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
       return 0;
     }
   }
-  int rc = encode_tensor_map_bf16(out, base, rank, dims, strides_bytes, box, swizzle128);
+  int rc = encode_tensor_map(out, base, rank, dims, strides_bytes, box, swizzle, f32);
   if (rc) return rc;
   std::lock_guard<std::mutex> lock(g_tm_mutex);
   if (g_tm_cache->size() > (1u << 16)) g_tm_cache->clear();  // unbounded callers (sweeps): start over
@@ -197,8 +203,8 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
   return 0;
 }
 
-static int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+static int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box, int swizzle, int f32) {
   EncodeTiledFn enc = get_encode();
   DV_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver / device?)");
   DV_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
@@ -216,9 +222,10 @@ static int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, 
     DV_REQUIRE(strides_bytes[i] % 16 == 0, "TMA stride[%d]=%llu not a multiple of 16 bytes", i,
                (unsigned long long)strides_bytes[i]);
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+  const CUtensorMapSwizzle sw = swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                   const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r,
              rank);

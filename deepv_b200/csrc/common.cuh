@@ -169,6 +169,32 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// ---- TMA stores (shared -> global through a tensor map, bulk-group completion) ----------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// global[...] += shared[...] element-wise (fp32 tensor map): the read-modify-write happens in L2
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// wait until all of this thread's bulk groups have completed (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ---- TMEM allocation (one full warp executes these) --------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {
@@ -307,6 +333,9 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+// general form: f32 = 1 for fp32 elements (else bf16); swizzle 0 none, 1 = 128 B, 2 = 64 B
+int make_tensor_map(CUtensorMap* out, const void* base, int f32, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
 int sm_count();
 bool pdl_enabled();  // false when DV_NO_PDL is set

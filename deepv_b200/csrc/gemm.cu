@@ -38,7 +38,12 @@ constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kBarBytes = 256;
 constexpr int kGnBytes = 4 * 8 * 8 * 2 * 4;  // fused GroupNorm partials: [warp][chunk][group][2] floats
-constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kGnBytes + 1024;  // + align slack
+// epilogue staging for TMA stores: 2 column halves x 2 buffers of 128 rows x 64 B (64B-swizzled); the GroupNorm
+// partials of the conv epilogue (which stores directly) live at the start of the same region
+constexpr int kOutBufBytes = 128 * 64;
+constexpr int kOutBytes = 4 * kOutBufBytes;
+static_assert(kGnBytes <= kOutBytes, "GroupNorm partials share the staging region");
+constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;  // + align slack
 constexpr uint32_t kTmemCols = 2 * BN;
 constexpr int kMaxSplits = 8;  // portable cluster size
 
@@ -47,6 +52,8 @@ struct Problem {
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmBh;  // CTA-pair mode: same matrix, 128-row box (each CTA loads half of N)
   alignas(64) CUtensorMap tmAp[3];  // strided conv: the other input parities (tmA = parity 0), see setup_problem
+  alignas(64) CUtensorMap tmOut;    // tma_out: the output as (N, M, batch), box 64 B x 128 rows, 64B swizzle
+  int tma_out;                      // epilogue stages tiles in shared memory and stores / reduce-adds them with TMA
   GemmDesc d;
   int m_tiles, n_tiles, k_blocks, tiles;
   int kb_per_split;      // split-K over a cluster of `splits` CTAs
@@ -245,6 +252,31 @@ struct EpiW {
   static constexpr int value = (MODE == EPI_QKV) ? 64 : 32;
 };
 
+// one head (64 columns) of the fused q|k|v projection of row m: bias, per-head RMSNorm (q, k), temporal RoPE on
+// adjacent pairs (mmdit.py:282-307,131-136); v stays as it is
+__device__ __forceinline__ void qkv_head(const GemmDesc& d, int m, int n, float (&v)[64]) {
+  add_bias<64>(d.bias, n, v);
+  const int region = n / d.heads_dim;  // 0 q, 1 k, 2 v
+  if (region < 2) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
+    const float rs = rsqrtf(ss * (1.0f / 64.0f) + 1e-5f);  // RMSNorm eps, mmdit.py:195,453-454
+    const float2* w2 = reinterpret_cast<const float2*>(d.qk_norm_w + region * 64);
+    const int fid = __ldg(d.frame_id + m);
+    const float2* cs = reinterpret_cast<const float2*>(d.rope_cs) + fid * 32;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float2 w = __ldg(w2 + i);
+      const float x0 = v[2 * i] * rs * w.x;
+      const float x1 = v[2 * i + 1] * rs * w.y;
+      const float2 t = __ldg(cs + i);  // (cos, sin) of frame * 10000^(-2i/64)
+      v[2 * i] = t.x * x0 - t.y * x1;
+      v[2 * i + 1] = t.y * x0 + t.x * x1;
+    }
+  }
+}
+
 // v = W accumulator columns [n, n + W) of output row `r`; n < d.N and r.ok hold.
 // `uniform`: every lane of the warp handles the same column chunk n of rows of ONE tile (true on the
 // TMEM path; false in the split-K reduction, where lanes may sit on different chunks).
@@ -309,27 +341,7 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
     for (int i = 0; i < W / 4; ++i)
       o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   } else if constexpr (MODE == EPI_QKV) {
-    // one head (64 columns): bias, per-head RMSNorm (q, k), temporal RoPE on adjacent pairs
-    add_bias<W>(d.bias, n, v);
-    const int region = n / d.heads_dim;  // 0 q, 1 k, 2 v
-    if (region < 2) {
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) ss += v[i] * v[i];
-      const float rs = rsqrtf(ss * (1.0f / 64.0f) + 1e-5f);  // RMSNorm eps, mmdit.py:195,453-454
-      const float2* w2 = reinterpret_cast<const float2*>(d.qk_norm_w + region * 64);
-      const int fid = __ldg(d.frame_id + r.m);
-      const float2* cs = reinterpret_cast<const float2*>(d.rope_cs) + fid * 32;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float2 w = __ldg(w2 + i);
-        const float x0 = v[2 * i] * rs * w.x;
-        const float x1 = v[2 * i + 1] * rs * w.y;
-        const float2 t = __ldg(cs + i);  // (cos, sin) of frame * 10000^(-2i/64)
-        v[2 * i] = t.x * x0 - t.y * x1;
-        v[2 * i + 1] = t.y * x0 + t.x * x1;
-      }
-    }
+    qkv_head(d, r.m, n, v);
     void* base = d.out;
     if (d.peer_cols > 0) base = d.out_peer[(n % d.heads_dim) / d.peer_cols];  // the rank that owns this head
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(base) +
@@ -474,6 +486,131 @@ __device__ __forceinline__ void epilogue_from_tmem(const Problem& a, const TileC
   }
 }
 
+template <int MODE>
+struct EpiTma {
+  static constexpr bool value = MODE == EPI_BF16 || MODE == EPI_GELU || MODE == EPI_QKV || MODE == EPI_RESID_GATE;
+};
+
+// Epilogue through shared memory and TMA (dense problems, no split-K): the TMEM layout gives every thread one output
+// ROW, so direct stores touch 32 different rows per instruction (half-used sectors, and a read-modify-write of the fp32
+// stream for the gated residual).  Here the 128 threads of a column half write their rows into a 64B-swizzled
+// 128 x 64 B staging buffer (conflict-free 16-byte stores) and one thread hands it to TMA: full-line writes for bf16
+// outputs, `cp.reduce.async.bulk ... add` for the gated residual (x += gate * (acc + bias) happens in L2, x is never
+// read by the SM).  Two buffers per half = the two 64-byte column groups of one step; rows / columns beyond the
+// problem are clipped by the tensor map.  `issuer`: the one thread per column half that owns the bulk groups.
+template <int MODE>
+__device__ __forceinline__ void epilogue_tma(const Problem& a, const TileCoord& tc, uint32_t tmem_acc,
+                                             int row_in_tile, int quarter, int half, uint8_t* out_stage, bool issuer) {
+  const GemmDesc& d = a.d;
+  const int nbase = tc.n_tile * BN + half * 128;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
+  const uint32_t bar = 2 + half;
+  uint8_t* buf0 = out_stage + half * (2 * kOutBufBytes);
+  uint8_t* buf1 = buf0 + kOutBufBytes;
+  const uint32_t sw = (row_in_tile >> 1) & 3;  // 64B swizzle: 16-byte chunk index ^= bits [7,9) of the byte address
+  uint4* row0 = reinterpret_cast<uint4*>(buf0 + row_in_tile * 64);
+  uint4* row1 = reinterpret_cast<uint4*>(buf1 + row_in_tile * 64);
+  const int m0 = tc.m_tile * BM;
+  const bool live = m0 < d.M;  // CTA pairs: the odd last m-tile does not exist
+  if constexpr (MODE == EPI_RESID_GATE) {
+    uint32_t buf[2][32];
+    tmem_ld_32x32(taddr, buf[0]);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int n = nbase + it * 32;
+      tmem_ld_wait();
+      if (it + 1 < 4) tmem_ld_32x32(taddr + (it + 1) * 32, buf[(it + 1) & 1]);
+      if (n < d.N) {  // uniform over the column half
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(buf[it & 1][i]);
+        add_bias<32>(d.bias, n, v);
+        const float4* g4 = reinterpret_cast<const float4*>(d.gate + tc.b * d.gate_batch_stride + n);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 g = __ldg(g4 + i);
+          v[4 * i + 0] *= g.x;
+          v[4 * i + 1] *= g.y;
+          v[4 * i + 2] *= g.z;
+          v[4 * i + 3] *= g.w;
+        }
+        if (issuer) bulk_wait_read<0>();  // both buffers have been read by their previous stores
+        named_bar_sync(bar, 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          row0[c ^ sw] = make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                                    __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+          row1[c ^ sw] = make_uint4(__float_as_uint(v[16 + 4 * c]), __float_as_uint(v[16 + 4 * c + 1]),
+                                    __float_as_uint(v[16 + 4 * c + 2]), __float_as_uint(v[16 + 4 * c + 3]));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar, 128);
+        if (issuer && live) {
+          tma_reduce_add_3d(&a.tmOut, buf0, n, m0, tc.b);
+          tma_reduce_add_3d(&a.tmOut, buf1, n + 16, m0, tc.b);
+          bulk_commit();
+        }
+      }
+    }
+    tmem_ld_wait();
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      const int n = nbase + it * 64;
+      if (n >= d.N) break;  // uniform over the column half
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(taddr + it * 64, r0);
+      tmem_ld_32x32(taddr + it * 64 + 32, r1);
+      tmem_ld_wait();
+      float v[64];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r0[i]);
+        v[32 + i] = __uint_as_float(r1[i]);
+      }
+      const bool second = n + 32 < d.N;
+      if constexpr (MODE == EPI_QKV) {
+        const int m = m0 + row_in_tile;
+        qkv_head(d, m < d.M ? m : 0, n, v);  // rows beyond M are clipped by the store; keep their table reads in range
+      } else {
+        if (d.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(d.bias + n);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < 8 || second) {
+              const float4 t = __ldg(bp + i);
+              v[4 * i + 0] += t.x;
+              v[4 * i + 1] += t.y;
+              v[4 * i + 2] += t.z;
+              v[4 * i + 3] += t.w;
+            }
+          }
+        }
+        if constexpr (MODE == EPI_GELU) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
+        }
+      }
+      if (issuer) bulk_wait_read<0>();
+      named_bar_sync(bar, 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        row0[c ^ sw] = make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                                  pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+        row1[c ^ sw] = make_uint4(pack_bf16x2(v[32 + 8 * c], v[32 + 8 * c + 1]), pack_bf16x2(v[32 + 8 * c + 2], v[32 + 8 * c + 3]),
+                                  pack_bf16x2(v[32 + 8 * c + 4], v[32 + 8 * c + 5]), pack_bf16x2(v[32 + 8 * c + 6], v[32 + 8 * c + 7]));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(bar, 128);
+      if (issuer && live) {
+        tma_store_3d(&a.tmOut, buf0, n, m0, tc.b);
+        if (second) tma_store_3d(&a.tmOut, buf1, n + 32, m0, tc.b);
+        bulk_commit();
+      }
+    }
+  }
+}
+
 // Swapped-operand conv tile (Cout <= 128): TMEM lane = output channel, column = pixel of the
 // 16x16 tile (w fastest).  One thread owns one channel; for every pixel the warp writes a
 // contiguous run of 32 channels (64 B) into the NDHWC output.  Plain store mode only.
@@ -548,7 +685,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   // 128B swizzle needs 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* out_stage = smem + kStages * kStageBytes;  // TMA-store staging (1024-byte aligned) / GroupNorm partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kOutBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -561,9 +699,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&k.p[0].tmA);
     tma_prefetch_desc(&k.p[0].tmB);
+    if (k.p[0].tma_out) tma_prefetch_desc(&k.p[0].tmOut);
     if (k.p[1].tiles > 0) {
       tma_prefetch_desc(&k.p[1].tmA);
       tma_prefetch_desc(&k.p[1].tmB);
+      if (k.p[1].tma_out) tma_prefetch_desc(&k.p[1].tmOut);
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -718,14 +858,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const TileCoord tc = decode_tile(a, tile, 0);
         mbar_wait(&tmem_full[as], aph);
         tc_fence_after();
-        if (MODE == EPI_CONV && a.swap)
+        if (MODE == EPI_CONV && a.swap) {
           epilogue_tile_swapped(a, tc, tmem_base + as * BN, quarter, lane, half);
-        else
+        } else if (EpiTma<MODE>::value && a.tma_out) {
+          if constexpr (EpiTma<MODE>::value)
+            epilogue_tma<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half, out_stage,
+                               quarter == 0 && lane == 0);
+        } else {
           epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half,
-                                   reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarBytes));
+                                   reinterpret_cast<float*>(out_stage));
+        }
         tc_fence_before();
         mbar_arrive(&tmem_empty[as]);
       }
+      if (EpiTma<MODE>::value && quarter == 0 && lane == 0) bulk_wait_all();  // my TMA stores have landed
     } else {
       // park the fp32 partial tile in this CTA's smem as [col4][row] float4 (the operand ring is
       // idle: every MMA that read it has retired once tmem_full fires)
@@ -817,7 +963,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 // ------------------------------------------------------------------------------
 constexpr int kPairStages = 6;
 constexpr int kPairStageBytes = kABytes + kBBytes / 2;  // 32 KB
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kBarBytes + kGnBytes + 1024;
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kOutBytes + kBarBytes + 1024;
 
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst,
                                                  int c0, int c1) {
@@ -908,7 +1054,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint8_t* out_stage = smem + kPairStages * kPairStageBytes;  // TMA-store staging / GroupNorm partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kOutBytes);
   uint64_t* full_bar = bars;                      // leader's are used (both CTAs' TMA signal them)
   uint64_t* empty_bar = bars + kPairStages;       // local, arrived by the leader's multicast commit
   uint64_t* tmem_full = bars + 2 * kPairStages;   // local, multicast commit
@@ -923,9 +1070,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&k.p[0].tmA);
     tma_prefetch_desc(&k.p[0].tmBh);
+    if (k.p[0].tma_out) tma_prefetch_desc(&k.p[0].tmOut);
     if (k.p[1].tiles > 0) {
       tma_prefetch_desc(&k.p[1].tmA);
       tma_prefetch_desc(&k.p[1].tmBh);
+      if (k.p[1].tma_out) tma_prefetch_desc(&k.p[1].tmOut);
     }
     for (int i = 0; i < kPairStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -1044,12 +1193,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
       const TileCoord tc = decode_pair_tile(a, tile, rank);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
-      epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half,
-                               reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + kBarBytes));
+      if (EpiTma<MODE>::value && a.tma_out) {
+        if constexpr (EpiTma<MODE>::value)
+          epilogue_tma<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half, out_stage,
+                             quarter == 0 && lane == 0);
+      } else {
+        epilogue_from_tmem<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half,
+                                 reinterpret_cast<float*>(out_stage));
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(&tmem_empty[as]), 0));
     }
+    if (EpiTma<MODE>::value && quarter == 0 && lane == 0) bulk_wait_all();  // my TMA stores have landed
   }
 
   pdl_trigger();
@@ -1240,6 +1396,26 @@ static int setup_problem(const GemmDesc& d, Problem& pr) {
   }
   pr.m_pairs = (pr.m_tiles + 1) / 2;
   pr.pair_tiles = pr.m_pairs * d.batch * pr.n_tiles;
+
+  // TMA-store epilogue (dense bf16 outputs and the gated fp32 residual; not with peer stores or a bf16 residual)
+  pr.tma_out = 0;
+  static const bool no_tma_store = getenv("DV_GEMM_NO_TMA_STORE") != nullptr;
+  const bool mode_ok = d.mode == EPI_BF16 || d.mode == EPI_GELU || d.mode == EPI_QKV || d.mode == EPI_RESID_GATE;
+  if (!no_tma_store && d.a_mode == 0 && mode_ok && d.residual == nullptr && d.peer_cols == 0) {
+    const uint64_t esz = d.mode == EPI_RESID_GATE ? 4 : 2;
+    const uint64_t row_bytes = static_cast<uint64_t>(d.ldo) * esz;
+    const uint64_t batch_bytes = d.batch == 1 ? row_bytes * static_cast<uint64_t>(d.M)
+                                              : static_cast<uint64_t>(d.out_batch_stride) * esz;
+    const char* base = reinterpret_cast<const char*>(d.out) + static_cast<uint64_t>(d.out_row_offset) * row_bytes;
+    if (row_bytes % 16 == 0 && batch_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+      uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)d.M, (uint64_t)d.batch};
+      uint64_t strides[2] = {row_bytes, batch_bytes};
+      uint32_t box[3] = {static_cast<uint32_t>(64 / esz), 128, 1};
+      int rc = make_tensor_map(&pr.tmOut, base, esz == 4 ? 1 : 0, 3, dims, strides, box, 2);
+      if (rc) return rc;
+      pr.tma_out = 1;
+    }
+  }
   return 0;
 }
 
@@ -1250,8 +1426,12 @@ static double plan_splits(long long tiles, int k_blocks, bool allow_split, int* 
   const int nsm = sm_count();
   double best = 1e30;
   int splits = 1;
+  static const bool split_large = getenv("DV_GEMM_SPLIT_LARGE") != nullptr;  // round-1 behaviour (A/B switch)
   for (int s = 1; s <= kMaxSplits; s *= 2) {
     if (s > 1 && (!allow_split || k_blocks / s < 2)) break;
+    // split-K CTAs run one pass each (no overlap of their reduction + epilogue with the next mainloop), which the
+    // model below does not see: with at least one tile per SM the persistent kernel / CTA pairs are used instead
+    if (s > 1 && tiles >= nsm && !split_large) break;
     const int usable = s == 1 ? nsm : cluster_capacity(s);
     if (usable <= 0) break;
     const long long ctas = tiles * s;

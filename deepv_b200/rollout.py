@@ -191,10 +191,34 @@ class B200Rollout:
         return out
 
     def _encode(self, x: torch.Tensor, noise) -> torch.Tensor:
-        dist = self.pipe.vae.encode(x).latent_dist
-        shape = list(dist.parameters.shape)
-        shape[1] //= 2
-        return dist.sample_with_noise(noise.randn(shape).to(self.device, torch.float32))
+        return self._encode_many([x], noise, None)[0]
+
+    def _encode_many(self, xs, noise, shard=None) -> List[torch.Tensor]:
+        """`vae.encode(x).latent_dist.sample()` for each clip of `xs` (pipeline.py:569,574 / :250-251), the normal
+        draws taken in that order.  Under a shard the clips (image, disparity) are dealt over the ranks of the
+        rollout group — each is encoded once and its latent broadcast — while EVERY rank takes every draw, so the
+        replicated generators stay in step."""
+        vae = self.pipe.vae
+        zc = vae.config["encoder_out_channels"]
+        shapes = [(x.shape[0], zc, (x.shape[2] - 1) // 8 + 1, x.shape[3] // 8, x.shape[4] // 8) for x in xs]
+        draws = [noise.randn(list(s)).to(self.device, torch.float32) for s in shapes]
+        split = shard is not None and shard.active and len(xs) > 1
+
+        def enc(i):
+            return vae.encode(xs[i]).latent_dist.sample_with_noise(draws[i])
+
+        if not split:
+            return [enc(i) for i in range(len(xs))]
+        import torch.distributed as dist
+        outs, works = [], []
+        for i in range(len(xs)):
+            owner = i % shard.world
+            z = enc(i).contiguous() if shard.rank == owner else torch.empty(shapes[i], device=self.device, dtype=self.dtype)
+            outs.append(z)
+            works.append(dist.broadcast(z, src=shard._global(owner), group=shard.group, async_op=True))
+        for w in works:
+            w.wait()
+        return outs
 
     @staticmethod
     def _normalise(z: torch.Tensor, first_only: bool = False) -> torch.Tensor:
@@ -232,11 +256,12 @@ class B200Rollout:
         lat_noise = pipe.noise_pyramid_base(lat_noise)                                                    # :554-557
         num_units = lat_noise.shape[2] // fpu
 
-        z_img = self._normalise(self._encode(input_image.to(self.dtype), noise))                          # :569-571
         if first:
+            z_img = self._normalise(self._encode(input_image.to(self.dtype), noise))                      # :569-571
             z_disp = torch.zeros_like(z_img)
         else:
-            z_disp = self._normalise(self._encode(input_disparity.to(self.dtype), noise))                 # :574-576
+            zi, zd = self._encode_many([input_image.to(self.dtype), input_disparity.to(self.dtype)], noise, shard)
+            z_img, z_disp = self._normalise(zi), self._normalise(zd)                                      # :569-576
         z_ray = torch.zeros_like(z_img[:, :ray, :1]) if input_raymap is None else input_raymap.to(z_img)
         generated = [torch.cat([z_img, z_disp, z_ray], dim=1).to(self.dtype)]                             # :578-582
 
@@ -275,9 +300,10 @@ class B200Rollout:
         return image, disparity, trans3d, trans2d
 
     # -- pipeline.py:243-262 ------------------------------------------------------------------------
-    def history_latent(self, rgb, disparity, raymap_normalised, noise) -> torch.Tensor:
-        video = self._normalise(self._encode(rgb.to(self.dtype), noise), first_only=True)
-        disp = self._normalise(self._encode(disparity.to(self.dtype), noise), first_only=True)
+    def history_latent(self, rgb, disparity, raymap_normalised, noise, shard=None) -> torch.Tensor:
+        zv, zd = self._encode_many([rgb.to(self.dtype), disparity.to(self.dtype)], noise, shard)
+        video = self._normalise(zv, first_only=True)
+        disp = self._normalise(zd, first_only=True)
         return torch.cat([video, disp, raymap_normalised.to(video)], dim=1)
 
     # -- pipeline.py:264-424 ------------------------------------------------------------------------
@@ -317,7 +343,7 @@ class B200Rollout:
             if ev:
                 ev[1].record()
             disp = state.absorb(it, image, disparity, t3, t2, motion)
-            frames, in_disp, in_ray, in_hist = state.next_inputs(image, disp, noise)
+            frames, in_disp, in_ray, in_hist = state.next_inputs(image, disp, noise, shard)
             if ev:
                 ev[2].record()
                 events.append(ev)
@@ -378,7 +404,7 @@ class _Feedback:
             self.trans2d.append(trans2d[:, NUM_INPUT_UNIT:])
         return disp
 
-    def next_inputs(self, images, disp, noise):
+    def next_inputs(self, images, disp, noise, shard=None):
         ro = self.ro
         T, H, W = images.shape[2], images.shape[3], images.shape[4]
         t0 = T - NUM_INPUT_IMAGE
@@ -413,5 +439,5 @@ class _Feedback:
         h3 = t3.index_select(1, k).clone()
         h3[:, :, :3, 3] = _signed_sqrt(h3[:, :, :3, 3] / scale)                              # :403-404
         h_ray = ro.camera_raymap(t2.index_select(1, k), h3, H, W)                            # :406-410 (+ :258-259)
-        history = ro.history_latent(h_img, h_disp, h_ray, noise)
+        history = ro.history_latent(h_img, h_disp, h_ray, noise, shard)
         return frames, in_disp, in_ray, history
