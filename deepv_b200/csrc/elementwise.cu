@@ -88,8 +88,14 @@ template <int NB>
 __global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(
     const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
     const float* __restrict__ in, int in_stride, float* __restrict__ out, int out_stride, int N,
-    int K, int silu_in, int accumulate, int row_blocks) {
+    int K, int silu_in, int accumulate, int row_blocks, const int* __restrict__ need) {
   extern __shared__ float s_in[];  // [NB][K]
+  if (need != nullptr) {  // conditioning cache: every batch row was found, nothing to compute (uniform over the grid)
+    int any = 0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) any |= need[b];
+    if (!any) return;
+  }
   for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
     const int b = i / K, k = i - b * K;
     float v = in[b * in_stride + k];
@@ -400,6 +406,97 @@ __global__ void sp_x_unpack_kernel(const float4* __restrict__ stage, float4* __r
   x[(static_cast<long long>(b) * Lv + i * Lw + l) * dv + c] = stage[idx];
 }
 
+// ---- conditioning cache (adaLN modulation table memoised per (timestep, pooled embedding)) -----------------
+// One CTA walks the B rows in order.  Row b's key = (t[b], pooled[b][:]) bit for bit; slot = hash % slots (direct
+// mapped).  hit: the slot holds exactly this key and was NOT installed during this call (its table would not be
+// there yet: rows 1 and 2 of a 3-branch CFG batch carry the same key).  miss: the key is installed; `store[b]`
+// says whether row b is the last row of this call that maps to its slot (it then owns the slot's table).
+__global__ void __launch_bounds__(256) cond_lookup_kernel(const float* __restrict__ t, const float* __restrict__ pooled,
+                                                          int pooled_dim, int B, float* __restrict__ keys,
+                                                          int* __restrict__ valid, int slots, int* __restrict__ slot_of,
+                                                          int* __restrict__ need, int* __restrict__ store) {
+  __shared__ unsigned long long red[8];
+  __shared__ int s_slot[4], s_need[4], s_flag;
+  const int klen = pooled_dim + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = 0; b < B; ++b) {
+    unsigned long long h = 0;
+    for (int i = threadIdx.x; i < klen; i += blockDim.x) {
+      const unsigned v = __float_as_uint(i == 0 ? t[b] : pooled[static_cast<long long>(b) * pooled_dim + i - 1]);
+      h += (static_cast<unsigned long long>(v) + 0x9E3779B97F4A7C15ull) * (2ull * i + 0x100000001B3ull);
+    }
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (lane == 0) red[warp] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      tot ^= tot >> 29;
+      s_slot[b] = static_cast<int>(tot % static_cast<unsigned long long>(slots));
+      s_flag = 1;
+    }
+    __syncthreads();
+    const int sl = s_slot[b];
+    float* key = keys + static_cast<long long>(sl) * klen;
+    bool installed_now = false;
+    for (int j = 0; j < b; ++j) installed_now |= (s_slot[j] == sl && s_need[j]);
+    int same = valid[sl] != 0;
+    if (same) {
+      for (int i = threadIdx.x; i < klen; i += blockDim.x) {
+        const unsigned v = __float_as_uint(i == 0 ? t[b] : pooled[static_cast<long long>(b) * pooled_dim + i - 1]);
+        if (v != __float_as_uint(key[i])) same = 0;
+      }
+    }
+    if (!same) s_flag = 0;   // benign race: every writer writes 0
+    __syncthreads();
+    const bool hit = s_flag != 0 && !installed_now;
+    if (!hit && !(s_flag != 0 && installed_now)) {   // a different key: install this one
+      for (int i = threadIdx.x; i < klen; i += blockDim.x)
+        key[i] = i == 0 ? t[b] : pooled[static_cast<long long>(b) * pooled_dim + i - 1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_need[b] = hit ? 0 : 1;
+      if (!hit) valid[sl] = 1;
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int st[4];
+    for (int b = 0; b < B; ++b) {
+      int last = 1;
+      for (int j = b + 1; j < B; ++j) last &= !(s_slot[j] == s_slot[b] && s_need[j]);
+      st[b] = s_need[b] && last;
+    }
+    // a found row whose slot is re-keyed by another row of this call must not read the slot while it is rewritten
+    for (int b = 0; b < B; ++b) {
+      if (s_need[b]) continue;
+      for (int j = 0; j < B; ++j)
+        if (j != b && s_slot[j] == s_slot[b] && st[j]) s_need[b] = 1;
+    }
+    for (int b = 0; b < B; ++b) {
+      slot_of[b] = s_slot[b];
+      need[b] = s_need[b];
+      store[b] = st[b];
+    }
+  }
+}
+// hit rows: cache -> plan table; owning miss rows: plan table -> cache
+__global__ void cond_finish_kernel(float4* __restrict__ mod, long long row4, float4* __restrict__ cache,
+                                   const int* __restrict__ slot_of, const int* __restrict__ need,
+                                   const int* __restrict__ store) {
+  const int b = blockIdx.y;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= row4) return;
+  float4* m = mod + b * row4 + i;
+  float4* c = cache + slot_of[b] * row4 + i;
+  if (!need[b])
+    *m = *c;
+  else if (store[b])
+    *c = *m;
+}
+
 // ---- sequence parallelism over peer memory: barrier and all-gather without NCCL ---------------------------
 struct SpPeers {
   void* p[8];
@@ -450,6 +547,27 @@ __global__ void sp_x_share_kernel(SpPeers xs, int B, int Lv, int D, int row0, in
 }
 
 }  // namespace
+
+int launch_cond_lookup(const float* t, const float* pooled, int pooled_dim, int B, float* keys, int* valid, int slots,
+                       int* slot_of, int* need, int* store, cudaStream_t stream) {
+  DV_REQUIRE(B >= 1 && B <= 4 && slots > 0, "cond_lookup: B=%d slots=%d", B, slots);
+  cond_lookup_kernel<<<1, 256, 0, stream>>>(t, pooled, pooled_dim, B, keys, valid, slots, slot_of, need, store);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+int launch_cond_finish(float* mod, long long row_floats, float* cache, const int* slot_of, const int* need,
+                       const int* store, int B, cudaStream_t stream) {
+  DV_REQUIRE(row_floats % 4 == 0, "cond_finish: row length %lld", row_floats);
+  const long long row4 = row_floats / 4;
+  ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(B) * row_floats * 8.0, stream, "cond_cache_copy");
+  cond_finish_kernel<<<dim3(static_cast<unsigned>((row4 + 255) / 256), B), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(mod), row4, reinterpret_cast<float4*>(cache), slot_of, need, store);
+  DV_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return 0;
+}
 
 int launch_sp_barrier(void* const* flag_peers, int* epoch, int rank, int P, cudaStream_t stream) {
   DV_REQUIRE(flag_peers && epoch && P >= 2 && P <= 8 && rank >= 0 && rank < P, "sp_barrier: bad argument");
@@ -519,7 +637,7 @@ int launch_ln_modulate(const float* x, long long x_bs, __nv_bfloat16* out, long 
 
 int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int in_stride,
                 float* out, int out_stride, int B, int N, int K, int silu_in, int accumulate,
-                cudaStream_t stream) {
+                cudaStream_t stream, const int* need) {
   DV_REQUIRE(B >= 1 && B <= 4, "gemv: batch %d not in [1,4]", B);
   DV_REQUIRE(K % 8 == 0, "gemv: K=%d must be a multiple of 8", K);
   const int rows_per_cta = kGemvWarps * kGemvRowsPerWarp;
@@ -539,7 +657,7 @@ int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int 
     const int blocks = row_blocks < resident ? row_blocks : resident;                            \
     gemv_kernel<NB><<<blocks, kGemvWarps * 32, smem, stream>>>(W, bias, in, in_stride, out,      \
                                                                out_stride, N, K, silu_in,        \
-                                                               accumulate, row_blocks);          \
+                                                               accumulate, row_blocks, need);    \
   } while (0)
   DV_REQUIRE(smem <= 96 * 1024, "gemv: B*K too large for smem staging");
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(N) * K * 2.0, stream, N > 100000 ? "gemv_adaln" : "gemv");

@@ -31,9 +31,17 @@ int launch_ln_modulate(const float* x, long long x_batch_stride, __nv_bfloat16* 
                        int mod_batch_stride, int B, int L, int D, float eps, cudaStream_t stream);
 
 // out[b][n] (+)= act_out( W[n][:] . act_in(in[b][:]) + bias[n] ),  W bf16 [N][K], B <= 4
+// need (optional, device int[B]): the launch does nothing when every entry is 0 (conditioning cache hit)
 int launch_gemv(const __nv_bfloat16* W, const float* bias, const float* in, int in_stride,
                 float* out, int out_stride, int B, int N, int K, int silu_in, int accumulate,
-                cudaStream_t stream);
+                cudaStream_t stream, const int* need = nullptr);
+// conditioning cache: the adaLN modulation table is a pure function of (timestep, pooled embedding) per batch row
+// (mmdit.py:747-753,548,495) and a rollout asks for the same 15 timesteps x few prompts over and over.
+// keys [slots][1 + pooled_dim], valid [slots], tables [slots][row_floats]; slot_of / need / store: device int[B]
+int launch_cond_lookup(const float* t, const float* pooled, int pooled_dim, int B, float* keys, int* valid, int slots,
+                       int* slot_of, int* need, int* store, cudaStream_t stream);
+int launch_cond_finish(float* mod, long long row_floats, float* cache, const int* slot_of, const int* need,
+                       const int* store, int B, cudaStream_t stream);
 
 // sinusoidal timestep features, cos first (mmdit.py:645-683 with flip_sin_to_cos, shift 0)
 int launch_timestep_features(const float* t, float* out, int B, cudaStream_t stream);

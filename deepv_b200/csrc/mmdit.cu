@@ -32,6 +32,10 @@ struct dv_mmdit {
   float* pos_base = nullptr;  // [S*S][D]
   float* rope_cs = nullptr;   // [kMaxFrames][32][2]
   int D = 0;
+  // conditioning cache: modulation tables memoised per (timestep, pooled embedding) row (DV_MOD_CACHE_SLOTS, 0 = off)
+  int cc_slots = 0;
+  float *cc_keys = nullptr, *cc_tables = nullptr;
+  int* cc_valid = nullptr;
 };
 
 static constexpr int kMaxFrames = 256;
@@ -55,6 +59,7 @@ struct dv_mmdit_plan {
   float *pos_x = nullptr, *pos_h = nullptr;
   float *x = nullptr, *c = nullptr, *key_bias = nullptr;
   float *tfeat = nullptr, *g1 = nullptr, *g3 = nullptr, *temb = nullptr, *mod = nullptr;
+  int* cc = nullptr;  // conditioning cache verdict of this forward: slot_of[4] | need[4] | store[4]
   __nv_bfloat16 *xn = nullptr, *cn = nullptr, *qkv = nullptr, *attn = nullptr, *ffh = nullptr, *ffh_c = nullptr;
   __nv_bfloat16 *patch_a = nullptr, *hist_a = nullptr, *enc_bf = nullptr, *xo = nullptr;
   // Ulysses sequence parallelism (dv_mmdit_plan_set_sp): this rank owns the video rows
@@ -193,6 +198,23 @@ extern "C" int dv_mmdit_create(const dv_mmdit_config* cfg, const dv_mmdit_weight
     delete m;
     return DV_ERR_CUDA;
   }
+  {
+    // 15 timesteps x (negative + a handful of prompts) of a rollout fit in 96 direct-mapped slots of 1.76 MB
+    const char* env = getenv("DV_MOD_CACHE_SLOTS");
+    m->cc_slots = env ? atoi(env) : 96;
+    if (m->cc_slots > 0) {
+      const size_t klen = static_cast<size_t>(cfg->pooled_dim) + 1;
+      e = cudaMalloc(&m->cc_keys, m->cc_slots * klen * sizeof(float));
+      if (e == cudaSuccess) e = cudaMalloc(&m->cc_tables, static_cast<size_t>(m->cc_slots) * w->mod_rows * sizeof(float));
+      if (e == cudaSuccess) e = cudaMalloc(&m->cc_valid, m->cc_slots * sizeof(int));
+      if (e == cudaSuccess) e = cudaMemset(m->cc_valid, 0, m->cc_slots * sizeof(int));
+      if (e != cudaSuccess) {
+        set_error("dv_mmdit_create: conditioning cache: %s", cudaGetErrorString(e));
+        dv_mmdit_destroy(m);
+        return DV_ERR_CUDA;
+      }
+    }
+  }
   *out = m;
   return DV_OK;
 }
@@ -201,6 +223,9 @@ extern "C" void dv_mmdit_destroy(dv_mmdit* m) {
   if (!m) return;
   cudaFree(m->pos_base);
   cudaFree(m->rope_cs);
+  cudaFree(m->cc_keys);
+  cudaFree(m->cc_tables);
+  cudaFree(m->cc_valid);
   delete m;
 }
 
@@ -283,6 +308,7 @@ extern "C" int dv_mmdit_plan_create(dv_mmdit* m, int batch, int n_clips, const i
   DV_A(p->g3, B * D);
   DV_A(p->temb, B * D);
   DV_A(p->mod, static_cast<long long>(B) * m->w.mod_rows);
+  DV_A(p->cc, 12);
   DV_A(p->xn, static_cast<long long>(B) * Lv * D);
   DV_A(p->cn, static_cast<long long>(B) * Lc * D);
   DV_A(p->qkv, static_cast<long long>(B) * L * 3 * D);
@@ -492,17 +518,26 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
   if ((rc = (call)) != 0) return rc
 
   // ---- conditioning: temb and every adaLN modulation vector -------------------------
+  // all of it is a pure function of (timestep, pooled embedding) per batch row: looked up in the model's cache
+  // first; the GEMVs return at once when every row was found, and found rows are copied from their slots
+  const int* need = nullptr;
+  if (m->cc_slots > 0 && MR % 4 == 0) {
+    DV_RUN(launch_cond_lookup(timestep_dev, pooled_dev, m->cfg.pooled_dim, B, m->cc_keys, m->cc_valid, m->cc_slots,
+                              p->cc, p->cc + 4, p->cc + 8, st));
+    need = p->cc + 4;
+  }
   DV_RUN(launch_timestep_features(timestep_dev, p->tfeat, B, st));
   DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_t1), w.b_t1, p->tfeat, 256, p->g1, D,
-                     B, D, 256, 0, 0, st));
+                     B, D, 256, 0, 0, st, need));
   DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_t2), w.b_t2, p->g1, D, p->temb, D, B,
-                     D, D, 1, 0, st));
+                     D, D, 1, 0, st, need));
   DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_p1), w.b_p1, pooled_dev,
-                     m->cfg.pooled_dim, p->g3, D, B, D, m->cfg.pooled_dim, 0, 0, st));
+                     m->cfg.pooled_dim, p->g3, D, B, D, m->cfg.pooled_dim, 0, 0, st, need));
   DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_p2), w.b_p2, p->g3, D, p->temb, D, B,
-                     D, D, 1, 1, st));
+                     D, D, 1, 1, st, need));
   DV_RUN(launch_gemv(reinterpret_cast<const __nv_bfloat16*>(w.w_mod), w.b_mod, p->temb, D, p->mod, MR,
-                     B, MR, D, 1, 0, st));
+                     B, MR, D, 1, 0, st, need));
+  if (need != nullptr) DV_RUN(launch_cond_finish(p->mod, MR, m->cc_tables, p->cc, p->cc + 4, p->cc + 8, B, st));
 
   // ---- context stream: [history tokens | text tokens] ---------------------------------
   DV_RUN(launch_to_bf16(enc_dev, enc_dtype == DV_DTYPE_BF16, p->enc_bf,

@@ -213,3 +213,72 @@ def test_mmdit_full_depth_large_layouts(dit24, name):
         err = rel_max(y, ref)
         print(f"24 blocks {name} ({dtype}): max|a-b|/max|ref| = {err:.3e} (ref absmax {ref.abs().max().item():.3f})")
         assert err <= DENOISER_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# A whole first iteration at the DEMO SHAPE with the REAL-SIZE models (BASELINE.json north_star: "decoded frames within
+# a stated PSNR floor over a full rollout"): generate_i2v = VAE encode of the input frame, 8
+# autoregressive units x 3 stages x 5 steps = 120 full-depth forwards with CFG, ray map -> poses, two 57-frame tiled
+# decodes, at 384x512 — against the oracle's generate_i2v (oracle/rollout_ref.py, pinned to the real reference's
+# generate() on CPU) run in fp32 on CUDA on the same noise tape.
+FULL_ROLLOUT_PSNR_FLOOR_DB = {torch.float32: 40.0, torch.bfloat16: 30.0}   # fp32 latents / the bench's bf16 latents
+FULL_ROLLOUT_LATENT_TOL = {torch.float32: 3e-2, torch.bfloat16: 1e-1}
+
+
+class _CudaTape:
+    """The seeded CPU tape of tests/golden/rollout_cases.py, handing its draws out on the device."""
+
+    def __init__(self, tape):
+        self.tape = tape
+
+    def randn(self, shape):
+        return self.tape.randn(shape).cuda()
+
+    def block(self, *a):
+        return self.tape.block(*a).cuda()
+
+
+def test_full_size_first_iteration_vs_cuda_fp32_oracle(dit24, vae_prod):
+    from deepv_b200.pipeline import B200Pipeline
+    from deepv_b200.rollout import B200Rollout, PromptCache
+    from deepv_b200.scheduler import B200Scheduler
+    from oracle import rollout_ref, scheduler_ref
+    from tests.golden import rollout_cases as rc
+    cfg, Wc, model = dit24
+    vcfg, VWc, _, _ = vae_prod
+    case = dict(rc.ROLLOUT, height=384, width=512, seed=91)
+    model_cfg = dict(case["model_cfg"], num_inference_steps=5)
+    embeds = rc.text_embeds(case)
+    embeds_c = {k: {n: t.cuda() for n, t in e.items()} for k, e in embeds.items()}
+    m = rollout_ref.RolloutModels(cfg, Wc, vcfg, VWc, scheduler_ref.pyramid_tables(**cases.SCHEDULER_KW), embeds_c, model_cfg)
+    m._pos = m.pos_table().cuda()
+    motion = ["w", "a", "w", "d", "w", "s", "a", "w"]
+    frame = rc.first_frame(case)
+    tape = rc.RecordingTape(case["seed"] + 3)
+    with exact_fp32():
+        o_img, o_disp, o_t3, o_t2, o_lat = rollout_ref.generate_i2v(m, motion, frame.unsqueeze(0).cuda(), None, None, None,
+                                                                    _CudaTape(tape), [5, 5, 5])
+    assert o_img.shape == (1, 3, 57, 384, 512)
+    from deepv_b200.vae import B200VAE
+    W_cpu = {k: v.cpu() for k, v in VWc.items()}
+    for dtype in (torch.float32, torch.bfloat16):
+        vae = B200VAE(W_cpu, vcfg, dtype=dtype)
+        vae.enable_tiling()
+        model.out_dtype = dtype
+        pipe = B200Pipeline(model, vae, B200Scheduler(**cases.SCHEDULER_KW), model_cfg=model_cfg, torch_dtype=dtype)
+        ro = B200Rollout(pipe, PromptCache(embeds))
+        replay = rc.ReplayTape(tape.draws, tape.calls, 0)
+        image, disparity, t3, t2, lat = ro.generate_i2v(motion, True, ro.frames_from_uint8(frame.unsqueeze(0)), None, None, None,
+                                                        temp=8, num_inference_steps=5, noise=replay, return_latents=True)
+        torch.cuda.synchronize()
+        assert image.shape == o_img.shape and torch.isfinite(image).all() and torch.isfinite(disparity).all()
+        per_unit = [rel_max(lat[:, :, u], o_lat[:, :, u]) for u in range(lat.shape[2])]
+        p_img, p_disp = psnr(image, o_img), psnr(disparity, o_disp)
+        worst = min(psnr(image[:, :, t], o_img[:, :, t]) for t in range(57))
+        print(f"full-size iteration ({dtype}): PSNR image {p_img:.1f} dB (worst frame {worst:.1f}), disparity {p_disp:.1f} dB; "
+              f"latent max|a-b|/max|ref| per unit " + " ".join(f"{e:.1e}" for e in per_unit) +
+              f"; trans3d {rel_max(t3, o_t3):.1e}")
+        assert p_img >= FULL_ROLLOUT_PSNR_FLOOR_DB[dtype] and p_disp >= FULL_ROLLOUT_PSNR_FLOOR_DB[dtype]
+        assert max(per_unit) <= FULL_ROLLOUT_LATENT_TOL[dtype]
+        del vae, pipe, ro
+    model.out_dtype = torch.float32

@@ -95,6 +95,40 @@ def test_mmdit_bf16_io_and_padding_invariance(dit2):
     assert rel_max(y1, gold) <= DENOISER_TOL
 
 
+def test_conditioning_cache_hits_are_bit_exact(monkeypatch):
+    """The adaLN modulation tables are memoised per (timestep, pooled embedding) row on the device (csrc/mmdit.cu,
+    cond_lookup / cond_finish): found rows, duplicate rows inside one CFG batch, evictions and a cache-less model
+    must all give bit-identical outputs."""
+    from deepv_b200.mmdit import B200MMDiT
+    cfg, W = weights.mmdit_weights(dict(num_layers=2), seed=1)
+    case = cases.MMDIT_CASES["two_block_b3_hist"]
+    inp = cases.mmdit_inputs(case)
+    inp["pooled"][2] = inp["pooled"][1]            # rows 1 and 2 of a 3-branch CFG batch share prompt and timestep
+    dev = "cuda"
+
+    def run(model, t):
+        y = model(sample=[[c.to(dev) for c in inp["clips"]]], timestep_ratio=torch.full((3,), t, device=dev),
+                  encoder_hidden_states=inp["enc"].to(dev), encoder_attention_mask=inp["mask"].to(dev),
+                  pooled_projections=inp["pooled"].to(dev), history=inp["hist"].to(dev), history_mask=inp["hmask"].to(dev),
+                  history_downsample_ratio=2)[0]
+        torch.cuda.synchronize()
+        return y.clone()
+
+    monkeypatch.setenv("DV_MOD_CACHE_SLOTS", "0")
+    plain = B200MMDiT(W, cfg, out_dtype=torch.float32)
+    monkeypatch.setenv("DV_MOD_CACHE_SLOTS", "5")  # tiny: forces slot conflicts and evictions
+    cached = B200MMDiT(W, cfg, out_dtype=torch.float32)
+    ts = [936.0639953613281, 872.1279907226562, 744.0, 654.5895004272461, 386.0, 289.84625244140625, 97.53875732421875]
+    want = {t: run(plain, t) for t in ts}
+    lib = cached.lib
+    for rnd in range(3):                           # round 0: misses; later rounds: hits and re-computed evictions
+        for t in (ts if rnd != 1 else reversed(ts)):
+            assert torch.equal(run(cached, t), want[t]), (rnd, t)
+    n0 = lib.dv_launch_count()
+    run(cached, ts[0])
+    assert lib.dv_launch_count() > n0              # (the cached forward still issues its launches; they return early)
+
+
 def test_mmdit_full_depth_vs_oracle():
     """24 blocks (the real depth), first-unit stage-1 layout, against the fp32 oracle."""
     from deepv_b200.mmdit import B200MMDiT
