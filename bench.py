@@ -517,6 +517,15 @@ def run_ours(args):
         img_h = first_frame().pin_memory()
         img_d = img_h.to(dev)
         seed_ctr = [0]
+        host_out = {}
+
+        def to_host(name, t):
+            # frames land in pinned host buffers (allocated once): the D2H is a real async DMA inside the timed region
+            buf = host_out.get(name)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = host_out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            return buf
 
         def step(img, fetch, use_shard=True):
             # every rank seeds its device generator identically: latents stay replicated over the rollout group
@@ -525,7 +534,7 @@ def run_ours(args):
             res = ro.generate(dict(img=img, prompt=list(ROLLOUT_PROMPTS), prompt_type="action"), noise=noise,
                               shard=sh if use_shard else None)
             if fetch:
-                return res["pred_img"].to("cpu", non_blocking=True), res["pred_disparity"].to("cpu", non_blocking=True)
+                return to_host("img", res["pred_img"]), to_host("disp", res["pred_disparity"])
             return res["pred_img"], res["pred_disparity"]
 
         def resident():
@@ -558,10 +567,18 @@ def run_ours(args):
             else:
                 img, dsp = pipe.decode_latent(dec[0]), pipe.decode_latent(dec[1])
             if fetch:
-                return img.to("cpu", non_blocking=True), dsp.to("cpu", non_blocking=True)
+                return to_host("img", img), to_host("disp", dsp)
             return img, dsp
 
         res_in = to_dev(unit_h, dec_h)
+        host_out = {}
+
+        def to_host(name, t):
+            buf = host_out.get(name)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = host_out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            return buf
 
         def resident():
             return res_in

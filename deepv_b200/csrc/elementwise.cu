@@ -407,15 +407,17 @@ __global__ void sp_x_unpack_kernel(const float4* __restrict__ stage, float4* __r
 }
 
 // ---- conditioning cache (adaLN modulation table memoised per (timestep, pooled embedding)) -----------------
-// One CTA walks the B rows in order.  Row b's key = (t[b], pooled[b][:]) bit for bit; slot = hash % slots (direct
-// mapped).  hit: the slot holds exactly this key and was NOT installed during this call (its table would not be
+// One CTA walks the B rows in order.  Row b's key = (t[b], pooled[b][:]) bit for bit; its slot is looked for in four
+// probes from hash % slots.  hit: the slot holds exactly this key and was NOT installed during this call (its table would not be
 // there yet: rows 1 and 2 of a 3-branch CFG batch carry the same key).  miss: the key is installed; `store[b]`
 // says whether row b is the last row of this call that maps to its slot (it then owns the slot's table).
+constexpr int kCondProbes = 4;
 __global__ void __launch_bounds__(256) cond_lookup_kernel(const float* __restrict__ t, const float* __restrict__ pooled,
                                                           int pooled_dim, int B, float* __restrict__ keys,
                                                           int* __restrict__ valid, int slots, int* __restrict__ slot_of,
                                                           int* __restrict__ need, int* __restrict__ store) {
   __shared__ unsigned long long red[8];
+  __shared__ unsigned long long s_hash;
   __shared__ int s_slot[4], s_need[4], s_flag;
   const int klen = pooled_dim + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -432,29 +434,44 @@ __global__ void __launch_bounds__(256) cond_lookup_kernel(const float* __restric
       unsigned long long tot = 0;
       for (int w = 0; w < 8; ++w) tot += red[w];
       tot ^= tot >> 29;
-      s_slot[b] = static_cast<int>(tot % static_cast<unsigned long long>(slots));
-      s_flag = 1;
+      s_hash = tot;
     }
     __syncthreads();
-    const int sl = s_slot[b];
-    float* key = keys + static_cast<long long>(sl) * klen;
+    // four probes (linear from hash % slots): the first slot that holds this key, else the first free one, else a
+    // victim picked by other bits of the hash
+    const int base = static_cast<int>(s_hash % static_cast<unsigned long long>(slots));
+    int found = -1, free_slot = -1;
+    for (int pr = 0; pr < kCondProbes && found < 0; ++pr) {
+      const int sl = (base + pr) % slots;
+      if (threadIdx.x == 0) s_flag = 1;
+      __syncthreads();
+      int same = valid[sl] != 0;
+      if (!same && free_slot < 0) free_slot = sl;
+      if (same) {
+        const float* key = keys + static_cast<long long>(sl) * klen;
+        for (int i = threadIdx.x; i < klen; i += blockDim.x) {
+          const unsigned v = __float_as_uint(i == 0 ? t[b] : pooled[static_cast<long long>(b) * pooled_dim + i - 1]);
+          if (v != __float_as_uint(key[i])) same = 0;
+        }
+      }
+      if (!same) s_flag = 0;   // benign race: every writer writes 0
+      __syncthreads();
+      if (s_flag != 0) found = sl;
+      __syncthreads();
+    }
+    const int sl = found >= 0 ? found
+                              : (free_slot >= 0 ? free_slot
+                                                : (base + static_cast<int>((s_hash >> 40) % kCondProbes)) % slots);
     bool installed_now = false;
     for (int j = 0; j < b; ++j) installed_now |= (s_slot[j] == sl && s_need[j]);
-    int same = valid[sl] != 0;
-    if (same) {
-      for (int i = threadIdx.x; i < klen; i += blockDim.x) {
-        const unsigned v = __float_as_uint(i == 0 ? t[b] : pooled[static_cast<long long>(b) * pooled_dim + i - 1]);
-        if (v != __float_as_uint(key[i])) same = 0;
-      }
-    }
-    if (!same) s_flag = 0;   // benign race: every writer writes 0
-    __syncthreads();
-    const bool hit = s_flag != 0 && !installed_now;
-    if (!hit && !(s_flag != 0 && installed_now)) {   // a different key: install this one
+    const bool hit = found >= 0 && !installed_now;
+    if (found < 0) {   // install this key (the table follows after the GEMVs)
+      float* key = keys + static_cast<long long>(sl) * klen;
       for (int i = threadIdx.x; i < klen; i += blockDim.x)
         key[i] = i == 0 ? t[b] : pooled[static_cast<long long>(b) * pooled_dim + i - 1];
     }
     __syncthreads();
+    if (threadIdx.x == 0) s_slot[b] = sl;
     if (threadIdx.x == 0) {
       s_need[b] = hit ? 0 : 1;
       if (!hit) valid[sl] = 1;

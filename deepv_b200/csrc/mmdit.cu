@@ -199,9 +199,9 @@ extern "C" int dv_mmdit_create(const dv_mmdit_config* cfg, const dv_mmdit_weight
     return DV_ERR_CUDA;
   }
   {
-    // 15 timesteps x (negative + a handful of prompts) of a rollout fit in 96 direct-mapped slots of 1.76 MB
+    // 15 timesteps x (negative + a handful of prompts) of a rollout: 128 slots of 1.76 MB, four probes per lookup
     const char* env = getenv("DV_MOD_CACHE_SLOTS");
-    m->cc_slots = env ? atoi(env) : 96;
+    m->cc_slots = env ? atoi(env) : 128;
     if (m->cc_slots > 0) {
       const size_t klen = static_cast<size_t>(cfg->pooled_dim) + 1;
       e = cudaMalloc(&m->cc_keys, m->cc_slots * klen * sizeof(float));

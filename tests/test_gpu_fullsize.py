@@ -221,8 +221,10 @@ def test_mmdit_full_depth_large_layouts(dit24, name):
 # autoregressive units x 3 stages x 5 steps = 120 full-depth forwards with CFG, ray map -> poses, two 57-frame tiled
 # decodes, at 384x512 — against the oracle's generate_i2v (oracle/rollout_ref.py, pinned to the real reference's
 # generate() on CPU) run in fp32 on CUDA on the same noise tape.
-FULL_ROLLOUT_PSNR_FLOOR_DB = {torch.float32: 40.0, torch.bfloat16: 30.0}   # fp32 latents / the bench's bf16 latents
-FULL_ROLLOUT_LATENT_TOL = {torch.float32: 3e-2, torch.bfloat16: 1e-1}
+# measured on B200 (profiles/r02e_pytest_gpu.log): fp32 latents 47.8 dB, per-unit latent error <= 9.1e-3; the bench's
+# bf16 latents (the reference's own GPU configuration, pipeline.py:190,486) 43.0 dB, worst frame 40.0 dB, <= 2.1e-2
+FULL_ROLLOUT_PSNR_FLOOR_DB = {torch.float32: 40.0, torch.bfloat16: 38.0}
+FULL_ROLLOUT_LATENT_TOL = {torch.float32: 2e-2, torch.bfloat16: 3e-2}
 
 
 class _CudaTape:
