@@ -64,6 +64,7 @@ struct AttnArgs {
   __nv_bfloat16* out_peer[8];
   int n_peers, peer_Lc, peer_Lw;
   float scale_log2;               // head_dim^-0.5 * log2(e)
+  int pdl_early;
 };
 
 // 2^x on the FMA pipe: round-to-nearest split x = n + f, degree-3 minimax of 2^f on [-0.5, 0.5]
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const int HD = a.H * kD;
   pdl_wait();  // (kv_end is plan data written long before; everything above overlapped the predecessor)
+  if (a.pdl_early) pdl_trigger();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
   const int HD = a.H * kD;
   pdl_wait();
+  if (a.pdl_early) pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -718,6 +721,7 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   for (int i = 0; i < 8; ++i)
     a.out_peer[i] = (out_peers && i < n_peers) ? reinterpret_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
+  a.pdl_early = pdl_early() ? 1 : 0;
   // double-buffered-S kernel (one CTA per SM, QK^T of tile j+1 issued before PV of tile j) is the default since
   // round 2: all GPU suites pass with it, attention time of a C2 step 16.8 -> 14.6 ms (profiles/r02a_summary.txt);
   // DV_ATTN_PIPE=0 selects the round-1 kernel (two CTAs per SM, S overwritten by P)

@@ -237,6 +237,15 @@ bool pdl_enabled() {
   return on;
 }
 
+// griddepcontrol.launch_dependents right after griddepcontrol.wait (DV_PDL_LATE=1: at the end of the kernel, the
+// round-1 placement).  The trigger only lets the successor's CTAs be SCHEDULED once every CTA of this grid has started;
+// they run their prologue (barrier init, TMEM allocation, descriptor prefetch) on idle / finished SMs and still block in
+// their own griddepcontrol.wait until this grid has completed and flushed.
+bool pdl_early() {
+  static const bool on = getenv("DV_PDL_LATE") == nullptr;
+  return on;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -339,6 +339,7 @@ int make_tensor_map(CUtensorMap* out, const void* base, int f32, int rank, const
 
 int sm_count();
 bool pdl_enabled();  // false when DV_NO_PDL is set
+bool pdl_early();    // launch_dependents right after the kernel's own wait (default) instead of at its end
 
 #if defined(__CUDACC__)
 // Launch with the programmatic-dependent-launch attribute (+ an optional cluster dimension).

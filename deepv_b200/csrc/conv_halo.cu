@@ -39,7 +39,7 @@ constexpr int kHaloSmem = kPixStages * kPixStride + kWStages * kWBytes + kHaloBa
 struct HaloArgs {
   CUtensorMap tmPix, tmW;
   GemmDesc d;
-  int T, H, W, tiles_w, tiles_h, c_blocks, tiles, n_chunks;
+  int T, H, W, tiles_w, tiles_h, c_blocks, tiles, n_chunks, pdl_early;
 };
 
 __device__ __forceinline__ void decode(const HaloArgs& a, int tile, int* b, int* t, int* h0, int* w0, int* chunk) {
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  if (a.pdl_early) pdl_trigger();
 
   const int tile0 = static_cast<int>(blockIdx.x), tile_step = static_cast<int>(gridDim.x);
   if (warp == 0) {
@@ -289,6 +290,7 @@ int launch_conv_halo(const GemmDesc& d, cudaStream_t stream) {
   a.tiles_h = (d.cH + kTileH - 1) / kTileH;
   a.c_blocks = d.cC / 64;
   a.n_chunks = (d.N + 127) / 128;
+  a.pdl_early = pdl_early() ? 1 : 0;
   const long long tiles = static_cast<long long>(d.batch) * d.cT * a.tiles_w * a.tiles_h * a.n_chunks;
   if (tiles < sm_count() || tiles >= (1ll << 30)) return 1;   // small problems: the generic path splits K
   {

@@ -28,6 +28,7 @@ struct LnArgs {
   LnSeg seg[2];  // seg[1].L == 0: single segment (rows of seg[0] come first)
   int mod_bs, B;
   float eps;
+  int pdl_early;
 };
 
 template <int D>
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int rows0 = a.B * a.seg[0].L;
   pdl_wait();
+  if (a.pdl_early) pdl_trigger();
   if (warp >= rows0 + a.B * a.seg[1].L) return;
   const bool second = warp >= rows0;
   if (second) warp -= rows0;
@@ -632,6 +634,7 @@ int launch_ln_modulate2(const LnRows& r0, const LnRows* r1, int mod_bs, int B, i
   a.mod_bs = mod_bs;
   a.B = B;
   a.eps = eps;
+  a.pdl_early = pdl_early() ? 1 : 0;
   const long long rows = static_cast<long long>(B) * (a.seg[0].L + a.seg[1].L);
   if (rows == 0) return 0;
   const int blocks = static_cast<int>((rows * 32 + 255) / 256);

@@ -72,6 +72,7 @@ struct KArgs {
   int total_tiles;
   int splits;
   int total_pair_tiles;
+  int pdl_early;
 };
 
 struct TileCoord {
@@ -723,6 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail
+  if (k.pdl_early) pdl_trigger();
 
   // split-K: the cluster = the splits of ONE tile (grid = tiles * splits, one pass);
   // otherwise a persistent loop over tiles
@@ -1093,6 +1095,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail
+  if (k.pdl_early) pdl_trigger();
 
   const int cluster_id = static_cast<int>(blockIdx.x) >> 1;
   const int n_clusters = static_cast<int>(gridDim.x) >> 1;
@@ -1526,6 +1529,7 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
   for (int i = 0; i < 2; ++i)
     if (ka.p[i].tiles > 0) ka.p[i].kb_per_split = (ka.p[i].k_blocks + ka.splits - 1) / ka.splits;
   ka.total_tiles = ka.p[0].tiles + ka.p[1].tiles;
+  ka.pdl_early = pdl_early() ? 1 : 0;
   if (ka.p[1].tiles == 0) ka.p[1].pair_tiles = 0;
   ka.total_pair_tiles = ka.p[0].pair_tiles + ka.p[1].pair_tiles;
   // CTA pairs (cta_group::2) once every SM pair has a 256-row tile: ~570 cycles per k-block instead
