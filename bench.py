@@ -336,6 +336,7 @@ class ReferenceSampler:
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return
     import torch
@@ -354,7 +355,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
             "sample_ms_per_step": sum(mean.values()) * 1e3,
             "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "fp32",
-            "data": "synthetic", "config": workload_config(args, "host CPU, %d threads" % cores),
+            # the same `config` as our arm at this N (the arm itself runs on the host cores: `cpu_baseline.cores`)
+            "data": "synthetic", "config": workload_config(args, parallelism_string(world, args.group if args.group > 0 else world)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": rs.kind, "sample": rs.describe(mean)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -688,6 +688,316 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
   }
 }
 
+// =====================================================================================================
+// attn_pipe2_kernel (round 2): the pipelined kernel above with TWO softmax groups of four warps.  Group g takes the key
+// tiles j = g, g + 2, ... into S buffer g and keeps its OWN running maximum, row sums and output accumulator
+// (O_g, l_g in tensor memory), so the groups never exchange anything inside the loop: while one waits for its TMEM
+// round trip or for P_j V_j + S_{j+2} on the tensor pipe, the other keeps the XU pipe (ex2) busy.  At the end group 1
+// parks its maxima in shared memory and group 0 merges the two partial softmaxes
+//     m = max(m0, m1),  O = 2^(m0-m) O0 + 2^(m1-m) O1,  l likewise
+// and stores.  TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) l0 [384,400) l1 [400,416) Q [416,448).
+// =====================================================================================================
+constexpr int kPipe2Threads = 64 + 2 * 128;
+constexpr uint32_t kP2ColS = 0, kP2ColO = 256, kP2ColL = 384, kP2ColQ = 416;
+constexpr int kPipe2SmemBytes = kTileBytes + kPipeStages * 2 * kTileBytes + kOnesBytes + 256 + 512 + 1024;
+
+__global__ void __launch_bounds__(kPipe2Threads, 1) attn_pipe2_kernel(const __grid_constant__ AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + kTileBytes;
+  uint8_t* sOnes = sKV + kPipeStages * 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes);
+  uint64_t* q_full = bars;
+  uint64_t* q_ready = bars + 1;
+  uint64_t* kv_full = bars + 2;                  // [kPipeStages]
+  uint64_t* kv_empty = kv_full + kPipeStages;    // [kPipeStages]
+  uint64_t* s_full = kv_empty + kPipeStages;     // [2]: S_j ready in buffer j & 1
+  uint64_t* p_full = s_full + 2;                 // [2]: P_j written over buffer j & 1 (128 arrivals)
+  uint64_t* pv_done = p_full + 2;                // [2]: P_j V_j retired, per softmax group (one phase per tile of the group)
+  uint64_t* o_done = pv_done + 2;
+  uint64_t* m_ready = o_done + 1;                // group 1 parked its running maxima (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(m_ready + 1);
+  float* sM = reinterpret_cast<float*>(bars + 32);  // [128] running maxima of group 1
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z);
+  const int q0 = qt * kTile;
+  const int head = a.head0 + static_cast<int>(blockIdx.x);
+  const int b = blockIdx.y;
+  const int last_q = min(q0 + kTile, a.L) - 1;
+  const int n_kv = (__ldg(a.kv_end + last_q) + kTile - 1) / kTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmQKV);
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 128);
+    for (int i = 0; i < kPipeStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
+    mbar_init(o_done, 1);
+    mbar_init(m_ready, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kPipeTmemCols>(tmem_slot);
+  for (int i = threadIdx.x; i < kOnesBytes / 4; i += kPipe2Threads)
+    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int HD = a.H * kD;
+  pdl_wait();
+  if (a.pdl_early) pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_3d(&a.tmQKV, q_full, sQ, head * kD, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kPipeStages;
+        const uint32_t ph = (j / kPipeStages) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* sK = sKV + s * 2 * kTileBytes;
+        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
+        tma_load_3d(&a.tmQKV, &kv_full[s], sK, HD + head * kD, j * kTile, b);
+        tma_load_3d(&a.tmQKV, &kv_full[s], sK + kTileBytes, 2 * HD + head * kD, j * kTile, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_kv > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 0);
+      const uint32_t tQ = tmem_base + kP2ColQ;
+      const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
+      auto issue_s = [&](int j) {
+        mbar_wait(&kv_full[j % kPipeStages], (j / kPipeStages) & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + kP2ColS + (j & 1) * 128;
+        const uint32_t aK = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes);
+        const uint64_t dk = umma_desc_sw128(aK, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ts(tS, tQ + k * 8, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_ready, 0);
+      issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in TMEM (and O / l rescaled if the max grew)
+        tc_fence_after();
+        const uint32_t tP = tmem_base + kP2ColS + (j & 1) * 128;
+        const uint32_t tO = tmem_base + kP2ColO + (j & 1) * 64, tL = tmem_base + kP2ColL + (j & 1) * 16;
+        const uint32_t aV = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes) + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k) {
+          const uint64_t dv = umma_desc_sw128(aV + k * 2048, 1024, 1024);
+          umma_bf16_ts(tO, tP + k * 8, dv, idesc_pv, ((j >> 1) | k) != 0);   // tiles 0 and 1 start their group's O / l
+          umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, ((j >> 1) | k) != 0);
+        }
+        umma_commit(&kv_empty[j % kPipeStages]);
+        umma_commit(&pv_done[j & 1]);
+        if (j + 2 < n_kv) issue_s(j + 2);  // in order behind P_j V_j: S_{j+2} may overwrite P_j
+        if (j + 1 == n_kv) umma_commit(o_done);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;   // softmax group: tiles j = grp, grp + 2, ... with its own running max, O and l
+    const int r = quarter * 32 + lane;
+    const int qi = q0 + r;
+    const bool row_ok = qi < a.L;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tO = tmem_base + kP2ColO + grp * 64 + lane_addr;
+    const uint32_t tL = tmem_base + kP2ColL + grp * 16 + lane_addr;
+    if (n_kv > 0) {
+      if (grp == 0) {
+      mbar_wait(q_full, 0);
+      {
+        uint32_t qr[32];
+        const uint8_t* row = sQ + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 t = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+          qr[4 * c + 0] = t.x;
+          qr[4 * c + 1] = t.y;
+          qr[4 * c + 2] = t.z;
+          qr[4 * c + 3] = t.w;
+        }
+        tmem_st_32x32(tmem_base + kP2ColQ + lane_addr, qr);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(q_ready);
+      }
+      }
+      const int kv_end = row_ok ? __ldg(a.kv_end + qi) : 0;
+      const int kv_end_min = __ldg(a.kv_end + q0);
+      const float* kb = a.key_bias + static_cast<long long>(b) * a.Lpad;
+      const float sc = a.scale_log2;
+      float m_ref = -INFINITY;
+      const int* dead_row = a.tile_dead ? a.tile_dead + b * (a.Lpad / kTile) : nullptr;
+      for (int j = grp; j < n_kv; j += 2) {
+        const int k0 = j * kTile;
+        const uint32_t tS = tmem_base + kP2ColS + grp * 128 + lane_addr;
+        const bool need_mask = (k0 + kTile > kv_end_min) || (dead_row == nullptr) || (__ldg(dead_row + j) != 0);
+        mbar_wait(&s_full[grp], (j >> 1) & 1);
+        tc_fence_after();
+        float s[kTile];
+#pragma unroll
+        for (int c = 0; c < kTile / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tS + c * 32, raw);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(raw[i]);
+        }
+        tmem_ld_wait();
+        float m_tile = -INFINITY;
+        if (need_mask) {
+#pragma unroll
+          for (int i4 = 0; i4 < kTile / 4; ++i4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(kb + k0) + i4);
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * i4 + e;
+              float x = s[i] + bv[e];
+              x = (k0 + i < kv_end) ? x : -INFINITY;
+              s[i] = x;
+              m_tile = fmaxf(m_tile, x);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kTile; ++i) m_tile = fmaxf(m_tile, s[i]);
+        }
+        m_tile *= sc;
+        const bool had = m_ref > -INFINITY;
+        const bool grow = had ? (m_tile > m_ref + kRescaleThreshold) : (m_tile > -INFINITY);
+        const float m_new = grow ? m_tile : m_ref;
+        if (j > 1 && __any_sync(0xffffffffu, grow && had)) {
+          // O and l of this group still receive P_{j-2} V_{j-2}: wait until it has retired before touching them
+          mbar_wait(&pv_done[grp], ((j >> 1) - 1) & 1);
+          tc_fence_after();
+          const float alpha = (grow && had) ? ex2(m_ref - m_new) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < kD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tO + c * 32, o);
+          }
+          const uint32_t lv = tmem_ld_1(tL);
+          tmem_ld_wait();
+          tmem_st_1(tL, __float_as_uint(__uint_as_float(lv) * alpha));
+          tmem_st_wait();
+        }
+        m_ref = m_new;
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x0 = fmaf(s[hlf * 64 + 2 * i], sc, neg_m);
+            const float x1 = fmaf(s[hlf * 64 + 2 * i + 1], sc, neg_m);
+            pk[i] = pack_bf16x2(ex2(x0), ex2(x1));
+          }
+          tmem_st_32x32(tS + hlf * 32, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[grp]);
+      }
+
+      if (grp == 1) {
+        // hand this group's running maxima to group 0, which merges the two partial results
+        sM[r] = m_ref;
+        mbar_arrive(m_ready);   // (release: the store above is visible to the waiter)
+      } else {
+      mbar_wait(o_done, 0);
+      tc_fence_after();
+      float l_run = __uint_as_float(tmem_ld_1(tL));
+      float o[kD];
+#pragma unroll
+      for (int c = 0; c < kD / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tO + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]);
+      }
+      if (n_kv > 1) {
+        // (m0, l0, O0) + (m1, l1, O1): both relative to their own running maxima (log2 domain)
+        mbar_wait(m_ready, 0);
+        const float m1 = sM[r];
+        const float m = fmaxf(m_ref, m1);
+        const float a0 = (m_ref == -INFINITY) ? 0.f : ex2(m_ref - m);
+        const float a1 = (m1 == -INFINITY) ? 0.f : ex2(m1 - m);
+        const float l1 = __uint_as_float(tmem_ld_1(tL + 16));
+        tmem_ld_wait();
+        l_run = a0 * l_run + a1 * l1;
+#pragma unroll
+        for (int c = 0; c < kD / 32; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tO + 64 + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = a0 * o[c * 32 + i] + a1 * __uint_as_float(raw[i]);
+        }
+      }
+      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+      if (row_ok) {
+        uint4 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          q[i].x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+          q[i].y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+          q[i].z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+          q[i].w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        }
+        const long long off = (static_cast<long long>(b) * a.L + qi) * HD + head * kD;
+        if (a.n_peers == 0) {
+          uint4* d4 = reinterpret_cast<uint4*>(a.out + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = q[i];
+        } else if (qi >= a.peer_Lc) {
+          uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[(qi - a.peer_Lc) / a.peer_Lw] + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = q[i];
+        } else {
+          for (int p = 0; p < a.n_peers; ++p) {
+            uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[p] + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d4[i] = q[i];
+          }
+        }
+      }
+      }  // group 0
+    }
+  }
+
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kPipeTmemCols>(tmem_base);
+  }
+}
+
 }  // namespace
 
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
@@ -725,20 +1035,26 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   // double-buffered-S kernel (one CTA per SM, QK^T of tile j+1 issued before PV of tile j) is the default since
   // round 2: all GPU suites pass with it, attention time of a C2 step 16.8 -> 14.6 ms (profiles/r02a_summary.txt);
   // DV_ATTN_PIPE=0 selects the round-1 kernel (two CTAs per SM, S overwritten by P)
-  static const bool pipe = !(getenv("DV_ATTN_PIPE") != nullptr && atoi(getenv("DV_ATTN_PIPE")) == 0);
+  // DV_ATTN_PIPE: 0 = round-1 kernel, 1 = pipelined kernel with one softmax group, 2 (default) = two softmax groups
+  static const int pipe_mode = getenv("DV_ATTN_PIPE") != nullptr ? atoi(getenv("DV_ATTN_PIPE")) : 2;
+  const bool pipe = pipe_mode != 0;
   static bool attr_set = false;
   if (!attr_set) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemBytes));
     DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kPipeSmemBytes));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pipe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kPipe2SmemBytes));
     attr_set = true;
   }
   dim3 grid(n_heads, B, (L + kTile - 1) / kTile);
   char tag[56] = "";
-  if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d%s", B, L, H, pipe ? " pipe" : "");
+  if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d%s", B, L, H, pipe_mode >= 2 ? " pipe2" : (pipe ? " pipe" : ""));
   const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);
-  if (pipe)
+  if (pipe_mode >= 2)
+    DV_CHECK_CUDA(launch_pdl(attn_pipe2_kernel, grid, dim3(kPipe2Threads), kPipe2SmemBytes, stream, 1, a));
+  else if (pipe)
     DV_CHECK_CUDA(launch_pdl(attn_pipe_kernel, grid, dim3(kAttnThreads), kPipeSmemBytes, stream, 1, a));
   else
     DV_CHECK_CUDA(launch_pdl(attn_kernel, grid, dim3(kAttnThreads), kSmemBytes, stream, 1, a));
