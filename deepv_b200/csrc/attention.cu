@@ -689,7 +689,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
 }
 
 // =====================================================================================================
-// attn_pipe2_kernel (round 2): the pipelined kernel above with TWO softmax groups of four warps.  Group g takes the key
+// attn_pipe2_kernel (round 2, EXPERIMENT, DV_ATTN_PIPE=2, not the default: measured 28 % slower than one group — 320
+// threads cap the kernel at 168 registers (spills in the softmax loop) and the second group's TMEM traffic competes with
+// the MMAs' TMEM operands): the pipelined kernel above with TWO softmax groups of four warps.  Group g takes the key
 // tiles j = g, g + 2, ... into S buffer g and keeps its OWN running maximum, row sums and output accumulator
 // (O_g, l_g in tensor memory), so the groups never exchange anything inside the loop: while one waits for its TMEM
 // round trip or for P_j V_j + S_{j+2} on the tensor pipe, the other keeps the XU pipe (ex2) busy.  At the end group 1
@@ -1035,8 +1037,9 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   // double-buffered-S kernel (one CTA per SM, QK^T of tile j+1 issued before PV of tile j) is the default since
   // round 2: all GPU suites pass with it, attention time of a C2 step 16.8 -> 14.6 ms (profiles/r02a_summary.txt);
   // DV_ATTN_PIPE=0 selects the round-1 kernel (two CTAs per SM, S overwritten by P)
-  // DV_ATTN_PIPE: 0 = round-1 kernel, 1 = pipelined kernel with one softmax group, 2 (default) = two softmax groups
-  static const int pipe_mode = getenv("DV_ATTN_PIPE") != nullptr ? atoi(getenv("DV_ATTN_PIPE")) : 2;
+  // DV_ATTN_PIPE: 0 = round-1 kernel, 1 (default) = pipelined kernel with one softmax group, 2 = two softmax groups
+  // (correct — all suites pass — but measured slower: 236 vs 184 us at B3 L2237, profiles/r02h_summary.txt)
+  static const int pipe_mode = getenv("DV_ATTN_PIPE") != nullptr ? atoi(getenv("DV_ATTN_PIPE")) : 1;
   const bool pipe = pipe_mode != 0;
   static bool attr_set = false;
   if (!attr_set) {
