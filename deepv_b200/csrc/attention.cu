@@ -408,10 +408,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 }
 
 // =====================================================================================================
-// EXPERIMENTAL (DV_ATTN_PIPE=1; off by default — DESIGN.md §7.1).  State at the end of round 1: passes the six
-// attention cases of tests/test_gpu_kernels.py on a B200 and runs the B2 / L1613 / 24-head micro-benchmark
-// (scripts/exp_attn.py, every tile on the masked path) in 93.6 us against 124.8 us for attn_kernel; the model-level
-// parity / sharding suites have not been run with it yet, which is why it is not the default.
+// attn_pipe_kernel — the DEFAULT since round 2 (DV_ATTN_PIPE=0 selects attn_kernel above): all GPU suites (kernel,
+// model-level parity, sharding, rollout, boundary) pass with it; attention time of a rollout 306 -> 265 ms, B3 / L2237
+// 209 -> 184 us (profiles/r02a_summary.txt, r02b_launch_table_rollout.txt).
 // one CTA per SM with TWO S buffers in tensor memory.  The MMA warp issues S_{j+1} = Q K_{j+1}^T before
 // O += P_j V_j, so the softmax warps find the next scores ready when they finish a tile and have the XU
 // pipe to themselves; the price is 512 TMEM columns (one CTA per SM) and a 4-stage K/V ring.
