@@ -457,6 +457,8 @@ def roofline_from_profile(path, prof_ms, peaks):
         ach, peak, unit = d["bytes"] / d["launches"] / 1e9 / (per_launch_ms / 1e3), peak_bw, "GB/s"
     top = {"bound": bound, "kernel": dtag, "kernel_class": dc, "achieved": round(ach, 1), "peak": peak, "unit": unit,
            "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+           "frac_of_burst_peak": round(ach / peaks["bf16_tflops"], 4) if bound == "tensor" and peaks.get("bf16_tflops") else None,
+           "frac_of_nominal_2250": round(ach / 2250.0, 4) if bound == "tensor" else None,
            "algorithmic_flops_per_launch": d["flops"] / d["launches"], "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
            "avg_launch_us": round(per_launch_ms * 1e3, 2), "launches_per_step": d["launches"],
            "kernel_share_of_step": round(d["ms"] / prof_ms, 4) if prof_ms > 0 else None,
@@ -673,6 +675,17 @@ def run_ours(args):
             except Exception:
                 pass
             roofline = roofline_from_profile(path, p0.elapsed_time(p1), peaks)
+            # the whole step against the tensor roofline: algorithmic FLOPs of the workload (deepv_b200/work.py,
+            # SURVEY.md §8d) over the timed step of this rank's rollout group
+            from deepv_b200 import work
+            if rollout:
+                alg = work.rollout_work(ROLLOUT_ITERS, LAT_H, LAT_W, STEPS_PER_STAGE)["total"]
+            else:
+                alg = 5 * sum(work.mmdit_flops(2, SAMPLE_CLIPS[st], False, n_layers=args.layers)["total"] for st in range(3)) \
+                    + 2 * work.vae_decode_flops(2)
+            sus = peaks.get("bf16_tflops_sustained") or 1400.0
+            roofline["whole_step"] = {"algorithmic_tflop": round(alg / 1e12, 1), "tflops_per_gpu": round(alg / 1e12 / (ms / 1e3) / gsz, 1),
+                                      "frac_of_sustained_peak": round(alg / 1e12 / (ms / 1e3) / gsz / sus, 4), "gpus_per_rollout": gsz}
             if not args.profile_dump:
                 os.unlink(path)
         lib.dv_profile_reset()
