@@ -394,6 +394,8 @@ def classify(kind, tag, n_sm=148):
     if kind == 2:
         return "attention"
     if kind == 0:
+        if tag.startswith("pbk"):      # persistent block kernel: only used for layouts with fewer tiles than SMs
+            return "dense_small_M"
         m = re.match(r"gemm B(\d+) M(\d+)(?:\+(\d+))? N(\d+) K(\d+)", tag)
         if m:
             B, m0, m1, N = int(m.group(1)), int(m.group(2)), int(m.group(3) or 0), int(m.group(4))

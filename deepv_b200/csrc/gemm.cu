@@ -313,7 +313,7 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
 #pragma unroll
     for (int i = 0; i < W / 4; ++i) {
       const float4 g = __ldg(g4 + i);
-      float4 t = x4[i];
+      float4 t = __ldcg(x4 + i);   // L2: inside the persistent block kernel x is updated by other SMs between phases
       t.x += g.x * v[4 * i + 0];
       t.y += g.y * v[4 * i + 1];
       t.z += g.z * v[4 * i + 2];
@@ -1221,6 +1221,341 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------
+// Persistent block kernel: the LN / GEMM steps between two attentions of the joint transformer blocks as PHASES of one
+// launch, separated by grid barriers (one CTA per SM, all co-resident).  For token layouts whose GEMMs have fewer
+// tiles than SMs a launch costs 17-30 us whatever its size (launch gap + set-up + pipeline fill + epilogue,
+// DESIGN.md 3.1 finding 7); here those costs are paid once per block instead of six times.
+//   kind LN      LayerNorm + adaLN modulate of the fp32 streams (one warp per row, rows over all warps of the grid)
+//   kind GEMM    units = (tile, k-split) dealt round-robin over the CTAs; splits == 1: the usual epilogue (TMA store /
+//                reduce-add or direct); splits > 1: the fp32 partial tile goes to a global workspace ([unit][col4][row])
+//   kind REDUCE  finishes the preceding split GEMM: items = (tile, 16-row slice); the partials are summed in split order
+//                (bit-reproducible) and the direct epilogue runs
+// Data written in one phase and read in a later one crosses SMs inside ONE kernel: generic-proxy readers use ld.global.cg
+// (L1 is not coherent), TMA stores are drained (wait_group 0) and both proxies fenced before every grid barrier.
+// ------------------------------------------------------------------------------
+constexpr int kPbkMaxPhases = 12;
+constexpr int kPbkMaxProblems = 8;
+enum PbkKind : int { PBK_LN = 0, PBK_GEMM = 1, PBK_REDUCE = 2 };
+
+struct PbkLnSeg {
+  const float* x;
+  long long x_bs;
+  __nv_bfloat16* out;
+  long long out_bs;
+  const float* shift;
+  const float* scale;
+  int L;
+};
+struct PbkPhase {
+  int kind;
+  int p0, np;      // problems of a GEMM / REDUCE phase: [p0, p0 + np)
+  int mode;        // EpiMode
+  int splits;
+  int tiles;       // over the phase's problems
+  PbkLnSeg ln[2];  // kind LN (ln[1].L == 0: one segment)
+  int mod_bs, B;
+  float eps;
+};
+struct PbkArgs {
+  Problem p[kPbkMaxProblems];
+  PbkPhase ph[kPbkMaxPhases];
+  int n_phases;
+  unsigned* bar;   // grid barrier counter, zero at launch
+  float4* work;    // split-K partials
+  int pdl_early;
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// all threads of all CTAs; `epoch` counts the barriers of this launch
+__device__ __forceinline__ void pbk_grid_sync(unsigned* bar, unsigned& epoch) {
+  fence_proxy_async_all();   // my TMA writes (already complete) / generic writes, ordered before the release below
+  __threadfence();
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    const unsigned target = epoch * gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    const uint64_t t0 = global_ns();
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (global_ns() - t0 > 4000000000ull) asm volatile("trap;");
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  fence_proxy_async_all();   // later TMA loads see what the other CTAs wrote with generic stores
+}
+
+__device__ __forceinline__ const Problem& pbk_problem(const PbkArgs& k, const PbkPhase& ph, int& tile) {
+  if (ph.np == 1 || tile < k.p[ph.p0].tiles) return k.p[ph.p0];
+  tile -= k.p[ph.p0].tiles;
+  return k.p[ph.p0 + 1];
+}
+
+__device__ __forceinline__ void pbk_ln_rows(const PbkPhase& ph, int gwarp, int nwarps, int lane) {
+  constexpr int D = 1536, V = D / 128;
+  const int rows0 = ph.B * ph.ln[0].L;
+  const int rows = rows0 + ph.B * ph.ln[1].L;
+  for (int w = gwarp; w < rows; w += nwarps) {
+    const bool second = w >= rows0;
+    const int wr = second ? w - rows0 : w;
+    const PbkLnSeg& sg = second ? ph.ln[1] : ph.ln[0];
+    const int b = wr / sg.L, l = wr - b * sg.L;
+    const float4* xr = reinterpret_cast<const float4*>(sg.x + b * sg.x_bs + static_cast<long long>(l) * D);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = __ldcg(xr + lane + 32 * i);   // the stream was updated by other SMs in the previous phase
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / D) + ph.eps);
+    const float4* sh = reinterpret_cast<const float4*>(sg.shift + static_cast<long long>(b) * ph.mod_bs);
+    const float4* sc = reinterpret_cast<const float4*>(sg.scale + static_cast<long long>(b) * ph.mod_bs);
+    uint2* o2 = reinterpret_cast<uint2*>(sg.out + b * sg.out_bs + static_cast<long long>(l) * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 h = __ldg(sh + lane + 32 * i);
+      const float4 c = __ldg(sc + lane + 32 * i);
+      uint2 pk;
+      pk.x = pack_bf16x2((v[i].x - mean) * rstd * (1.0f + c.x) + h.x, (v[i].y - mean) * rstd * (1.0f + c.y) + h.y);
+      pk.y = pack_bf16x2((v[i].z - mean) * rstd * (1.0f + c.z) + h.z, (v[i].w - mean) * rstd * (1.0f + c.w) + h.w);
+      o2[lane + 32 * i] = pk;
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void pbk_epilogue(const Problem& a, const TileCoord& tc, uint32_t tmem_acc, int row_in_tile,
+                                             int quarter, int half, uint8_t* out_stage, bool issuer) {
+  if (a.tma_out)
+    epilogue_tma<MODE>(a, tc, tmem_acc, row_in_tile, quarter, half, out_stage, issuer);
+  else
+    epilogue_from_tmem<MODE>(a, tc, tmem_acc, row_in_tile, quarter, half, nullptr);
+}
+
+// REDUCE item: rows [slice * 16, +16) of one tile; t = 0..255
+template <int MODE>
+__device__ __forceinline__ void pbk_reduce_item(const Problem& a, const TileCoord& tc, const float4* work,
+                                                int unit0, int splits, int slice, int t) {
+  constexpr int W = EpiW<MODE>::value;
+  const int row_in_tile = slice * 16 + (t & 15);
+  const int group = t >> 4;  // 0..15
+  const RowCtx r = make_row(a, tc, row_in_tile);
+  if (!r.ok) return;
+  for (int c = group; c < BN / W; c += 16) {
+    const int n = tc.n_tile * BN + c * W;
+    if (n >= a.d.N) continue;
+    float v[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = 0.f;
+#pragma unroll 1
+    for (int sp = 0; sp < splits; ++sp) {  // fixed order: bit-reproducible sums
+      const float4* part = work + static_cast<long long>(unit0 + sp) * (BM * BN / 4);
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        const float4 q = __ldcg(part + (c * (W / 4) + i) * BM + row_in_tile);
+        v[4 * i + 0] += q.x;
+        v[4 * i + 1] += q.y;
+        v[4 * i + 2] += q.z;
+        v[4 * i + 3] += q.w;
+      }
+    }
+    epi_row<MODE, W>(a, r, n, v, false);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) pbk_kernel(const __grid_constant__ PbkArgs k) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* out_stage = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kOutBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 32 * kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  if (k.pdl_early) pdl_trigger();
+
+  // per-role pipeline state, carried across the phases
+  int stage = 0;
+  uint32_t phase = 0;
+  int acc_it = 0;
+  unsigned epoch = 0;
+  const int quarter = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int row_in_tile = quarter * 32 + lane;
+  const bool issuer = warp >= 2 && quarter == 0 && lane == 0;
+  constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+
+  for (int pi = 0; pi < k.n_phases; ++pi) {
+    const PbkPhase& ph = k.ph[pi];
+    if (ph.kind == PBK_LN) {
+      pbk_ln_rows(ph, static_cast<int>(blockIdx.x) * (kThreads / 32) + warp, static_cast<int>(gridDim.x) * (kThreads / 32), lane);
+    } else if (ph.kind == PBK_GEMM) {
+      const int units = ph.tiles * ph.splits;
+      if (warp == 0) {
+        if (lane == 0) {
+          for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            int tile = u / ph.splits;
+            const Problem& a = pbk_problem(k, ph, tile);
+            const TileCoord tc = decode_tile(a, tile, u % ph.splits);
+            for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * kStageBytes;
+              uint8_t* sb = sa + kABytes;
+              mbar_expect_tx(&full_bar[stage], kStageBytes);
+              tma_load_3d(&a.tmA, &full_bar[stage], sa, kb * BK, tc.m_tile * BM, tc.b);
+              tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      } else if (warp == 1) {
+        if (lane == 0) {
+          for (int u = blockIdx.x; u < units; u += gridDim.x, ++acc_it) {
+            const int as = acc_it & 1;
+            const uint32_t aph = (acc_it >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + as * BN;
+            int tile = u / ph.splits;
+            const Problem& a = pbk_problem(k, ph, tile);
+            const TileCoord tc = decode_tile(a, tile, u % ph.splits);
+            for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+              const uint32_t sb = sa + kABytes;
+              const uint64_t da = umma_desc_sw128(sa, 16, 1024);
+              const uint64_t db = umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk)
+                umma_bf16_ss(tmem_acc, da + 2 * kk, db + 2 * kk, idesc, ((kb - tc.kb0) | kk) != 0);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            if (tc.kb0 < tc.kb1)
+              umma_commit(&tmem_full[as]);
+            else
+              mbar_arrive(&tmem_full[as]);
+          }
+        }
+      } else {
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++acc_it) {
+          const int as = acc_it & 1;
+          const uint32_t aph = (acc_it >> 1) & 1;
+          int tile = u / ph.splits;
+          const Problem& a = pbk_problem(k, ph, tile);
+          const TileCoord tc = decode_tile(a, tile, u % ph.splits);
+          mbar_wait(&tmem_full[as], aph);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + as * BN;
+          if (ph.splits == 1) {
+            if (ph.mode == EPI_GELU)
+              pbk_epilogue<EPI_GELU>(a, tc, tmem_acc, row_in_tile, quarter, half, out_stage, issuer);
+            else if (ph.mode == EPI_QKV)
+              pbk_epilogue<EPI_QKV>(a, tc, tmem_acc, row_in_tile, quarter, half, out_stage, issuer);
+            else
+              pbk_epilogue<EPI_RESID_GATE>(a, tc, tmem_acc, row_in_tile, quarter, half, out_stage, issuer);
+          } else {
+            // park the fp32 partial tile of this unit in the workspace as [col4][row] float4
+            const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+            float4* part = k.work + static_cast<long long>(u) * (BM * BN / 4);
+            const bool empty = tc.kb0 >= tc.kb1;
+#pragma unroll 1
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+              uint32_t raw[32];
+              tmem_ld_32x32(taddr + c * 32, raw);
+              tmem_ld_wait();
+              if (empty) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) raw[i] = 0u;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                __stcg(part + (c * 8 + i) * BM + row_in_tile,
+                       make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                                   __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3])));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[as]);
+        }
+        if (issuer) bulk_wait_all();  // my TMA stores / reduce-adds of this phase are performed
+      }
+    } else {  // PBK_REDUCE
+      if (warp >= 2) {
+        const int t = static_cast<int>(threadIdx.x) - 64;
+        const int items = ph.tiles * (BM / 16);
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+          int tile = it / (BM / 16);
+          const int slice = it % (BM / 16);
+          const int unit0 = tile * ph.splits;
+          const Problem& a = pbk_problem(k, ph, tile);
+          const TileCoord tc = decode_tile(a, tile, 0);
+          if (ph.mode == EPI_GELU)
+            pbk_reduce_item<EPI_GELU>(a, tc, k.work, unit0, ph.splits, slice, t);
+          else if (ph.mode == EPI_QKV)
+            pbk_reduce_item<EPI_QKV>(a, tc, k.work, unit0, ph.splits, slice, t);
+          else
+            pbk_reduce_item<EPI_RESID_GATE>(a, tc, k.work, unit0, ph.splits, slice, t);
+        }
+      }
+    }
+    if (pi + 1 < k.n_phases) pbk_grid_sync(k.bar, epoch);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 template <int MODE>
 int launch_mode(const KArgs& ka, cudaStream_t stream) {
   static bool attr_set = false;
@@ -1483,6 +1818,102 @@ static int launch_args(KArgs& ka, int mode, bool pair, cudaStream_t stream) {
       set_error("gemm: unknown epilogue mode %d", mode);
       return -1;
   }
+}
+
+long long pbk_workspace_floats() { return static_cast<long long>(sm_count()) * BM * BN; }
+
+int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar, cudaStream_t stream) {
+  DV_REQUIRE(phases && n >= 1 && workspace && bar, "pbk: bad argument");
+  static bool attr_set = false;
+  if (!attr_set) {
+    DV_CHECK_CUDA(cudaFuncSetAttribute(pbk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    int occ = 0;
+    DV_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pbk_kernel, kThreads, kSmemBytes));
+    DV_REQUIRE(occ >= 1, "pbk: the kernel does not fit an SM");
+    attr_set = true;
+  }
+  const int grid = sm_count();   // one CTA per SM, all co-resident: the grid barrier relies on it
+  PbkArgs ka;                    // ~13 KB, passed by value (large kernel parameters)
+  ka.n_phases = 0;
+  ka.bar = bar;
+  ka.work = reinterpret_cast<float4*>(workspace);
+  ka.pdl_early = pdl_early() ? 1 : 0;
+  int np = 0;
+  double flops = 0.0, bytes = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const PbkPhaseIn& in = phases[i];
+    DV_REQUIRE(ka.n_phases + 2 <= kPbkMaxPhases, "pbk: too many phases");
+    PbkPhase& ph = ka.ph[ka.n_phases++];
+    ph = PbkPhase{};
+    if (in.kind == 0) {
+      ph.kind = PBK_LN;
+      auto fill = [](PbkLnSeg& sg, const LnRows& r) {
+        sg.x = r.x;
+        sg.x_bs = r.x_bs;
+        sg.out = r.out;
+        sg.out_bs = r.out_bs;
+        sg.shift = r.shift;
+        sg.scale = r.scale;
+        sg.L = r.L;
+      };
+      fill(ph.ln[0], in.ln0);
+      if (in.has_ln1) {
+        fill(ph.ln[1], in.ln1);
+      } else {
+        ph.ln[1] = ph.ln[0];
+        ph.ln[1].L = 0;
+      }
+      ph.mod_bs = in.mod_bs;
+      ph.B = in.B;
+      ph.eps = in.eps;
+      bytes += static_cast<double>(in.B) * (in.ln0.L + (in.has_ln1 ? in.ln1.L : 0)) * 1536.0 * 6.0;
+      continue;
+    }
+    DV_REQUIRE(in.kind == 1, "pbk: phase kind %d", in.kind);
+    DV_REQUIRE(np + 1 + in.has_g1 <= kPbkMaxProblems, "pbk: too many GEMM problems");
+    DV_REQUIRE(in.g0.a_mode == 0 && (in.g0.mode == EPI_GELU || in.g0.mode == EPI_QKV || in.g0.mode == EPI_RESID_GATE),
+               "pbk: dense GELU / QKV / gated-residual problems only (mode %d)", in.g0.mode);
+    ph.kind = PBK_GEMM;
+    ph.p0 = np;
+    ph.np = 1 + (in.has_g1 ? 1 : 0);
+    ph.mode = in.g0.mode;
+    int rc = setup_problem(in.g0, ka.p[np]);
+    if (rc) return rc;
+    if (in.has_g1) {
+      DV_REQUIRE(in.g1.mode == in.g0.mode && in.g1.a_mode == 0 && in.g1.K == in.g0.K && in.g1.N == in.g0.N,
+                 "pbk: the two problems of a phase must share mode, N and K");
+      rc = setup_problem(in.g1, ka.p[np + 1]);
+      if (rc) return rc;
+    }
+    ph.tiles = ka.p[np].tiles + (in.has_g1 ? ka.p[np + 1].tiles : 0);
+    const int kb = ka.p[np].k_blocks;
+    int splits = 1;
+    if (ph.tiles < grid) {
+      splits = grid / ph.tiles;
+      if (splits > 8) splits = 8;
+      while (splits > 1 && kb / splits < 2) --splits;
+    }
+    ph.splits = splits;
+    for (int j = 0; j < ph.np; ++j) ka.p[np + j].kb_per_split = (kb + splits - 1) / splits;
+    for (int j = 0; j < ph.np; ++j) {
+      const GemmDesc& d = j ? in.g1 : in.g0;
+      const double rows = static_cast<double>(d.M) * d.batch;
+      flops += 2.0 * rows * d.N * d.K;
+      bytes += 2.0 * (rows * d.K + static_cast<double>(d.N) * d.K + rows * d.N);
+    }
+    np += ph.np;
+    if (splits > 1) {
+      DV_REQUIRE(static_cast<long long>(ph.tiles) * splits <= grid, "pbk: %d units of partials exceed the workspace", ph.tiles * splits);
+      PbkPhase& red = ka.ph[ka.n_phases++];
+      red = ph;
+      red.kind = PBK_REDUCE;
+    }
+  }
+  DV_CHECK_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), stream));
+  ProfScope ps(PROF_GEMM, flops, bytes, stream, "pbk (persistent block kernel)");
+  DV_CHECK_CUDA(launch_pdl(pbk_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, ka));
+  note_launch();
+  return 0;
 }
 
 int launch_gemm(const GemmDesc& d, cudaStream_t stream) { return launch_gemm_pair(d, nullptr, stream); }

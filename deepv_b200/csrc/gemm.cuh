@@ -12,6 +12,7 @@
 //   runs as separate ATen kernels.
 #pragma once
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace dv {
 
@@ -95,5 +96,20 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream);
 int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream);
 // conv_halo.cu: 0 = launched, 1 = not a problem that kernel takes (use the generic path), < 0 = error
 int launch_conv_halo(const GemmDesc& d, cudaStream_t stream);
+
+// Persistent block kernel (gemm.cu, pbk_kernel): a sequence of LN-modulate and dense GEMM phases of the joint transformer
+// blocks in ONE launch, grid barriers between the phases.  For token layouts whose GEMMs have fewer tiles than SMs.
+struct PbkPhaseIn {
+  int kind;          // 0 = LN-modulate (ln0, optional ln1), 1 = GEMM (g0, optional g1, same epilogue mode / N / K)
+  LnRows ln0, ln1;
+  int has_ln1;
+  int mod_bs, B;
+  float eps;
+  GemmDesc g0, g1;
+  int has_g1;
+};
+// workspace: fp32 scratch for split-K partials (pbk_workspace_floats() floats); bar: one zero-initialised device word
+long long pbk_workspace_floats();
+int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar, cudaStream_t stream);
 
 }  // namespace dv

@@ -36,6 +36,9 @@ struct dv_mmdit {
   int cc_slots = 0;
   float *cc_keys = nullptr, *cc_tables = nullptr;
   int* cc_valid = nullptr;
+  // persistent block kernel: split-K partial workspace (one 128 x 256 fp32 tile per SM) and the grid-barrier word
+  float* pbk_work = nullptr;
+  unsigned* pbk_bar = nullptr;
 };
 
 static constexpr int kMaxFrames = 256;
@@ -215,12 +218,21 @@ extern "C" int dv_mmdit_create(const dv_mmdit_config* cfg, const dv_mmdit_weight
       }
     }
   }
+  e = cudaMalloc(&m->pbk_work, static_cast<size_t>(pbk_workspace_floats()) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&m->pbk_bar, 64);
+  if (e != cudaSuccess) {
+    set_error("dv_mmdit_create: persistent-kernel workspace: %s", cudaGetErrorString(e));
+    dv_mmdit_destroy(m);
+    return DV_ERR_CUDA;
+  }
   *out = m;
   return DV_OK;
 }
 
 extern "C" void dv_mmdit_destroy(dv_mmdit* m) {
   if (!m) return;
+  cudaFree(m->pbk_work);
+  cudaFree(m->pbk_bar);
   cudaFree(m->pos_base);
   cudaFree(m->rope_cs);
   cudaFree(m->cc_keys);
@@ -606,44 +618,149 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
     return exchange(0);
   };
   // ---- transformer blocks ------------------------------------------------------------------
-  // Every step of a joint block is ONE launch covering the video and the context stream
-  // (the reference runs them as separate modules, mmdit.py:385-433).
-  for (int i = 0; i < NL; ++i) {
+  // Every step of a joint block covers the video and the context stream at once (the reference runs them as separate
+  // modules, mmdit.py:385-433).  The six LN / GEMM steps between two attentions are described as phases and either
+  // launched one by one or, for token layouts whose GEMMs have fewer tiles than SMs, handed to the persistent block
+  // kernel in one launch (gemm.cu, pbk_kernel).
+  auto ln_phase = [&](int i, bool second) {
     const bool last = (i == NL - 1);
     const float* mx = p->mod + static_cast<long long>(i) * 12 * D;  // video modulation, 6 chunks
     const float* mc = mx + 6 * D;                                   // context modulation
-    // norm1 / norm1_context: chunk order shift, scale, gate (msa), shift, scale, gate (mlp);
-    // last block: AdaLayerNormContinuous on the context, chunk order scale, shift (mmdit.py:513)
-    {
-      LnRows rx = {xw, xs, xnw, xs, mx + 0 * D, mx + 1 * D, Lw};
-      LnRows rcx = {p->c, cs, p->cn, cs, last ? mc + 1 * D : mc + 0 * D, last ? mc + 0 * D : mc + 1 * D, Lc};
-      DV_RUN(launch_ln_modulate2(rx, &rcx, MR, B, D, 1e-6f, st));
+    PbkPhaseIn ph = {};
+    ph.kind = 0;
+    ph.mod_bs = MR;
+    ph.B = B;
+    ph.eps = 1e-6f;
+    if (!second) {
+      // norm1 / norm1_context: chunk order shift, scale, gate (msa), shift, scale, gate (mlp);
+      // last block: AdaLayerNormContinuous on the context, chunk order scale, shift (mmdit.py:513)
+      ph.ln0 = LnRows{xw, xs, xnw, xs, mx + 0 * D, mx + 1 * D, Lw};
+      ph.ln1 = LnRows{p->c, cs, p->cn, cs, last ? mc + 1 * D : mc + 0 * D, last ? mc + 0 * D : mc + 1 * D, Lc};
+      ph.has_ln1 = 1;
+    } else {
+      ph.ln0 = LnRows{xw, xs, xnw, xs, mx + 3 * D, mx + 4 * D, Lw};
+      ph.ln1 = LnRows{p->c, cs, p->cn, cs, mc + 3 * D, mc + 4 * D, Lc};
+      ph.has_ln1 = last ? 0 : 1;
     }
-    // fused q|k|v projection + per-head RMSNorm + temporal RoPE, written into the joint layout
-    {
-      GemmDesc dq[2];
-      for (int s = 0; s < 2; ++s) {
-        const bool vid = (s == 0);
-        GemmDesc d = dense_desc(vid ? xnw : p->cn, vid ? xs : cs, D,
-                                vid ? m->p_w_qkv_x[i] : m->p_w_qkv_c[i], 3 * D,
-                                vid ? m->p_b_qkv_x[i] : m->p_b_qkv_c[i], B, vid ? Lw : Lc, 3 * D, D);
-        d.mode = EPI_QKV;
-        d.out = p->qkv;
-        d.out_batch_stride = static_cast<long long>(L) * 3 * D;
-        d.ldo = 3 * D;
-        d.out_row_offset = vid ? Lc + v0 : 0;
-        d.qk_norm_w = vid ? m->p_qk_norm_x[i] : m->p_qk_norm_c[i];
-        d.rope_cs = m->rope_cs;
-        d.frame_id = vid ? p->frame_x + v0 : p->frame_c;
-        d.heads_dim = D;
-        if (vid && P > 1 && p->peers_set) {  // each head straight into the buffer of the rank that owns it
-          for (int j = 0; j < P; ++j) d.out_peer[j] = p->qkv_peer[j];
-          d.peer_cols = Hc;
-        }
-        dq[s] = d;
+    return ph;
+  };
+  // fused q|k|v projection + per-head RMSNorm + temporal RoPE, written into the joint layout
+  auto qkv_phase = [&](int i) {
+    PbkPhaseIn ph = {};
+    ph.kind = 1;
+    ph.has_g1 = 1;
+    for (int s = 0; s < 2; ++s) {
+      const bool vid = (s == 0);
+      GemmDesc d = dense_desc(vid ? xnw : p->cn, vid ? xs : cs, D,
+                              vid ? m->p_w_qkv_x[i] : m->p_w_qkv_c[i], 3 * D,
+                              vid ? m->p_b_qkv_x[i] : m->p_b_qkv_c[i], B, vid ? Lw : Lc, 3 * D, D);
+      d.mode = EPI_QKV;
+      d.out = p->qkv;
+      d.out_batch_stride = static_cast<long long>(L) * 3 * D;
+      d.ldo = 3 * D;
+      d.out_row_offset = vid ? Lc + v0 : 0;
+      d.qk_norm_w = vid ? m->p_qk_norm_x[i] : m->p_qk_norm_c[i];
+      d.rope_cs = m->rope_cs;
+      d.frame_id = vid ? p->frame_x + v0 : p->frame_c;
+      d.heads_dim = D;
+      if (vid && P > 1 && p->peers_set) {  // each head straight into the buffer of the rank that owns it
+        for (int j = 0; j < P; ++j) d.out_peer[j] = p->qkv_peer[j];
+        d.peer_cols = Hc;
       }
-      DV_RUN(launch_gemm_pair(dq[0], &dq[1], st));
+      (vid ? ph.g0 : ph.g1) = d;
     }
+    return ph;
+  };
+  // x += gate_msa * to_out(attn);  c += c_gate_msa * to_add_out(attn_c)  (not in the last block)
+  auto out_phase = [&](int i) {
+    const bool last = (i == NL - 1);
+    const float* mx = p->mod + static_cast<long long>(i) * 12 * D;
+    const float* mc = mx + 6 * D;
+    PbkPhaseIn ph = {};
+    ph.kind = 1;
+    GemmDesc dx = dense_desc(p->attn + static_cast<long long>(Lc + v0) * D, js, D, m->p_w_out_x[i], D,
+                             m->p_b_out_x[i], B, Lw, D, D);
+    dx.mode = EPI_RESID_GATE;
+    dx.out = xw;
+    dx.out_batch_stride = xs;
+    dx.ldo = D;
+    dx.gate = mx + 2 * D;
+    dx.gate_batch_stride = MR;
+    ph.g0 = dx;
+    if (!last) {
+      GemmDesc dc = dense_desc(p->attn, js, D, m->p_w_out_c[i], D, m->p_b_out_c[i], B, Lc, D, D);
+      dc.mode = EPI_RESID_GATE;
+      dc.out = p->c;
+      dc.out_batch_stride = cs;
+      dc.ldo = D;
+      dc.gate = mc + 2 * D;
+      dc.gate_batch_stride = MR;
+      ph.g1 = dc;
+      ph.has_g1 = 1;
+    }
+    return ph;
+  };
+  // feed-forward, both streams: W1 + GELU (which = 0), W2 + gated residual (which = 1)
+  auto ff_phase = [&](int i, int which) {
+    const bool last = (i == NL - 1);
+    const float* mx = p->mod + static_cast<long long>(i) * 12 * D;
+    const float* mc = mx + 6 * D;
+    PbkPhaseIn ph = {};
+    ph.kind = 1;
+    ph.has_g1 = last ? 0 : 1;
+    for (int s = 0; s < 2; ++s) {
+      const bool vid = (s == 0);
+      const float* mm = vid ? mx : mc;
+      float* res = vid ? xw : p->c;
+      __nv_bfloat16* nrm = vid ? xnw : p->cn;
+      __nv_bfloat16* hid = vid ? ffhw : p->ffh_c;
+      const long long rs = vid ? xs : cs;
+      const int Ls = vid ? Lw : Lc;
+      const long long hs = static_cast<long long>(vid ? Lv : Lc) * 4 * D;  // hidden batch stride
+      GemmDesc d;
+      if (which == 0) {
+        d = dense_desc(nrm, rs, D, vid ? m->p_w_ff1_x[i] : m->p_w_ff1_c[i], 4 * D,
+                       vid ? m->p_b_ff1_x[i] : m->p_b_ff1_c[i], B, Ls, 4 * D, D);
+        d.mode = EPI_GELU;
+        d.out = hid;
+        d.out_batch_stride = hs;
+        d.ldo = 4 * D;
+      } else {
+        d = dense_desc(hid, hs, 4 * D, vid ? m->p_w_ff2_x[i] : m->p_w_ff2_c[i], D,
+                       vid ? m->p_b_ff2_x[i] : m->p_b_ff2_c[i], B, Ls, D, 4 * D);
+        d.mode = EPI_RESID_GATE;
+        d.out = res;
+        d.out_batch_stride = rs;
+        d.ldo = D;
+        d.gate = mm + 5 * D;
+        d.gate_batch_stride = MR;
+      }
+      (vid ? ph.g0 : ph.g1) = d;
+    }
+    return ph;
+  };
+  auto run_phase = [&](const PbkPhaseIn& ph) -> int {
+    if (ph.kind == 0) return launch_ln_modulate2(ph.ln0, ph.has_ln1 ? &ph.ln1 : nullptr, ph.mod_bs, ph.B, D, ph.eps, st);
+    return launch_gemm_pair(ph.g0, ph.has_g1 ? &ph.g1 : nullptr, st);
+  };
+  // persistent block kernel: DV_MMDIT_PBK=0 never, =1 whenever the layout is small enough (rows per rank <=
+  // DV_PBK_MAX_ROWS, default 2048); default: on
+  static const int pbk_env = getenv("DV_MMDIT_PBK") ? atoi(getenv("DV_MMDIT_PBK")) : 1;
+  static const int pbk_max_rows = getenv("DV_PBK_MAX_ROWS") ? atoi(getenv("DV_PBK_MAX_ROWS")) : 2048;
+  const bool use_pbk = pbk_env != 0 && m->pbk_work != nullptr && B * (Lw + Lc) <= pbk_max_rows;
+  auto run_phases = [&](const PbkPhaseIn* ph, int n) -> int {
+    if (use_pbk) return launch_pbk(ph, n, m->pbk_work, m->pbk_bar, st);
+    for (int j = 0; j < n; ++j) {
+      const int prc = run_phase(ph[j]);
+      if (prc) return prc;
+    }
+    return 0;
+  };
+  {
+    PbkPhaseIn head[2] = {ln_phase(0, false), qkv_phase(0)};
+    DV_RUN(run_phases(head, 2));
+  }
+  for (int i = 0; i < NL; ++i) {
     if (peer) {
       DV_RUN(sp_sync());  // barrier: every rank's q|k|v stores have landed
     } else if (P > 1) {
@@ -663,59 +780,14 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
       DV_RUN(exchange(static_cast<long long>(B) * (Lc + Lw) * Hc * 2));
       DV_RUN(launch_sp_attn_unpack(p->sp_recv, p->attn, B, L, D, Lc, Lw, P, Hc, R, st));
     }
-    // x += gate_msa * to_out(attn);  c += c_gate_msa * to_add_out(attn_c)  (not in the last block)
-    {
-      GemmDesc dx = dense_desc(p->attn + static_cast<long long>(Lc + v0) * D, js, D, m->p_w_out_x[i], D,
-                               m->p_b_out_x[i], B, Lw, D, D);
-      dx.mode = EPI_RESID_GATE;
-      dx.out = xw;
-      dx.out_batch_stride = xs;
-      dx.ldo = D;
-      dx.gate = mx + 2 * D;
-      dx.gate_batch_stride = MR;
-      GemmDesc dc = dense_desc(p->attn, js, D, m->p_w_out_c[i], D, m->p_b_out_c[i], B, Lc, D, D);
-      dc.mode = EPI_RESID_GATE;
-      dc.out = p->c;
-      dc.out_batch_stride = cs;
-      dc.ldo = D;
-      dc.gate = mc + 2 * D;
-      dc.gate_batch_stride = MR;
-      DV_RUN(launch_gemm_pair(dx, last ? nullptr : &dc, st));
+    // the rest of block i and, up to its q|k|v projection, block i + 1
+    PbkPhaseIn tail[6] = {out_phase(i), ln_phase(i, true), ff_phase(i, 0), ff_phase(i, 1)};
+    int nt = 4;
+    if (i + 1 < NL) {
+      tail[nt++] = ln_phase(i + 1, false);
+      tail[nt++] = qkv_phase(i + 1);
     }
-    // feed-forward, both streams: LN + modulate, W1 + GELU, W2 + gated residual
-    {
-      LnRows rx = {xw, xs, xnw, xs, mx + 3 * D, mx + 4 * D, Lw};
-      LnRows rcx = {p->c, cs, p->cn, cs, mc + 3 * D, mc + 4 * D, Lc};
-      DV_RUN(launch_ln_modulate2(rx, last ? nullptr : &rcx, MR, B, D, 1e-6f, st));
-      GemmDesc d1[2], d2[2];
-      for (int s = 0; s < 2; ++s) {
-        const bool vid = (s == 0);
-        const float* mm = vid ? mx : mc;
-        float* res = vid ? xw : p->c;
-        __nv_bfloat16* nrm = vid ? xnw : p->cn;
-        __nv_bfloat16* hid = vid ? ffhw : p->ffh_c;
-        const long long rs = vid ? xs : cs;
-        const int Ls = vid ? Lw : Lc;
-        const long long hs = static_cast<long long>(vid ? Lv : Lc) * 4 * D;  // hidden batch stride
-        d1[s] = dense_desc(nrm, rs, D, vid ? m->p_w_ff1_x[i] : m->p_w_ff1_c[i], 4 * D,
-                           vid ? m->p_b_ff1_x[i] : m->p_b_ff1_c[i], B, Ls, 4 * D, D);
-        d1[s].mode = EPI_GELU;
-        d1[s].out = hid;
-        d1[s].out_batch_stride = hs;
-        d1[s].ldo = 4 * D;
-        d2[s] = dense_desc(hid, hs, 4 * D,
-                           vid ? m->p_w_ff2_x[i] : m->p_w_ff2_c[i], D,
-                           vid ? m->p_b_ff2_x[i] : m->p_b_ff2_c[i], B, Ls, D, 4 * D);
-        d2[s].mode = EPI_RESID_GATE;
-        d2[s].out = res;
-        d2[s].out_batch_stride = rs;
-        d2[s].ldo = D;
-        d2[s].gate = mm + 5 * D;
-        d2[s].gate_batch_stride = MR;
-      }
-      DV_RUN(launch_gemm_pair(d1[0], last ? nullptr : &d1[1], st));
-      DV_RUN(launch_gemm_pair(d2[0], last ? nullptr : &d2[1], st));
-    }
+    DV_RUN(run_phases(tail, nt));
   }
 
   if (P > 1) {
