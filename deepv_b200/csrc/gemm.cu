@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
 //   kind LN      LayerNorm + adaLN modulate of the fp32 streams (one warp per row, rows over all warps of the grid)
 //   kind GEMM    units = (tile, k-split) dealt round-robin over the CTAs; splits == 1: the usual epilogue (TMA store /
 //                reduce-add or direct); splits > 1: the fp32 partial tile goes to a global workspace ([unit][col4][row])
-//   kind REDUCE  finishes the preceding split GEMM: items = (tile, 16-row slice); the partials are summed in split order
+//   kind REDUCE  finishes the preceding split GEMM: items = (tile, 32-row slice); the partials are summed in split order
 //                (bit-reproducible) and the direct epilogue runs
 // Data written in one phase and read in a later one crosses SMs inside ONE kernel: generic-proxy readers use ld.global.cg
 // (L1 is not coherent), TMA stores are drained (wait_group 0) and both proxies fenced before every grid barrier.
@@ -1349,31 +1349,44 @@ __device__ __forceinline__ void pbk_epilogue(const Problem& a, const TileCoord& 
     epilogue_from_tmem<MODE>(a, tc, tmem_acc, row_in_tile, quarter, half, nullptr);
 }
 
-// REDUCE item: rows [slice * 16, +16) of one tile; t = 0..255
+// REDUCE item: rows [slice * 32, +32) of one tile; t = 0..255.  The partials of two splits are fetched together (their
+// loads are independent, the L2 round trips overlap); the sum still runs in split order.
 template <int MODE>
 __device__ __forceinline__ void pbk_reduce_item(const Problem& a, const TileCoord& tc, const float4* work,
                                                 int unit0, int splits, int slice, int t) {
   constexpr int W = EpiW<MODE>::value;
-  const int row_in_tile = slice * 16 + (t & 15);
-  const int group = t >> 4;  // 0..15
+  const int row_in_tile = slice * 32 + (t & 31);
+  const int group = t >> 5;  // 0..7
   const RowCtx r = make_row(a, tc, row_in_tile);
   if (!r.ok) return;
-  for (int c = group; c < BN / W; c += 16) {
+  for (int c = group; c < BN / W; c += 8) {
     const int n = tc.n_tile * BN + c * W;
     if (n >= a.d.N) continue;
     float v[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) v[i] = 0.f;
+    const float4* part = work + static_cast<long long>(unit0) * (BM * BN / 4) + (c * (W / 4)) * BM + row_in_tile;
+    constexpr int STEP = (W == 32) ? 2 : 1;   // W = 64 (q|k|v heads): one split at a time keeps the registers
 #pragma unroll 1
-    for (int sp = 0; sp < splits; ++sp) {  // fixed order: bit-reproducible sums
-      const float4* part = work + static_cast<long long>(unit0 + sp) * (BM * BN / 4);
+    for (int sp = 0; sp < splits; sp += STEP) {  // fixed order: bit-reproducible sums
+      float4 q[STEP][W / 4];
 #pragma unroll
-      for (int i = 0; i < W / 4; ++i) {
-        const float4 q = __ldcg(part + (c * (W / 4) + i) * BM + row_in_tile);
-        v[4 * i + 0] += q.x;
-        v[4 * i + 1] += q.y;
-        v[4 * i + 2] += q.z;
-        v[4 * i + 3] += q.w;
+      for (int j = 0; j < STEP; ++j) {
+        const bool live = sp + j < splits;
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i)
+          q[j][i] = live ? __ldcg(part + static_cast<long long>(sp + j) * (BM * BN / 4) + i * BM)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < STEP; ++j) {
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) {
+          v[4 * i + 0] += q[j][i].x;
+          v[4 * i + 1] += q[j][i].y;
+          v[4 * i + 2] += q[j][i].z;
+          v[4 * i + 3] += q[j][i].w;
+        }
       }
     }
     epi_row<MODE, W>(a, r, n, v, false);
@@ -1529,10 +1542,10 @@ __global__ void __launch_bounds__(kThreads, 1) pbk_kernel(const __grid_constant_
     } else {  // PBK_REDUCE
       if (warp >= 2) {
         const int t = static_cast<int>(threadIdx.x) - 64;
-        const int items = ph.tiles * (BM / 16);
+        const int items = ph.tiles * (BM / 32);
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
-          int tile = it / (BM / 16);
-          const int slice = it % (BM / 16);
+          int tile = it / (BM / 32);
+          const int slice = it % (BM / 32);
           const int unit0 = tile * ph.splits;
           const Problem& a = pbk_problem(k, ph, tile);
           const TileCoord tc = decode_tile(a, tile, 0);
@@ -1890,8 +1903,8 @@ int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar,
     int splits = 1;
     if (ph.tiles < grid) {
       splits = grid / ph.tiles;
-      if (splits > 8) splits = 8;
-      while (splits > 1 && kb / splits < 2) --splits;
+      if (splits > 6) splits = 6;
+      while (splits > 1 && kb / splits < 4) --splits;
     }
     ph.splits = splits;
     for (int j = 0; j < ph.np; ++j) ka.p[np + j].kb_per_split = (kb + splits - 1) / splits;
@@ -1910,7 +1923,14 @@ int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar,
     }
   }
   DV_CHECK_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), stream));
-  ProfScope ps(PROF_GEMM, flops, bytes, stream, "pbk (persistent block kernel)");
+  char tag[56] = "pbk";
+  if (prof_on()) {
+    int rows = 0;
+    for (int i = 0; i < n && rows == 0; ++i)
+      if (phases[i].kind == 1) rows = phases[i].g0.batch * (phases[i].g0.M + (phases[i].has_g1 ? phases[i].g1.M : 0));
+    snprintf(tag, sizeof(tag), "pbk rows%d phases%d", rows, ka.n_phases);
+  }
+  ProfScope ps(PROF_GEMM, flops, bytes, stream, tag);
   DV_CHECK_CUDA(launch_pdl(pbk_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, 1, ka));
   note_launch();
   return 0;
