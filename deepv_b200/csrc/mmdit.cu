@@ -743,11 +743,14 @@ static int forward_body(dv_mmdit_plan* p, const void* const* clips_dev, int io_d
     if (ph.kind == 0) return launch_ln_modulate2(ph.ln0, ph.has_ln1 ? &ph.ln1 : nullptr, ph.mod_bs, ph.B, D, ph.eps, st);
     return launch_gemm_pair(ph.g0, ph.has_g1 ? &ph.g1 : nullptr, st);
   };
-  // persistent block kernel: DV_MMDIT_PBK=0 never, =1 whenever the layout is small enough (rows per rank <=
-  // DV_PBK_MAX_ROWS, default 2048); default: on
-  static const int pbk_env = getenv("DV_MMDIT_PBK") ? atoi(getenv("DV_MMDIT_PBK")) : 1;
-  static const int pbk_max_rows = getenv("DV_PBK_MAX_ROWS") ? atoi(getenv("DV_PBK_MAX_ROWS")) : 2048;
-  const bool use_pbk = pbk_env != 0 && m->pbk_work != nullptr && B * (Lw + Lc) <= pbk_max_rows;
+  // persistent block kernel (EXPERIMENT, off by default): DV_MMDIT_PBK=1 uses it for layouts with at most
+  // DV_PBK_MAX_ROWS (default 512) rows per rank.  Correct (the parity suites pass with it) but not faster: 122 us for the
+  // six steps of the smallest block against ~120 us as six launches — a grid barrier + pipeline refill per phase costs what
+  // a dependent launch costs (profiles/r02k_summary.txt, r02l_summary.txt).  Read per call so that tests can switch it.
+  const char* pbk_s = getenv("DV_MMDIT_PBK");
+  const char* pbk_r = getenv("DV_PBK_MAX_ROWS");
+  const int pbk_max_rows = pbk_r ? atoi(pbk_r) : 512;
+  const bool use_pbk = pbk_s != nullptr && atoi(pbk_s) != 0 && m->pbk_work != nullptr && B * (Lw + Lc) <= pbk_max_rows;
   auto run_phases = [&](const PbkPhaseIn* ph, int n) -> int {
     if (use_pbk) return launch_pbk(ph, n, m->pbk_work, m->pbk_bar, st);
     for (int j = 0; j < n; ++j) {

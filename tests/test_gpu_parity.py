@@ -129,6 +129,25 @@ def test_conditioning_cache_hits_are_bit_exact(monkeypatch):
     assert lib.dv_launch_count() > n0              # (the cached forward still issues its launches; they return early)
 
 
+def test_persistent_block_kernel_matches_the_per_launch_path(monkeypatch):
+    """DV_MMDIT_PBK=1 (experimental, csrc/gemm.cu pbk_kernel): the LN / GEMM steps between two attentions as phases of one
+    launch behind grid barriers.  Same arithmetic up to the split-K re-association of the small GEMMs."""
+    from deepv_b200.mmdit import B200MMDiT
+    case = cases.MMDIT_CASES["three_block_mixed"]
+    cfg, W = weights.mmdit_weights(case["cfg"], seed=case["wseed"])
+    model = B200MMDiT(W, cfg, out_dtype=torch.float32)
+    gold = torch.load(G / "mmdit_golden.pt")["three_block_mixed"]
+    plain = _run_case(model, case)
+    monkeypatch.setenv("DV_MMDIT_PBK", "1")
+    monkeypatch.setenv("DV_PBK_MAX_ROWS", "4096")
+    fused = _run_case(model, case)
+    again = _run_case(model, case)
+    assert torch.equal(fused, again)                      # bit-reproducible
+    assert rel_max(fused, gold) <= DENOISER_TOL
+    assert rel_max(fused, plain) <= 2e-3
+    print(f"persistent block kernel: vs golden {rel_max(fused, gold):.3e}, vs per-launch path {rel_max(fused, plain):.3e}")
+
+
 def test_mmdit_full_depth_vs_oracle():
     """24 blocks (the real depth), first-unit stage-1 layout, against the fp32 oracle."""
     from deepv_b200.mmdit import B200MMDiT
