@@ -83,6 +83,7 @@ SIGNATURES = {
     "dv_conv3d_strided_cl": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dv_mmdit_create": (_i, [C.POINTER(MMDiTConfig), C.POINTER(MMDiTWeights), C.POINTER(_vp)]),
     "dv_mmdit_destroy": (None, [_vp]),
+    "dv_mmdit_debug_buffer": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_ll)]),
     "dv_mmdit_plan_create": (_i, [_vp, _i, _i, C.POINTER(_i), _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "dv_mmdit_plan_destroy": (None, [_vp]),
     "dv_mmdit_plan_workspace_bytes": (_ll, [_vp]),

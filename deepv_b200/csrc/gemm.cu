@@ -73,6 +73,7 @@ struct KArgs {
   int splits;
   int total_pair_tiles;
   int pdl_early;
+  int l2_prefetch;  // dense problems with fewer tiles than SMs: prefetch a unit's whole weight panel into L2 first
 };
 
 struct TileCoord {
@@ -752,6 +753,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           h0 = (r / a.tiles_w) * (a.swap ? 16 : 8);
           w0 = (r % a.tiles_w) * 16;
         }
+        if (k.l2_prefetch && d.a_mode == 0 && d.w_batch_stride == 0) {
+          // weight streaming from HBM is latency-bound with four 48 KB stages in flight: ask for the whole panel now
+          for (int kb = tc.kb0; kb < tc.kb1; ++kb) tma_prefetch_l2_2d(&a.tmB, kb * BK, tc.n_tile * BN);
+        }
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -1264,6 +1269,7 @@ struct PbkArgs {
   unsigned* bar;   // grid barrier counter, zero at launch
   float4* work;    // split-K partials
   int pdl_early;
+  unsigned long long* trace;  // debug (DV_PBK_TRACE): [phase + 1][CTA] globaltimer stamps, or null
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -1437,6 +1443,7 @@ __global__ void __launch_bounds__(kThreads, 1) pbk_kernel(const __grid_constant_
   const bool issuer = warp >= 2 && quarter == 0 && lane == 0;
   constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
 
+  if (k.trace != nullptr && threadIdx.x == 0) k.trace[blockIdx.x] = global_ns();
   for (int pi = 0; pi < k.n_phases; ++pi) {
     const PbkPhase& ph = k.ph[pi];
     if (ph.kind == PBK_LN) {
@@ -1449,6 +1456,8 @@ __global__ void __launch_bounds__(kThreads, 1) pbk_kernel(const __grid_constant_
             int tile = u / ph.splits;
             const Problem& a = pbk_problem(k, ph, tile);
             const TileCoord tc = decode_tile(a, tile, u % ph.splits);
+            if (units <= static_cast<int>(gridDim.x))
+              for (int kb = tc.kb0; kb < tc.kb1; ++kb) tma_prefetch_l2_2d(&a.tmB, kb * BK, tc.n_tile * BN);
             for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * kStageBytes;
@@ -1557,6 +1566,10 @@ __global__ void __launch_bounds__(kThreads, 1) pbk_kernel(const __grid_constant_
             pbk_reduce_item<EPI_RESID_GATE>(a, tc, k.work, unit0, ph.splits, slice, t);
         }
       }
+    }
+    if (k.trace != nullptr) {   // end of this CTA's work in the phase (before the barrier)
+      __syncthreads();
+      if (threadIdx.x == 0) k.trace[static_cast<long long>(pi + 1) * gridDim.x + blockIdx.x] = global_ns();
     }
     if (pi + 1 < k.n_phases) pbk_grid_sync(k.bar, epoch);
   }
@@ -1851,6 +1864,9 @@ int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar,
   ka.bar = bar;
   ka.work = reinterpret_cast<float4*>(workspace);
   ka.pdl_early = pdl_early() ? 1 : 0;
+  // DV_PBK_TRACE=1: per-phase time stamps of every CTA behind the barrier word ([kPbkMaxPhases + 1][grid] u64; the
+  // caller's `bar` buffer must then be that large — scripts/probe/pbk_trace.py)
+  ka.trace = getenv("DV_PBK_TRACE") ? reinterpret_cast<unsigned long long*>(bar) + 8 : nullptr;
   int np = 0;
   double flops = 0.0, bytes = 0.0;
   for (int i = 0; i < n; ++i) {
@@ -1981,6 +1997,8 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
     if (ka.p[i].tiles > 0) ka.p[i].kb_per_split = (ka.p[i].k_blocks + ka.splits - 1) / ka.splits;
   ka.total_tiles = ka.p[0].tiles + ka.p[1].tiles;
   ka.pdl_early = pdl_early() ? 1 : 0;
+  static const bool no_l2_prefetch = getenv("DV_GEMM_NO_L2_PREFETCH") != nullptr;
+  ka.l2_prefetch = (!no_l2_prefetch && d0.a_mode == 0 && ka.total_tiles < sm_count()) ? 1 : 0;
   if (ka.p[1].tiles == 0) ka.p[1].pair_tiles = 0;
   ka.total_pair_tiles = ka.p[0].pair_tiles + ka.p[1].pair_tiles;
   // CTA pairs (cta_group::2) once every SM pair has a 256-row tile: ~570 cycles per k-block instead

@@ -219,13 +219,21 @@ extern "C" int dv_mmdit_create(const dv_mmdit_config* cfg, const dv_mmdit_weight
     }
   }
   e = cudaMalloc(&m->pbk_work, static_cast<size_t>(pbk_workspace_floats()) * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&m->pbk_bar, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&m->pbk_bar, 64 + 16 * 160 * 8);   // barrier word (+ room for DV_PBK_TRACE stamps)
   if (e != cudaSuccess) {
     set_error("dv_mmdit_create: persistent-kernel workspace: %s", cudaGetErrorString(e));
     dv_mmdit_destroy(m);
     return DV_ERR_CUDA;
   }
   *out = m;
+  return DV_OK;
+}
+
+extern "C" int dv_mmdit_debug_buffer(dv_mmdit* m, int which, void** dev_ptr, long long* bytes) {
+  DV_REQUIRE(m && dev_ptr && bytes, "dv_mmdit_debug_buffer: null argument");
+  DV_REQUIRE(which == 0, "dv_mmdit_debug_buffer: unknown buffer %d", which);
+  *dev_ptr = m->pbk_bar;   // [0] grid-barrier word; from byte 64: DV_PBK_TRACE stamps [phase + 1][SM] u64 (globaltimer ns)
+  *bytes = 64 + 16 * 160 * 8;
   return DV_OK;
 }
 

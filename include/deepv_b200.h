@@ -147,6 +147,8 @@ typedef struct {
 
 int dv_mmdit_create(const dv_mmdit_config* cfg, const dv_mmdit_weights* w, dv_mmdit** out);
 void dv_mmdit_destroy(dv_mmdit* m);
+/* debug: which = 0 -> the persistent block kernel's barrier word + (DV_PBK_TRACE=1) per-phase time stamps of every CTA */
+int dv_mmdit_debug_buffer(dv_mmdit* m, int which, void** dev_ptr, long long* bytes);
 
 /* A plan fixes one token layout: batch, the clips of one sample (oldest
  * first, the LAST one is the noisy clip and the only one returned), context length and the
