@@ -73,7 +73,6 @@ struct KArgs {
   int splits;
   int total_pair_tiles;
   int pdl_early;
-  int l2_prefetch;  // dense problems with fewer tiles than SMs: prefetch a unit's whole weight panel into L2 first
 };
 
 struct TileCoord {
@@ -752,10 +751,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int r = tc.m_tile % per_frame;
           h0 = (r / a.tiles_w) * (a.swap ? 16 : 8);
           w0 = (r % a.tiles_w) * 16;
-        }
-        if (k.l2_prefetch && d.a_mode == 0 && d.w_batch_stride == 0) {
-          // weight streaming from HBM is latency-bound with four 48 KB stages in flight: ask for the whole panel now
-          for (int kb = tc.kb0; kb < tc.kb1; ++kb) tma_prefetch_l2_2d(&a.tmB, kb * BK, tc.n_tile * BN);
         }
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -1456,8 +1451,6 @@ __global__ void __launch_bounds__(kThreads, 1) pbk_kernel(const __grid_constant_
             int tile = u / ph.splits;
             const Problem& a = pbk_problem(k, ph, tile);
             const TileCoord tc = decode_tile(a, tile, u % ph.splits);
-            if (units <= static_cast<int>(gridDim.x))
-              for (int kb = tc.kb0; kb < tc.kb1; ++kb) tma_prefetch_l2_2d(&a.tmB, kb * BK, tc.n_tile * BN);
             for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * kStageBytes;
@@ -1997,8 +1990,6 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
     if (ka.p[i].tiles > 0) ka.p[i].kb_per_split = (ka.p[i].k_blocks + ka.splits - 1) / ka.splits;
   ka.total_tiles = ka.p[0].tiles + ka.p[1].tiles;
   ka.pdl_early = pdl_early() ? 1 : 0;
-  static const bool no_l2_prefetch = getenv("DV_GEMM_NO_L2_PREFETCH") != nullptr;
-  ka.l2_prefetch = (!no_l2_prefetch && d0.a_mode == 0 && ka.total_tiles < sm_count()) ? 1 : 0;
   if (ka.p[1].tiles == 0) ka.p[1].pair_tiles = 0;
   ka.total_pair_tiles = ka.p[0].pair_tiles + ka.p[1].pair_tiles;
   // CTA pairs (cta_group::2) once every SM pair has a 256-row tile: ~570 cycles per k-block instead
