@@ -53,6 +53,7 @@ constexpr int kPolyPer8 = DV_ATTN_POLY;    // exponentials per 8 computed on the
 
 struct AttnArgs {
   alignas(64) CUtensorMap tmQKV;  // (3*H*64, L, B) bf16, box {64, 128, 1}
+  alignas(64) CUtensorMap tmKV64; // the same tensor, box {64, 64, 1}: K / V tiles of the 64-key kernel
   __nv_bfloat16* out;             // [B][L][H*64]
   const int* kv_end;              // [L]
   const float* key_bias;          // [B][Lpad]: 0 live, -inf dead / beyond L (Lpad % 128 == 0)
@@ -65,7 +66,31 @@ struct AttnArgs {
   int n_peers, peer_Lc, peer_Lw;
   float scale_log2;               // head_dim^-0.5 * log2(e)
   int pdl_early;
+#ifdef DV_ATTN_TRACE
+  long long* trace;               // probe build only (scripts/probe/attn_trace.py): clock64 stamps of CTA (0,0,0)
+#endif
 };
+
+// probe build: stamp (role, tile j, event k) of the heaviest CTA; role 0/1 = first warp of softmax group 0/1, 2/3 = the
+// MMA thread's work for group 0/1
+#ifdef DV_ATTN_TRACE
+#define DV_TR(on, role, j, k)                                                              \
+  do {                                                                                     \
+    if ((on) && (j) < 32) a.trace[((role) * 32 + (j)) * 8 + (k)] = clock64();              \
+  } while (0)
+// per-CTA record (pipe kernel): slot k of CTA `cta` <- globaltimer; slot 0 holds the SM id
+#define DV_TC(on, cta, k)                                                                                     \
+  do {                                                                                                        \
+    if (on) a.trace[1024 + (cta) * 8 + (k)] = static_cast<long long>(global_ns());                            \
+  } while (0)
+#else
+#define DV_TR(on, role, j, k) \
+  do {                        \
+  } while (0)
+#define DV_TC(on, cta, k) \
+  do {                    \
+  } while (0)
+#endif
 
 // 2^x on the FMA pipe: round-to-nearest split x = n + f, degree-3 minimax of 2^f on [-0.5, 0.5]
 // (relative error 2e-4, below the bf16 rounding of P), exponent added as integer bits.
@@ -407,6 +432,162 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
   }
 }
 
+// ---- one key tile of one query row (shared by attn_pipe_kernel and attn_pair_kernel) ------------------------------
+// kPolyPairs of every 4 (pairs of) exponentials run on the FMA pipe (ex2_poly2) instead of the XU pipe: with one row per
+// thread the 128 MUFU.EX2 of a tile hold the XU pipe (4 lanes / clock / SM sub-partition) for 1024 cycles, which is
+// what bounds the tile once the MMA issue is out of the way (scripts/probe/attn_trace.py: exp + pack 1240 of 1900
+// cycles).  Scale-and-shift, the polynomial and the row sum use the packed fp32x2 forms (FFMA2 / FADD2).
+#ifndef DV_ATTN_POLY_PAIRS
+#define DV_ATTN_POLY_PAIRS 1
+#endif
+constexpr int kPolyPairs = DV_ATTN_POLY_PAIRS;
+
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);   // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float2 xr = __fadd2_rn(x, magic);
+  const float2 t = __fadd2_rn(xr, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(t, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.053027521818876266f, 0.053027521818876266f),
+                        make_float2(0.24221394956111908f, 0.24221394956111908f));
+  p = __ffma2_rn(p, f, make_float2(0.6935725808143616f, 0.6935725808143616f));
+  p = __ffma2_rn(p, f, make_float2(0.9999590516090393f, 0.9999590516090393f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(xr.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(xr.y) << 23)));
+}
+
+struct RowState {
+  float m_ref;   // running maximum the stored exponentials are relative to (log2 domain, lazily raised)
+  float l;       // running row sum
+};
+
+// S (fp32, this thread's KT columns at tS) -> P = 2^(s * sc - m) as bf16 over S[0, KT / 2); keeps the running maximum and
+// row sum in `st`; rescales O (64 fp32 columns at tO) when the maximum grew by more than 2^kRescaleThreshold — only
+// after `pv_bar` says the previous P V has retired (first == no previous tile).
+template <int KT>
+__device__ __forceinline__ void softmax_tile(RowState& st, uint32_t tS, uint32_t tO, bool need_mask, const float* kb_tile,
+                                             int k0, int kv_end, float sc, bool first, uint64_t* pv_bar,
+                                             uint32_t pv_parity) {
+  float s[KT];
+#pragma unroll
+  for (int c = 0; c < KT / 32; ++c) {
+    uint32_t raw[32];
+    tmem_ld_32x32(tS + c * 32, raw);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(raw[i]);
+  }
+  tmem_ld_wait();
+  if (need_mask) {
+#pragma unroll
+    for (int i4 = 0; i4 < KT / 4; ++i4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(kb_tile) + i4);
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * i4 + e;
+        const float x = s[i] + bv[e];
+        s[i] = (k0 + i < kv_end) ? x : -INFINITY;
+      }
+    }
+  }
+  // four independent maximum chains (one dependent chain of 64 three-input maxima costs ~450 cycles)
+  float mx[4];
+  constexpr int W = KT / 4;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float m = s[W * c];
+#pragma unroll
+    for (int i = 1; i < W - 1; i += 2) m = fmaxf(fmaxf(m, s[W * c + i]), s[W * c + i + 1]);
+    mx[c] = fmaxf(m, s[W * c + W - 1]);
+  }
+  const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc;
+  const bool had = st.m_ref > -INFINITY;
+  const bool grow = had ? (m_tile > st.m_ref + kRescaleThreshold) : (m_tile > -INFINITY);
+  const float m_new = grow ? m_tile : st.m_ref;
+  if (!first && __any_sync(0xffffffffu, grow && had)) {
+    // O still receives the previous P V: wait until it has retired before touching it
+    mbar_wait(pv_bar, pv_parity);
+    tc_fence_after();
+    const float alpha = (grow && had) ? ex2(st.m_ref - m_new) : 1.0f;
+#pragma unroll
+    for (int c = 0; c < kD / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(tO + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st_32x32(tO + c * 32, o);
+    }
+    st.l *= alpha;
+    tmem_st_wait();
+  }
+  st.m_ref = m_new;
+  const float neg_m = (m_new == -INFINITY) ? 0.f : -m_new;
+  const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(neg_m, neg_m);
+  float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+  for (int hlf = 0; hlf < KT / 64; ++hlf) {
+    uint32_t pk[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float2 x = __ffma2_rn(make_float2(s[hlf * 64 + 2 * i], s[hlf * 64 + 2 * i + 1]), sc2, nm2);
+      float2 e;
+      if ((i & 3) < kPolyPairs) {
+        e = ex2_poly2(x);
+      } else {
+        e.x = ex2(x.x);
+        e.y = ex2(x.y);
+      }
+      acc[i & 3] = __fadd2_rn(acc[i & 3], e);
+      pk[i] = pack_bf16x2(e.x, e.y);
+    }
+    tmem_st_32x32(tS + hlf * 32, pk);
+  }
+  const float2 a01 = __fadd2_rn(acc[0], acc[1]), a23 = __fadd2_rn(acc[2], acc[3]);
+  st.l += (a01.x + a01.y) + (a23.x + a23.y);
+}
+
+// normalise this thread's output row (64 fp32 columns at tO) and store it (Ulysses: to the owning ranks' buffers)
+__device__ __forceinline__ void store_row(const AttnArgs& a, uint32_t tO, float l_run, bool row_ok, int b, int qi, int head) {
+  float o[kD];
+#pragma unroll
+  for (int c = 0; c < kD / 32; ++c) {
+    uint32_t raw[32];
+    tmem_ld_32x32(tO + c * 32, raw);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]);
+  }
+  const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+  if (!row_ok) return;
+  uint4 q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    q[i].x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+    q[i].y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+    q[i].z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+    q[i].w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+  }
+  const int HD = a.H * kD;
+  const long long off = (static_cast<long long>(b) * a.L + qi) * HD + head * kD;
+  if (a.n_peers == 0) {
+    uint4* d4 = reinterpret_cast<uint4*>(a.out + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d4[i] = q[i];
+  } else if (qi >= a.peer_Lc) {  // a video row: straight into its owner's buffer (NVLink store)
+    uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[(qi - a.peer_Lc) / a.peer_Lw] + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d4[i] = q[i];
+  } else {                       // a context row: every rank continues the replicated stream
+    for (int p = 0; p < a.n_peers; ++p) {
+      uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[p] + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d4[i] = q[i];
+    }
+  }
+}
+
 // =====================================================================================================
 // attn_pipe_kernel — the DEFAULT since round 2 (DV_ATTN_PIPE=0 selects attn_kernel above): all GPU suites (kernel,
 // model-level parity, sharding, rollout, boundary) pass with it; attention time of a rollout 306 -> 265 ms, B3 / L2237
@@ -414,23 +595,28 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_kernel(const __grid_cons
 // one CTA per SM with TWO S buffers in tensor memory.  The MMA warp issues S_{j+1} = Q K_{j+1}^T before
 // O += P_j V_j, so the softmax warps find the next scores ready when they finish a tile and have the XU
 // pipe to themselves; the price is 512 TMEM columns (one CTA per SM) and a 4-stage K/V ring.
-//   TMEM: S0 [0,128)  S1 [128,256)  O [256,320)  l [320,336)  Q [336,368);  P_j aliases S_{j&1}[0,64)
+//   TMEM: S0 [0,128)  S1 [128,256)  O [256,320)  Q [320,352);  P_j aliases S_{j&1}[0,64).  Row sums stay in registers.
 //   order on the tensor pipe: S0, S1, (P0V0, S2), (P1V1, S3), ...  — in order, so S_{j+2} may overwrite P_j
 //   lazy rescale of O / l (rare path) first waits for pv_done(j-1): P_{j-1} V_{j-1} has retired.
 // =====================================================================================================
 constexpr int kPipeStages = 4;
-constexpr uint32_t kPipeTmemCols = 512;
-constexpr uint32_t kPColS = 0, kPColO = 256, kPColL = 320, kPColQ = 336;
-constexpr int kPipeSmemBytes = kTileBytes + kPipeStages * 2 * kTileBytes + kOnesBytes + 256 + 1024;
+constexpr uint32_t kPipeTmemCols = 512;   // (the pair kernel's allocation; the pipe kernel takes 4 * KT)
+constexpr int pipe_smem_bytes(int KT) { return kTileBytes + kPipeStages * 2 * KT * 128 + 256 + 1024; }
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid_constant__ AttnArgs a) {
+// KT = keys per inner tile.  KT = 128: one CTA per SM (512 TMEM columns).  KT = 64: S0 [0,64) S1 [64,128) O [128,192)
+// Q [192,224) = 256 columns and 82 KB of shared memory, so TWO CTAs share an SM: a second softmax warp on every
+// scheduler to fill the dependency stalls of the first (one warp per scheduler issues at ~0.4 IPC), and a CTA's
+// prologue / epilogue hidden behind its neighbour's main loop.
+template <int KT>
+__global__ void __launch_bounds__(kAttnThreads, KT == 64 ? 2 : 1) attn_pipe_kernel(const __grid_constant__ AttnArgs a) {
+  constexpr uint32_t kPColS = 0, kPColO = 2 * KT, kPColQ = 2 * KT + 64, kCols = 4 * KT;
+  constexpr int kStageBytes = 2 * KT * 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + kTileBytes;
-  uint8_t* sOnes = sKV + kPipeStages * 2 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kPipeStages * kStageBytes);
   uint64_t* q_full = bars;
   uint64_t* q_ready = bars + 1;
   uint64_t* kv_full = bars + 2;                  // [kPipeStages]
@@ -448,10 +634,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
   const int head = a.head0 + static_cast<int>(blockIdx.x);
   const int b = blockIdx.y;
   const int last_q = min(q0 + kTile, a.L) - 1;
-  const int n_kv = (__ldg(a.kv_end + last_q) + kTile - 1) / kTile;
+  const int n_kv = (__ldg(a.kv_end + last_q) + KT - 1) / KT;
+#ifdef DV_ATTN_TRACE
+  const bool tr_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  const bool tc = threadIdx.x == 64;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (tc && cta < 8192) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.trace[1024 + cta * 8] = smid;
+  }
+  DV_TC(tc, cta, 1);   // entry
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmQKV);
+    if (KT != 128) tma_prefetch_desc(&a.tmKV64);
     mbar_init(q_full, 1);
     mbar_init(q_ready, 128);
     for (int i = 0; i < kPipeStages; ++i) {
@@ -466,10 +664,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kPipeTmemCols>(tmem_slot);
-  for (int i = threadIdx.x; i < kOnesBytes / 4; i += kAttnThreads)
-    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
-  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc<kCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -477,56 +672,58 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
   const int HD = a.H * kD;
   pdl_wait();
   if (a.pdl_early) pdl_trigger();
+  DV_TC(tc, cta, 2);   // set up (barriers, tensor memory), predecessor's data visible
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_3d(&a.tmQKV, q_full, sQ, head * kD, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kPipeStages;
-        const uint32_t ph = (j / kPipeStages) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t* sK = sKV + s * 2 * kTileBytes;
-        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
-        tma_load_3d(&a.tmQKV, &kv_full[s], sK, HD + head * kD, j * kTile, b);
-        tma_load_3d(&a.tmQKV, &kv_full[s], sK + kTileBytes, 2 * HD + head * kD, j * kTile, b);
-      }
+    // whole warp, converged: the w_ forms elect one lane and keep their operands in uniform registers
+    w_mbar_expect_tx(q_full, kTileBytes);
+    w_tma_load_3d(&a.tmQKV, q_full, sQ, head * kD, q0, b);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j % kPipeStages;
+      const uint32_t ph = (j / kPipeStages) & 1;
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      uint8_t* sK = sKV + s * kStageBytes;
+      const CUtensorMap* tm = KT == 128 ? &a.tmQKV : &a.tmKV64;
+      w_mbar_expect_tx(&kv_full[s], kStageBytes);
+      w_tma_load_3d(tm, &kv_full[s], sK, HD + head * kD, j * KT, b);
+      w_tma_load_3d(tm, &kv_full[s], sK + kStageBytes / 2, 2 * HD + head * kD, j * KT, b);
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_kv > 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    if (n_kv > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KT, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 0);
-      const uint32_t tO = tmem_base + kPColO, tL = tmem_base + kPColL, tQ = tmem_base + kPColQ;
-      const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
+      const uint32_t tO = tmem_base + kPColO, tQ = tmem_base + kPColQ;
       auto issue_s = [&](int j) {
         mbar_wait(&kv_full[j % kPipeStages], (j / kPipeStages) & 1);
         tc_fence_after();
-        const uint32_t tS = tmem_base + kPColS + (j & 1) * 128;
-        const uint32_t aK = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes);
+        const uint32_t tS = tmem_base + kPColS + (j & 1) * KT;
+        const uint32_t aK = smem_u32(sKV + (j % kPipeStages) * kStageBytes);
         const uint64_t dk = umma_desc_sw128(aK, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ts(tS, tQ + k * 8, dk + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
+        for (int k = 0; k < kD / 16; ++k) w_umma_bf16_ts(tS, tQ + k * 8, dk + 2 * k, idesc_s, k != 0);
+        w_umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_ready, 0);
       issue_s(0);
       if (n_kv > 1) issue_s(1);
       for (int j = 0; j < n_kv; ++j) {
+        DV_TR(tr_cta, 2, j, 0);
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in TMEM (and O / l rescaled if the max grew)
         tc_fence_after();
-        const uint32_t tP = tmem_base + kPColS + (j & 1) * 128;
-        const uint32_t aV = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes) + kTileBytes;
+        DV_TR(tr_cta, 2, j, 1);
+        const uint32_t tP = tmem_base + kPColS + (j & 1) * KT;
+        const uint32_t aV = smem_u32(sKV + (j % kPipeStages) * kStageBytes) + kStageBytes / 2;
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
+        for (int k = 0; k < KT / 16; ++k) {
           const uint64_t dv = umma_desc_sw128(aV + k * 2048, 1024, 1024);
-          umma_bf16_ts(tO, tP + k * 8, dv, idesc_pv, (j | k) != 0);
-          umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, (j | k) != 0);
+          w_umma_bf16_ts(tO, tP + k * 8, dv, idesc_pv, (j | k) != 0);
         }
-        umma_commit(&kv_empty[j % kPipeStages]);
-        umma_commit(pv_done);
+        w_umma_commit(&kv_empty[j % kPipeStages]);
+        w_umma_commit(pv_done);
+        DV_TR(tr_cta, 2, j, 2);
         if (j + 2 < n_kv) issue_s(j + 2);  // in order behind P_j V_j: S_{j+2} may overwrite P_j
-        if (j + 1 == n_kv) umma_commit(o_done);
+        if (j + 1 == n_kv) w_umma_commit(o_done);
+        DV_TR(tr_cta, 2, j, 3);
       }
     }
   } else {
@@ -536,7 +733,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
     const bool row_ok = qi < a.L;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tO = tmem_base + kPColO + lane_addr;
-    const uint32_t tL = tmem_base + kPColL + lane_addr;
     if (n_kv > 0) {
       mbar_wait(q_full, 0);
       {
@@ -559,122 +755,34 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
       const int kv_end_min = __ldg(a.kv_end + q0);
       const float* kb = a.key_bias + static_cast<long long>(b) * a.Lpad;
       const float sc = a.scale_log2;
-      float m_ref = -INFINITY;
+      RowState st = {-INFINITY, 0.f};
+      DV_TC(tc, cta, 3);   // Q parked in tensor memory
       const int* dead_row = a.tile_dead ? a.tile_dead + b * (a.Lpad / kTile) : nullptr;
       for (int j = 0; j < n_kv; ++j) {
-        const int k0 = j * kTile;
-        const uint32_t tS = tmem_base + kPColS + (j & 1) * 128 + lane_addr;
-        const bool need_mask = (k0 + kTile > kv_end_min) || (dead_row == nullptr) || (__ldg(dead_row + j) != 0);
+        const int k0 = j * KT;
+        const uint32_t tS = tmem_base + kPColS + (j & 1) * KT + lane_addr;
+        const bool need_mask = (k0 + KT > kv_end_min) || (dead_row == nullptr) || (__ldg(dead_row + k0 / kTile) != 0);
+#ifdef DV_ATTN_TRACE
+        const bool tr = tr_cta && warp == 2;
+#endif
+        DV_TR(tr, 0, j, 0);
         mbar_wait(&s_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        float s[kTile];
-#pragma unroll
-        for (int c = 0; c < kTile / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(tS + c * 32, raw);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(raw[i]);
-        }
-        tmem_ld_wait();
-        float m_tile = -INFINITY;
-        if (need_mask) {
-#pragma unroll
-          for (int i4 = 0; i4 < kTile / 4; ++i4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(kb + k0) + i4);
-            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = 4 * i4 + e;
-              float x = s[i] + bv[e];
-              x = (k0 + i < kv_end) ? x : -INFINITY;
-              s[i] = x;
-              m_tile = fmaxf(m_tile, x);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < kTile; ++i) m_tile = fmaxf(m_tile, s[i]);
-        }
-        m_tile *= sc;
-        const bool had = m_ref > -INFINITY;
-        const bool grow = had ? (m_tile > m_ref + kRescaleThreshold) : (m_tile > -INFINITY);
-        const float m_new = grow ? m_tile : m_ref;
-        if (j > 0 && __any_sync(0xffffffffu, grow && had)) {
-          // O and l still receive P_{j-1} V_{j-1}: wait until it has retired before touching them
-          mbar_wait(pv_done, (j - 1) & 1);
-          tc_fence_after();
-          const float alpha = (grow && had) ? ex2(m_ref - m_new) : 1.0f;
-#pragma unroll
-          for (int c = 0; c < kD / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(tO + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(tO + c * 32, o);
-          }
-          const uint32_t lv = tmem_ld_1(tL);
-          tmem_ld_wait();
-          tmem_st_1(tL, __float_as_uint(__uint_as_float(lv) * alpha));
-          tmem_st_wait();
-        }
-        m_ref = m_new;
-        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x0 = fmaf(s[hlf * 64 + 2 * i], sc, neg_m);
-            const float x1 = fmaf(s[hlf * 64 + 2 * i + 1], sc, neg_m);
-            pk[i] = pack_bf16x2(ex2(x0), ex2(x1));
-          }
-          tmem_st_32x32(tS + hlf * 32, pk);
-        }
+        DV_TR(tr, 0, j, 1);
+        if (j == 0) DV_TC(tc, cta, 4);   // first scores ready
+        softmax_tile<KT>(st, tS, tO, need_mask, kb + k0, k0, kv_end, sc, j == 0, pv_done, (j - 1) & 1);
+        DV_TR(tr, 0, j, 4);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[j & 1]);
+        DV_TR(tr, 0, j, 5);
       }
 
+      DV_TC(tc, cta, 5);   // last P handed over
       mbar_wait(o_done, 0);
       tc_fence_after();
-      const float l_run = __uint_as_float(tmem_ld_1(tL));
-      float o[kD];
-#pragma unroll
-      for (int c = 0; c < kD / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tO + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]);
-      }
-      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-      if (row_ok) {
-        uint4 q[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          q[i].x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-          q[i].y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-          q[i].z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-          q[i].w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-        }
-        const long long off = (static_cast<long long>(b) * a.L + qi) * HD + head * kD;
-        if (a.n_peers == 0) {
-          uint4* d4 = reinterpret_cast<uint4*>(a.out + off);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d4[i] = q[i];
-        } else if (qi >= a.peer_Lc) {
-          uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[(qi - a.peer_Lc) / a.peer_Lw] + off);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d4[i] = q[i];
-        } else {
-          for (int p = 0; p < a.n_peers; ++p) {
-            uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[p] + off);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d4[i] = q[i];
-          }
-        }
-      }
+      store_row(a, tO, st.l, row_ok, b, qi, head);
+      DV_TC(tc, cta, 6);   // row stored
     }
   }
 
@@ -683,76 +791,82 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_pipe_kernel(const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kPipeTmemCols>(tmem_base);
+    tmem_dealloc<kCols>(tmem_base);
   }
+  DV_TC(tc, cta, 7);   // exit
 }
 
 // =====================================================================================================
-// attn_pipe2_kernel (round 2, EXPERIMENT, DV_ATTN_PIPE=2, not the default: measured 28 % slower than one group — 320
-// threads cap the kernel at 168 registers (spills in the softmax loop) and the second group's TMEM traffic competes with
-// the MMAs' TMEM operands): the pipelined kernel above with TWO softmax groups of four warps.  Group g takes the key
-// tiles j = g, g + 2, ... into S buffer g and keeps its OWN running maximum, row sums and output accumulator
-// (O_g, l_g in tensor memory), so the groups never exchange anything inside the loop: while one waits for its TMEM
-// round trip or for P_j V_j + S_{j+2} on the tensor pipe, the other keeps the XU pipe (ex2) busy.  At the end group 1
-// parks its maxima in shared memory and group 0 merges the two partial softmaxes
-//     m = max(m0, m1),  O = 2^(m0-m) O0 + 2^(m1-m) O1,  l likewise
-// and stores.  TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) l0 [384,400) l1 [400,416) Q [416,448).
+// attn_pair_kernel (round 2, DV_ATTN_PIPE=2): TWO query tiles (256 rows) of one head per CTA, one softmax warpgroup
+// each, sharing every K/V tile.  While group g waits for O_g += P_g V_j and S_g = Q_g K_{j+1}^T on the tensor pipe the
+// other group has the XU pipe (ex2) to itself, and each K/V tile is fetched once for 256 queries instead of 128.  The
+// register file is re-partitioned with setmaxnreg: the two softmax warpgroups (one row of S = 128 fp32 per thread) grow
+// to 232 registers, the warpgroup that holds the TMA and MMA warps shrinks to 40 — the first two-group attempt
+// (attn_pipe2, groups on alternate key tiles of the SAME query tile, 320 threads at the 168-register cap, partial
+// results merged at the end) spilled in the softmax loop and measured 28 % slower than one group (profiles/r02h_summary.txt).
+//   warps 0-3   softmax of rows q0 + [0, 128)       warps 4-7   softmax of rows q0 + [128, 256)
+//   warp 8      TMA producer (Q0, Q1, then K_j / V_j into a 4-stage ring)      warp 9   MMA issuer     warps 10, 11 idle
+//   TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) Q0 [384,416) Q1 [416,448); P_g aliases S_g[0,64); the row
+//   sums stay in registers.  Tensor-pipe order: S0(0) S1(0) | PV0(j) S0(j+1) PV1(j) S1(j+1) | ... — in order, so
+//   S_g(j+1) may overwrite P_g(j).  The second tile sees at least as many keys as the first (kv_end is non-decreasing);
+//   a tile beyond L takes no part.
 // =====================================================================================================
-constexpr int kPipe2Threads = 64 + 2 * 128;
-constexpr uint32_t kP2ColS = 0, kP2ColO = 256, kP2ColL = 384, kP2ColQ = 416;
-constexpr int kPipe2SmemBytes = kTileBytes + kPipeStages * 2 * kTileBytes + kOnesBytes + 256 + 512 + 1024;
+constexpr int kPairThreads = 384;
+constexpr uint32_t kQColS = 0, kQColO = 256, kQColQ = 384;
+constexpr int kPairSmemBytes = 2 * kTileBytes + kPipeStages * 2 * kTileBytes + 256 + 1024;
 
-__global__ void __launch_bounds__(kPipe2Threads, 1) attn_pipe2_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __launch_bounds__(kPairThreads, 1) attn_pair_kernel(const __grid_constant__ AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + kTileBytes;
-  uint8_t* sOnes = sKV + kPipeStages * 2 * kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes);
-  uint64_t* q_full = bars;
-  uint64_t* q_ready = bars + 1;
-  uint64_t* kv_full = bars + 2;                  // [kPipeStages]
+  uint8_t* sQ = smem;                            // two tiles
+  uint8_t* sKV = sQ + 2 * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kPipeStages * 2 * kTileBytes);
+  uint64_t* q_full = bars;                       // [2]
+  uint64_t* q_ready = bars + 2;                  // [2] (128 arrivals)
+  uint64_t* kv_full = bars + 4;                  // [kPipeStages]
   uint64_t* kv_empty = kv_full + kPipeStages;    // [kPipeStages]
-  uint64_t* s_full = kv_empty + kPipeStages;     // [2]: S_j ready in buffer j & 1
-  uint64_t* p_full = s_full + 2;                 // [2]: P_j written over buffer j & 1 (128 arrivals)
-  uint64_t* pv_done = p_full + 2;                // [2]: P_j V_j retired, per softmax group (one phase per tile of the group)
-  uint64_t* o_done = pv_done + 2;
-  uint64_t* m_ready = o_done + 1;                // group 1 parked its running maxima (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(m_ready + 1);
-  float* sM = reinterpret_cast<float*>(bars + 32);  // [128] running maxima of group 1
+  uint64_t* s_full = kv_empty + kPipeStages;     // [2]: S_g(j) ready
+  uint64_t* p_full = s_full + 2;                 // [2]: P_g(j) written over S_g (128 arrivals)
+  uint64_t* pv_done = p_full + 2;                // [2]: P_g(j) V_j retired (one phase per tile)
+  uint64_t* o_done = pv_done + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
   const int qt = static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z);
-  const int q0 = qt * kTile;
+  const int q0 = qt * 2 * kTile;
   const int head = a.head0 + static_cast<int>(blockIdx.x);
   const int b = blockIdx.y;
-  const int last_q = min(q0 + kTile, a.L) - 1;
-  const int n_kv = (__ldg(a.kv_end + last_q) + kTile - 1) / kTile;
+  int n_kv[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int first = q0 + g * kTile;
+    n_kv[g] = first < a.L ? (__ldg(a.kv_end + min(first + kTile, a.L) - 1) + kTile - 1) / kTile : 0;
+  }
+  const int n_max = max(n_kv[0], n_kv[1]);
+#ifdef DV_ATTN_TRACE
+  const bool tr_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&a.tmQKV);
-    mbar_init(q_full, 1);
-    mbar_init(q_ready, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_ready[i], 128);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_done[i], 1);
+    }
     for (int i = 0; i < kPipeStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-    }
-    mbar_init(&pv_done[0], 1);
-    mbar_init(&pv_done[1], 1);
-    mbar_init(o_done, 1);
-    mbar_init(m_ready, 128);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kPipeTmemCols>(tmem_slot);
-  for (int i = threadIdx.x; i < kOnesBytes / 4; i += kPipe2Threads)
-    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
-  fence_proxy_async_smem();
+  if (warp == 9) tmem_alloc<kPipeTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -761,73 +875,85 @@ __global__ void __launch_bounds__(kPipe2Threads, 1) attn_pipe2_kernel(const __gr
   pdl_wait();
   if (a.pdl_early) pdl_trigger();
 
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_3d(&a.tmQKV, q_full, sQ, head * kD, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
+  if (wg == 2) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 8) {
+      // whole warp, converged: the w_ forms elect one lane and keep their operands in uniform registers
+      for (int g = 0; g < 2; ++g)
+        if (n_kv[g] > 0) {
+          w_mbar_expect_tx(&q_full[g], kTileBytes);
+          w_tma_load_3d(&a.tmQKV, &q_full[g], sQ + g * kTileBytes, head * kD, q0 + g * kTile, b);
+        }
+      for (int j = 0; j < n_max; ++j) {
         const int s = j % kPipeStages;
         const uint32_t ph = (j / kPipeStages) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* sK = sKV + s * 2 * kTileBytes;
-        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
-        tma_load_3d(&a.tmQKV, &kv_full[s], sK, HD + head * kD, j * kTile, b);
-        tma_load_3d(&a.tmQKV, &kv_full[s], sK + kTileBytes, 2 * HD + head * kD, j * kTile, b);
+        w_mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
+        w_tma_load_3d(&a.tmQKV, &kv_full[s], sK, HD + head * kD, j * kTile, b);
+        w_tma_load_3d(&a.tmQKV, &kv_full[s], sK + kTileBytes, 2 * HD + head * kD, j * kTile, b);
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && n_kv > 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
-      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 0);
-      const uint32_t tQ = tmem_base + kP2ColQ;
-      const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
-      auto issue_s = [&](int j) {
-        mbar_wait(&kv_full[j % kPipeStages], (j / kPipeStages) & 1);
-        tc_fence_after();
-        const uint32_t tS = tmem_base + kP2ColS + (j & 1) * 128;
-        const uint32_t aK = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes);
-        const uint64_t dk = umma_desc_sw128(aK, 16, 1024);
+    } else if (warp == 9) {
+      if (n_max > 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);
+        auto issue_s = [&](int g, int j) {
+          mbar_wait(&kv_full[j % kPipeStages], (j / kPipeStages) & 1);
+          tc_fence_after();
+          const uint32_t tS = tmem_base + kQColS + g * 128;
+          const uint32_t tQ = tmem_base + kQColQ + g * 32;
+          const uint64_t dk = umma_desc_sw128(smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ts(tS, tQ + k * 8, dk + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_ready, 0);
-      issue_s(0);
-      if (n_kv > 1) issue_s(1);
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);  // P_j in TMEM (and O / l rescaled if the max grew)
-        tc_fence_after();
-        const uint32_t tP = tmem_base + kP2ColS + (j & 1) * 128;
-        const uint32_t tO = tmem_base + kP2ColO + (j & 1) * 64, tL = tmem_base + kP2ColL + (j & 1) * 16;
-        const uint32_t aV = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes) + kTileBytes;
+          for (int k = 0; k < kD / 16; ++k) w_umma_bf16_ts(tS, tQ + k * 8, dk + 2 * k, idesc_s, k != 0);
+          w_umma_commit(&s_full[g]);
+        };
+        for (int g = 0; g < 2; ++g)
+          if (n_kv[g] > 0) {
+            mbar_wait(&q_ready[g], 0);
+            issue_s(g, 0);
+          }
+        for (int j = 0; j < n_max; ++j) {
+          for (int g = 0; g < 2; ++g) {
+            if (j >= n_kv[g]) continue;
+            DV_TR(tr_cta, 2 + g, j, 0);
+            mbar_wait(&p_full[g], j & 1);  // P_g(j) in TMEM (and O_g / l_g rescaled if the max grew)
+            tc_fence_after();
+            DV_TR(tr_cta, 2 + g, j, 1);
+            const uint32_t tP = tmem_base + kQColS + g * 128;
+            const uint32_t tO = tmem_base + kQColO + g * 64;
+            const uint32_t aV = smem_u32(sKV + (j % kPipeStages) * 2 * kTileBytes) + kTileBytes;
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
-          const uint64_t dv = umma_desc_sw128(aV + k * 2048, 1024, 1024);
-          umma_bf16_ts(tO, tP + k * 8, dv, idesc_pv, ((j >> 1) | k) != 0);   // tiles 0 and 1 start their group's O / l
-          umma_bf16_ts(tL, tP + k * 8, d_ones, idesc_l, ((j >> 1) | k) != 0);
+            for (int k = 0; k < kTile / 16; ++k) {
+              const uint64_t dv = umma_desc_sw128(aV + k * 2048, 1024, 1024);
+              w_umma_bf16_ts(tO, tP + k * 8, dv, idesc_pv, (j | k) != 0);
+            }
+            if (g == 1 || j >= n_kv[1]) w_umma_commit(&kv_empty[j % kPipeStages]);  // the last reader of K_j / V_j
+            w_umma_commit(&pv_done[g]);
+            DV_TR(tr_cta, 2 + g, j, 2);
+            if (j + 1 < n_kv[g]) issue_s(g, j + 1);   // in order behind P_g(j) V_j: S_g(j+1) may overwrite P_g(j)
+            else w_umma_commit(&o_done[g]);
+            DV_TR(tr_cta, 2 + g, j, 3);
+          }
         }
-        umma_commit(&kv_empty[j % kPipeStages]);
-        umma_commit(&pv_done[j & 1]);
-        if (j + 2 < n_kv) issue_s(j + 2);  // in order behind P_j V_j: S_{j+2} may overwrite P_j
-        if (j + 1 == n_kv) umma_commit(o_done);
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = wg;
+    const int n_g = n_kv[g];
     const int quarter = warp & 3;
-    const int grp = (warp - 2) >> 2;   // softmax group: tiles j = grp, grp + 2, ... with its own running max, O and l
     const int r = quarter * 32 + lane;
-    const int qi = q0 + r;
+    const int qbase = q0 + g * kTile;
+    const int qi = qbase + r;
     const bool row_ok = qi < a.L;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tO = tmem_base + kP2ColO + grp * 64 + lane_addr;
-    const uint32_t tL = tmem_base + kP2ColL + grp * 16 + lane_addr;
-    if (n_kv > 0) {
-      if (grp == 0) {
-      mbar_wait(q_full, 0);
+    const uint32_t tS = tmem_base + kQColS + g * 128 + lane_addr;
+    const uint32_t tO = tmem_base + kQColO + g * 64 + lane_addr;
+    if (n_g > 0) {
+      mbar_wait(&q_full[g], 0);
       {
         uint32_t qr[32];
-        const uint8_t* row = sQ + (r >> 3) * 1024 + (r & 7) * 128;
+        const uint8_t* row = sQ + g * kTileBytes + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 t = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
@@ -836,170 +962,62 @@ __global__ void __launch_bounds__(kPipe2Threads, 1) attn_pipe2_kernel(const __gr
           qr[4 * c + 2] = t.z;
           qr[4 * c + 3] = t.w;
         }
-        tmem_st_32x32(tmem_base + kP2ColQ + lane_addr, qr);
+        tmem_st_32x32(tmem_base + kQColQ + g * 32 + lane_addr, qr);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(q_ready);
-      }
+        mbar_arrive(&q_ready[g]);
       }
       const int kv_end = row_ok ? __ldg(a.kv_end + qi) : 0;
-      const int kv_end_min = __ldg(a.kv_end + q0);
+      const int kv_end_min = __ldg(a.kv_end + qbase);
       const float* kb = a.key_bias + static_cast<long long>(b) * a.Lpad;
       const float sc = a.scale_log2;
-      float m_ref = -INFINITY;
+      RowState st = {-INFINITY, 0.f};
       const int* dead_row = a.tile_dead ? a.tile_dead + b * (a.Lpad / kTile) : nullptr;
-      for (int j = grp; j < n_kv; j += 2) {
+      for (int j = 0; j < n_g; ++j) {
         const int k0 = j * kTile;
-        const uint32_t tS = tmem_base + kP2ColS + grp * 128 + lane_addr;
         const bool need_mask = (k0 + kTile > kv_end_min) || (dead_row == nullptr) || (__ldg(dead_row + j) != 0);
-        mbar_wait(&s_full[grp], (j >> 1) & 1);
+#ifdef DV_ATTN_TRACE
+        const bool tr = tr_cta && quarter == 0;
+#endif
+        DV_TR(tr, g, j, 0);
+        mbar_wait(&s_full[g], j & 1);
         tc_fence_after();
-        float s[kTile];
-#pragma unroll
-        for (int c = 0; c < kTile / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(tS + c * 32, raw);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(raw[i]);
-        }
-        tmem_ld_wait();
-        float m_tile = -INFINITY;
-        if (need_mask) {
-#pragma unroll
-          for (int i4 = 0; i4 < kTile / 4; ++i4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(kb + k0) + i4);
-            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = 4 * i4 + e;
-              float x = s[i] + bv[e];
-              x = (k0 + i < kv_end) ? x : -INFINITY;
-              s[i] = x;
-              m_tile = fmaxf(m_tile, x);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < kTile; ++i) m_tile = fmaxf(m_tile, s[i]);
-        }
-        m_tile *= sc;
-        const bool had = m_ref > -INFINITY;
-        const bool grow = had ? (m_tile > m_ref + kRescaleThreshold) : (m_tile > -INFINITY);
-        const float m_new = grow ? m_tile : m_ref;
-        if (j > 1 && __any_sync(0xffffffffu, grow && had)) {
-          // O and l of this group still receive P_{j-2} V_{j-2}: wait until it has retired before touching them
-          mbar_wait(&pv_done[grp], ((j >> 1) - 1) & 1);
-          tc_fence_after();
-          const float alpha = (grow && had) ? ex2(m_ref - m_new) : 1.0f;
-#pragma unroll
-          for (int c = 0; c < kD / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(tO + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(tO + c * 32, o);
-          }
-          const uint32_t lv = tmem_ld_1(tL);
-          tmem_ld_wait();
-          tmem_st_1(tL, __float_as_uint(__uint_as_float(lv) * alpha));
-          tmem_st_wait();
-        }
-        m_ref = m_new;
-        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x0 = fmaf(s[hlf * 64 + 2 * i], sc, neg_m);
-            const float x1 = fmaf(s[hlf * 64 + 2 * i + 1], sc, neg_m);
-            pk[i] = pack_bf16x2(ex2(x0), ex2(x1));
-          }
-          tmem_st_32x32(tS + hlf * 32, pk);
-        }
+        DV_TR(tr, g, j, 1);
+        softmax_tile<kTile>(st, tS, tO, need_mask, kb + k0, k0, kv_end, sc, j == 0, &pv_done[g], (j - 1) & 1);
+        DV_TR(tr, g, j, 4);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[grp]);
+        mbar_arrive(&p_full[g]);
+        DV_TR(tr, g, j, 5);
       }
 
-      if (grp == 1) {
-        // hand this group's running maxima to group 0, which merges the two partial results
-        sM[r] = m_ref;
-        mbar_arrive(m_ready);   // (release: the store above is visible to the waiter)
-      } else {
-      mbar_wait(o_done, 0);
+      mbar_wait(&o_done[g], 0);
       tc_fence_after();
-      float l_run = __uint_as_float(tmem_ld_1(tL));
-      float o[kD];
-#pragma unroll
-      for (int c = 0; c < kD / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tO + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(raw[i]);
-      }
-      if (n_kv > 1) {
-        // (m0, l0, O0) + (m1, l1, O1): both relative to their own running maxima (log2 domain)
-        mbar_wait(m_ready, 0);
-        const float m1 = sM[r];
-        const float m = fmaxf(m_ref, m1);
-        const float a0 = (m_ref == -INFINITY) ? 0.f : ex2(m_ref - m);
-        const float a1 = (m1 == -INFINITY) ? 0.f : ex2(m1 - m);
-        const float l1 = __uint_as_float(tmem_ld_1(tL + 16));
-        tmem_ld_wait();
-        l_run = a0 * l_run + a1 * l1;
-#pragma unroll
-        for (int c = 0; c < kD / 32; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(tO + 64 + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = a0 * o[c * 32 + i] + a1 * __uint_as_float(raw[i]);
-        }
-      }
-      const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
-      if (row_ok) {
-        uint4 q[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          q[i].x = pack_bf16x2(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-          q[i].y = pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-          q[i].z = pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-          q[i].w = pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-        }
-        const long long off = (static_cast<long long>(b) * a.L + qi) * HD + head * kD;
-        if (a.n_peers == 0) {
-          uint4* d4 = reinterpret_cast<uint4*>(a.out + off);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d4[i] = q[i];
-        } else if (qi >= a.peer_Lc) {
-          uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[(qi - a.peer_Lc) / a.peer_Lw] + off);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d4[i] = q[i];
-        } else {
-          for (int p = 0; p < a.n_peers; ++p) {
-            uint4* d4 = reinterpret_cast<uint4*>(a.out_peer[p] + off);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d4[i] = q[i];
-          }
-        }
-      }
-      }  // group 0
+      store_row(a, tO, st.l, row_ok, b, qi, head);
     }
   }
 
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<kPipeTmemCols>(tmem_base);
   }
 }
 
 }  // namespace
+
+#ifdef DV_ATTN_TRACE
+long long* g_attn_trace = nullptr;
+extern "C" long long* dv_attn_trace_buffer() {
+  if (!g_attn_trace) {
+    cudaMalloc(&g_attn_trace, (1024 + 8 * 8192) * sizeof(long long));
+    cudaMemset(g_attn_trace, 0, (1024 + 8 * 8192) * sizeof(long long));
+  }
+  return g_attn_trace;
+}
+#endif
 
 int launch_attention(const void* qkv, void* out, const int* kv_end, const float* key_bias,
                      const int* tile_dead, int B, int L, int Lpad, int H, cudaStream_t stream,
@@ -1016,6 +1034,18 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
   uint32_t box[3] = {64, 128, 1};
   int rc = make_tensor_map_bf16(&a.tmQKV, qkv, 3, dims, strides, box, 1);
   if (rc) return rc;
+  // DV_ATTN_PIPE: 0 = round-1 kernel, 1 = pipelined kernel, 128-key tiles, one CTA per SM, 2 = two query tiles per CTA
+  // (attn_pair_kernel), 3 = pipelined kernel, 64-key tiles, two CTAs per SM
+  // (the default: 291 us over four rollout layouts against 367 us for mode 1 and 352 us for mode 2, scripts/probe/attn_time.py,
+  // profiles/r02p_attn_modes.txt)
+  static const int pipe_mode = getenv("DV_ATTN_PIPE") != nullptr ? atoi(getenv("DV_ATTN_PIPE")) : 3;
+  if (pipe_mode == 3) {
+    uint32_t box64[3] = {64, 64, 1};
+    rc = make_tensor_map_bf16(&a.tmKV64, qkv, 3, dims, strides, box64, 1);
+    if (rc) return rc;
+  } else {
+    a.tmKV64 = a.tmQKV;
+  }
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.kv_end = kv_end;
   a.key_bias = key_bias;
@@ -1033,31 +1063,41 @@ int launch_attention(const void* qkv, void* out, const int* kv_end, const float*
     a.out_peer[i] = (out_peers && i < n_peers) ? reinterpret_cast<__nv_bfloat16*>(out_peers[i]) : nullptr;
   a.scale_log2 = 0.125f * 1.4426950408889634f;
   a.pdl_early = pdl_early() ? 1 : 0;
-  // double-buffered-S kernel (one CTA per SM, QK^T of tile j+1 issued before PV of tile j) is the default since
-  // round 2: all GPU suites pass with it, attention time of a C2 step 16.8 -> 14.6 ms (profiles/r02a_summary.txt);
-  // DV_ATTN_PIPE=0 selects the round-1 kernel (two CTAs per SM, S overwritten by P)
-  // DV_ATTN_PIPE: 0 = round-1 kernel, 1 (default) = pipelined kernel with one softmax group, 2 = two softmax groups
-  // (correct — all suites pass — but measured slower: 236 vs 184 us at B3 L2237, profiles/r02h_summary.txt)
-  static const int pipe_mode = getenv("DV_ATTN_PIPE") != nullptr ? atoi(getenv("DV_ATTN_PIPE")) : 1;
+#ifdef DV_ATTN_TRACE
+  a.trace = dv_attn_trace_buffer();
+  if (a.tile_dead == nullptr) {   // the probe calls dv_attention (no dead-tile table): use an all-live one, as a forward has
+    static int* zeros = nullptr;
+    if (!zeros) {
+      cudaMalloc(&zeros, 65536 * sizeof(int));
+      cudaMemset(zeros, 0, 65536 * sizeof(int));
+    }
+    a.tile_dead = zeros;
+  }
+#endif
   const bool pipe = pipe_mode != 0;
   static bool attr_set = false;
   if (!attr_set) {
     DV_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemBytes));
-    DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kPipeSmemBytes));
-    DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pipe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kPipe2SmemBytes));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pipe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       pipe_smem_bytes(128)));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pipe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       pipe_smem_bytes(64)));
+    DV_CHECK_CUDA(cudaFuncSetAttribute(attn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kPairSmemBytes));
     attr_set = true;
   }
   dim3 grid(n_heads, B, (L + kTile - 1) / kTile);
+  const dim3 grid_pair(n_heads, B, (L + 2 * kTile - 1) / (2 * kTile));
   char tag[56] = "";
-  if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d%s", B, L, H, pipe_mode >= 2 ? " pipe2" : (pipe ? " pipe" : ""));
+  if (prof_on()) snprintf(tag, sizeof(tag), "attn B%d L%d H%d%s", B, L, H, pipe_mode == 3 ? " k64" : pipe_mode == 2 ? " pair" : (pipe ? " pipe" : ""));
   const int pid = prof_begin(PROF_ATTN, flops, 2.0 * B * L * 4.0 * H * kD, stream, tag);
-  if (pipe_mode >= 2)
-    DV_CHECK_CUDA(launch_pdl(attn_pipe2_kernel, grid, dim3(kPipe2Threads), kPipe2SmemBytes, stream, 1, a));
+  if (pipe_mode == 3)
+    DV_CHECK_CUDA(launch_pdl(attn_pipe_kernel<64>, grid, dim3(kAttnThreads), pipe_smem_bytes(64), stream, 1, a));
+  else if (pipe_mode == 2)
+    DV_CHECK_CUDA(launch_pdl(attn_pair_kernel, grid_pair, dim3(kPairThreads), kPairSmemBytes, stream, 1, a));
   else if (pipe)
-    DV_CHECK_CUDA(launch_pdl(attn_pipe_kernel, grid, dim3(kAttnThreads), kPipeSmemBytes, stream, 1, a));
+    DV_CHECK_CUDA(launch_pdl(attn_pipe_kernel<128>, grid, dim3(kAttnThreads), pipe_smem_bytes(128), stream, 1, a));
   else
     DV_CHECK_CUDA(launch_pdl(attn_kernel, grid, dim3(kAttnThreads), kSmemBytes, stream, 1, a));
   prof_end(pid, stream);

@@ -1889,6 +1889,12 @@ int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar,
       ph.B = in.B;
       ph.eps = in.eps;
       bytes += static_cast<double>(in.B) * (in.ln0.L + (in.has_ln1 ? in.ln1.L : 0)) * 1536.0 * 6.0;
+      // probe (DV_PBK_TRACE=2): run every LN phase twice (it is idempotent) to see what the second, instruction-cache-warm
+      // pass costs
+      if (getenv("DV_PBK_TRACE") && atoi(getenv("DV_PBK_TRACE")) == 2 && ka.n_phases + 3 <= kPbkMaxPhases) {
+        ka.ph[ka.n_phases] = ph;
+        ++ka.n_phases;
+      }
       continue;
     }
     DV_REQUIRE(in.kind == 1, "pbk: phase kind %d", in.kind);

@@ -8,7 +8,7 @@ from pathlib import Path
 
 os.environ["DV_MMDIT_PBK"] = "1"
 os.environ["DV_PBK_MAX_ROWS"] = "4096"
-os.environ["DV_PBK_TRACE"] = "1"
+os.environ["DV_PBK_TRACE"] = os.environ.get("DV_PBK_TRACE", "1")
 os.environ["DV_MOD_CACHE_SLOTS"] = "0"
 import torch
 
