@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const int tile0 = static_cast<int>(blockIdx.x), tile_step = static_cast<int>(gridDim.x);
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    // (the whole converged warp runs the loop; the w_ forms elect the issuing lane and keep operands in uniform registers)
+    {
       int ps = 0, ws = 0;
       uint32_t pph = 0, wph = 0;
       for (int tile = tile0; tile < a.tiles; tile += tile_step) {
@@ -109,9 +110,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         for (int dt = 0; dt < 3; ++dt) {
           for (int cb = 0; cb < a.c_blocks; ++cb) {
             mbar_wait(&empty_p[ps], pph ^ 1);
-            mbar_expect_tx(&full_p[ps], kPixBytes);
+            w_mbar_expect_tx(&full_p[ps], kPixBytes);
             // causal in time (two frames of zero history), centred in space: out-of-bounds = zero padding
-            tma_load_5d(&a.tmPix, &full_p[ps], pix + ps * kPixStride, cb * 64, w0 - 1, h0 - 1, t + dt - 2, b);
+            w_tma_load_5d(&a.tmPix, &full_p[ps], pix + ps * kPixStride, cb * 64, w0 - 1, h0 - 1, t + dt - 2, b);
             if (++ps == kPixStages) {
               ps = 0;
               pph ^= 1;
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             for (int s = 0; s < 9; ++s) {
               const int kb = (dt * 9 + s) * a.c_blocks + cb;   // weight K index: tap-major, then channel block
               mbar_wait(&empty_w[ws], wph ^ 1);
-              mbar_expect_tx(&full_w[ws], kWBytes);
-              tma_load_2d(&a.tmW, &full_w[ws], wgt + ws * kWBytes, kb * 64, chunk * 128);
+              w_mbar_expect_tx(&full_w[ws], kWBytes);
+              w_tma_load_2d(&a.tmW, &full_w[ws], wgt + ws * kWBytes, kb * 64, chunk * 128);
               if (++ws == kWStages) {
                 ws = 0;
                 wph ^= 1;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 256, 0, 0);
       int ps = 0, ws = 0, it = 0;
       uint32_t pph = 0, wph = 0;
@@ -155,22 +156,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const uint64_t db = umma_desc_sw128(sp + (dy * kBoxW + dx) * 128, 16, kBoxW * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_bf16_ss(acc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+              w_umma_bf16_ss(acc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
             }
             first = false;
-            umma_commit(&empty_w[ws]);
+            w_umma_commit(&empty_w[ws]);
             if (++ws == kWStages) {
               ws = 0;
               wph ^= 1;
             }
           }
-          umma_commit(&empty_p[ps]);
+          w_umma_commit(&empty_p[ps]);
           if (++ps == kPixStages) {
             ps = 0;
             pph ^= 1;
           }
         }
-        umma_commit(&tmem_full[as]);
+        w_umma_commit(&tmem_full[as]);
       }
     }
   } else {

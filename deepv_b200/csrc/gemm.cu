@@ -736,7 +736,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    // (the whole converged warp runs the loop; the w_ forms elect the issuing lane and keep operands in uniform registers)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int gtile = tile0; gtile < k.total_tiles; gtile += tile_step) {
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          w_mbar_expect_tx(&full_bar[stage], kStageBytes);
           if (d.a_mode == 1) {
             const int tap = kb / a.c_blocks;
             const int cb = kb - tap * a.c_blocks;
@@ -785,18 +786,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             if (a.swap) {
               // weights (<= 128 rows) feed the M side, a 16x16-pixel box the N side
-              tma_load_2d(&a.tmB, &full_bar[stage], sa, kb * BK, 0);
-              tma_load_5d(tma, &full_bar[stage], sb, cb * 64, x, y, t, tc.b);
+              w_tma_load_2d(&a.tmB, &full_bar[stage], sa, kb * BK, 0);
+              w_tma_load_5d(tma, &full_bar[stage], sb, cb * 64, x, y, t, tc.b);
             } else {
-              tma_load_5d(tma, &full_bar[stage], sa, cb * 64, x, y, t, tc.b);
-              tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
+              w_tma_load_5d(tma, &full_bar[stage], sa, cb * 64, x, y, t, tc.b);
+              w_tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
             }
           } else {
-            tma_load_3d(&a.tmA, &full_bar[stage], sa, kb * BK, tc.m_tile * BM, tc.b);
+            w_tma_load_3d(&a.tmA, &full_bar[stage], sa, kb * BK, tc.m_tile * BM, tc.b);
             if (d.w_batch_stride != 0)
-              tma_load_3d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN, tc.b);
+              w_tma_load_3d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN, tc.b);
             else
-              tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
+              w_tma_load_2d(&a.tmB, &full_bar[stage], sb, kb * BK, tc.n_tile * BN);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -831,17 +832,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 slice inside the 128 B swizzle row (address field is >>4)
-            umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, ((kb - tc.kb0) | k) != 0);
+            w_umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, ((kb - tc.kb0) | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          w_umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         if (tc.kb0 < tc.kb1)
-          umma_commit(&tmem_full[as]);
-        else
+          w_umma_commit(&tmem_full[as]);
+        else if (lane == 0)
           mbar_arrive(&tmem_full[as]);  // empty K range (tail split): nothing was issued
       }
     }
@@ -1017,6 +1018,70 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       "h"(mask)
       : "memory");
 }
+// whole-warp forms (see common.cuh): all 32 converged lanes execute them, one elected lane issues
+__device__ __forceinline__ void w_tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void w_tma_load_3d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1,
+                                                   int c2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void w_tma_load_5d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1,
+                                                   int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t"
+      "}\n"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void w_umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void w_umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
@@ -1102,7 +1167,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
 
   if (warp == 0) {
     // ============================ TMA producer (both CTAs) ============================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int gtile = cluster_id; gtile < k.total_pair_tiles; gtile += n_clusters) {
@@ -1124,22 +1189,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
           uint8_t* sa = smem + stage * kPairStageBytes;
           uint8_t* sb = sa + kABytes;
           const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          if (leader) w_mbar_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
           if (d.a_mode == 1) {
             const int tap = kb / a.c_blocks;
             const int cb = kb - tap * a.c_blocks;
             const int dt = tap / (d.kh * d.kw);
             const int dh = (tap / d.kw) % d.kh;
             const int dw = tap % d.kw;
-            tma_load_5d_pair(&a.tmA, lbar, sa, cb * 64, w0 + dw - d.kw / 2, h0 + dh - d.kh / 2,
+            w_tma_load_5d_pair(&a.tmA, lbar, sa, cb * 64, w0 + dw - d.kw / 2, h0 + dh - d.kh / 2,
                              ct + dt - (d.kt - 1), tc.b);
-            tma_load_2d_pair(&a.tmBh, lbar, sb, kb * BK, n_row);
+            w_tma_load_2d_pair(&a.tmBh, lbar, sb, kb * BK, n_row);
           } else {
-            tma_load_3d_pair(&a.tmA, lbar, sa, kb * BK, tc.m_tile * BM, tc.b);
+            w_tma_load_3d_pair(&a.tmA, lbar, sa, kb * BK, tc.m_tile * BM, tc.b);
             if (d.w_batch_stride != 0)
-              tma_load_3d_pair(&a.tmBh, lbar, sb, kb * BK, n_row, tc.b);
+              w_tma_load_3d_pair(&a.tmBh, lbar, sb, kb * BK, n_row, tc.b);
             else
-              tma_load_2d_pair(&a.tmBh, lbar, sb, kb * BK, n_row);
+              w_tma_load_2d_pair(&a.tmBh, lbar, sb, kb * BK, n_row);
           }
           if (++stage == kPairStages) {
             stage = 0;
@@ -1150,7 +1215,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA only) ========================
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -1172,14 +1237,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
           const uint64_t db = umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)
-            umma_bf16_ss_pair(tmem_acc, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
-          umma_commit_pair(&empty_bar[stage]);
+            w_umma_bf16_ss_pair(tmem_acc, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0);
+          w_umma_commit_pair(&empty_bar[stage]);
           if (++stage == kPairStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_pair(&tmem_full[as]);
+        w_umma_commit_pair(&tmem_full[as]);
       }
     }
   } else {
