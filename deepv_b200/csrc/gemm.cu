@@ -63,6 +63,11 @@ struct Problem {
   int swap;              // conv, Cout <= 128: weights are the M operand, 16x16 pixels the N operand
   int oT, oH, oW;        // conv: output dims (input dims over the strides)
   int sT, sH, sW;        // conv: strides (1 or 2)
+  // dense problems whose batch rows are contiguous in A and in the output run as ONE problem of flat_B * flat_M rows
+  // (d.M = flat_B * flat_M, d.batch = 1): a 128-row (CTA pair: 256-row) tile then wastes at most one partial tile per
+  // launch instead of one per batch row — B = 3 x 269 context rows are 4 pair tiles instead of 6, B = 2 x 384 video
+  // rows 3 instead of 4.  flat_M = 0: not flattened.  The logical batch of a row (per-batch gate vectors) is row / flat_M.
+  int flat_M, flat_B;
 };
 
 // One launch runs up to two problems of the same epilogue mode (the video and the context stream
@@ -73,7 +78,22 @@ struct KArgs {
   int splits;
   int total_pair_tiles;
   int pdl_early;
+#ifdef DV_GEMM_TRACE
+  long long* trace;   // probe build only (scripts/probe/gemm_trace.py): per-CTA globaltimer stamps
+#endif
 };
+
+// probe build: slot k of this CTA's record <- globaltimer (slot 0 holds the SM id)
+#ifdef DV_GEMM_TRACE
+#define DV_GT(on, slot)                                                                                       \
+  do {                                                                                                        \
+    if ((on) && blockIdx.x < 4096) k.trace[blockIdx.x * 12 + (slot)] = static_cast<long long>(global_ns());    \
+  } while (0)
+#else
+#define DV_GT(on, slot) \
+  do {                  \
+  } while (0)
+#endif
 
 struct TileCoord {
   int b, m_tile, n_tile, kb0, kb1;
@@ -125,6 +145,7 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
 // ------------------------------------------------------------------------------
 struct RowCtx {
   int b, m;        // batch, dense row index inside the batch (conv: unused)
+  int gb;          // logical batch of the row (differs from b for a flattened problem)
   bool ok;         // row exists
   int ct, ch, cw;  // conv: output pixel
 };
@@ -145,6 +166,7 @@ __device__ __forceinline__ RowCtx make_row(const Problem& a, const TileCoord& tc
   } else {
     r.ok = r.m < d.M;
   }
+  r.gb = a.flat_M ? min(r.m / a.flat_M, a.flat_B - 1) : tc.b;
   return r;
 }
 
@@ -309,7 +331,7 @@ __device__ __forceinline__ void epi_row(const Problem& a, const RowCtx& r, int n
     float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) +
                                            static_cast<long long>(r.b) * d.out_batch_stride +
                                            static_cast<long long>(r.m + d.out_row_offset) * d.ldo + n);
-    const float4* g4 = reinterpret_cast<const float4*>(d.gate + r.b * d.gate_batch_stride + n);
+    const float4* g4 = reinterpret_cast<const float4*>(d.gate + r.gb * d.gate_batch_stride + n);
 #pragma unroll
     for (int i = 0; i < W / 4; ++i) {
       const float4 g = __ldg(g4 + i);
@@ -526,7 +548,8 @@ __device__ __forceinline__ void epilogue_tma(const Problem& a, const TileCoord& 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(buf[it & 1][i]);
         add_bias<32>(d.bias, n, v);
-        const float4* g4 = reinterpret_cast<const float4*>(d.gate + tc.b * d.gate_batch_stride + n);
+        const int gb = a.flat_M ? min((m0 + row_in_tile) / a.flat_M, a.flat_B - 1) : tc.b;
+        const float4* g4 = reinterpret_cast<const float4*>(d.gate + gb * d.gate_batch_stride + n);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 g = __ldg(g4 + i);
@@ -696,6 +719,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef DV_GEMM_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 4096) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    k.trace[blockIdx.x * 12] = smid;
+  }
+#endif
+  DV_GT(threadIdx.x == 0, 1);   // entry
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&k.p[0].tmA);
@@ -723,8 +754,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  DV_GT(threadIdx.x == 0, 2);   // barriers + tensor memory set up
   pdl_wait();  // everything above overlapped the previous kernel's tail
   if (k.pdl_early) pdl_trigger();
+  DV_GT(threadIdx.x == 0, 3);   // predecessor's data visible
 
   // split-K: the cluster = the splits of ONE tile (grid = tiles * splits, one pass);
   // otherwise a persistent loop over tiles
@@ -825,6 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == tc.kb0) DV_GT(lane == 0, 4);   // first operands landed
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t da = umma_desc_sw128(sa, 16, 1024);
@@ -840,6 +874,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             phase ^= 1;
           }
         }
+        DV_GT(lane == 0, 5);   // (last tile's) MMAs issued
         if (tc.kb0 < tc.kb1)
           w_umma_commit(&tmem_full[as]);
         else if (lane == 0)
@@ -861,6 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const TileCoord tc = decode_tile(a, tile, 0);
         mbar_wait(&tmem_full[as], aph);
         tc_fence_after();
+        DV_GT(threadIdx.x == 64, 6);   // (last tile's) accumulator complete
         if (MODE == EPI_CONV && a.swap) {
           epilogue_tile_swapped(a, tc, tmem_base + as * BN, quarter, lane, half);
         } else if (EpiTma<MODE>::value && a.tma_out) {
@@ -880,6 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       // idle: every MMA that read it has retired once tmem_full fires)
       mbar_wait(&tmem_full[0], 0);
       tc_fence_after();
+      DV_GT(threadIdx.x == 64, 6);   // accumulator complete
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       float4* part = reinterpret_cast<float4*>(smem);
       int tile = tile0;
@@ -908,6 +945,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // every CTA of the cluster has parked its partial tile
     __syncwarp();
     cluster_sync_all();
+    DV_GT(threadIdx.x == 64, 7);   // every split parked its partial tile
     if (warp >= 2) {
       constexpr int W = EpiW<MODE>::value;
       const int t = threadIdx.x - 64;      // 0..255
@@ -948,6 +986,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     cluster_sync_all();
   }
 
+  DV_GT(threadIdx.x == 64, 8);   // epilogue / reduction done
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
@@ -955,6 +994,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+  DV_GT(threadIdx.x == 0, 9);   // exit
 }
 
 // ------------------------------------------------------------------------------
@@ -1131,6 +1171,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef DV_GEMM_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 4096) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    k.trace[blockIdx.x * 12] = smid;
+  }
+#endif
+  DV_GT(threadIdx.x == 0, 1);   // entry
   const int rank = static_cast<int>(cluster_ctarank());
   const bool leader = rank == 0;
 
@@ -1159,8 +1207,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
   cluster_sync_all();  // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  DV_GT(threadIdx.x == 0, 2);   // barriers + tensor memory set up
   pdl_wait();  // everything above overlapped the previous kernel's tail
   if (k.pdl_early) pdl_trigger();
+  DV_GT(threadIdx.x == 0, 3);   // predecessor's data visible
 
   const int cluster_id = static_cast<int>(blockIdx.x) >> 1;
   const int n_clusters = static_cast<int>(gridDim.x) >> 1;
@@ -1231,6 +1281,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
         for (int kb = 0; kb < a.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == 0) DV_GT(lane == 0, 4);   // first operands landed
           const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t da = umma_desc_sw128(sa, 16, 1024);
@@ -1244,6 +1295,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
             phase ^= 1;
           }
         }
+        DV_GT(lane == 0, 5);   // (last tile's) MMAs issued
         w_umma_commit_pair(&tmem_full[as]);
       }
     }
@@ -1261,6 +1313,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
       const TileCoord tc = decode_pair_tile(a, tile, rank);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
+      DV_GT(threadIdx.x == 64, 6);   // (last tile's) accumulator complete
       if (EpiTma<MODE>::value && a.tma_out) {
         if constexpr (EpiTma<MODE>::value)
           epilogue_tma<MODE>(a, tc, tmem_base + as * BN, row_in_tile, quarter, half, out_stage,
@@ -1276,6 +1329,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
     if (EpiTma<MODE>::value && quarter == 0 && lane == 0) bulk_wait_all();  // my TMA stores have landed
   }
 
+  DV_GT(threadIdx.x == 64, 8);   // epilogue done
   pdl_trigger();
   tc_fence_before();
   __syncwarp();
@@ -1284,6 +1338,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
     tc_fence_after();
     tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
+  DV_GT(threadIdx.x == 0, 9);   // exit
 }
 
 // ------------------------------------------------------------------------------
@@ -1701,7 +1756,20 @@ int cluster_capacity(int s) {
 }  // namespace
 
 // geometry + tensor maps of one problem
-static int setup_problem(const GemmDesc& d, Problem& pr) {
+static int setup_problem(const GemmDesc& d_in, Problem& pr, bool allow_flat = true) {
+  GemmDesc d = d_in;
+  pr.flat_M = 0;
+  pr.flat_B = 1;
+  static const bool no_flat = getenv("DV_GEMM_NO_FLAT") != nullptr;
+  if (allow_flat && !no_flat && d.a_mode == 0 && d.batch > 1 && d.w_batch_stride == 0 && d.peer_cols == 0 &&
+      (d.mode == EPI_BF16 || d.mode == EPI_GELU || d.mode == EPI_RESID_GATE) && d.out_row_offset == 0 &&
+      d.a_batch_stride == static_cast<long long>(d.M) * d.lda &&
+      d.out_batch_stride == static_cast<long long>(d.M) * d.ldo) {
+    pr.flat_M = d.M;
+    pr.flat_B = d.batch;
+    d.M *= d.batch;
+    d.batch = 1;
+  }
   pr.d = d;
   pr.swap = 0;
   DV_REQUIRE(d.batch > 0 && d.N > 0, "gemm: empty problem (batch=%d N=%d)", d.batch, d.N);
@@ -1970,12 +2038,12 @@ int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar,
     ph.p0 = np;
     ph.np = 1 + (in.has_g1 ? 1 : 0);
     ph.mode = in.g0.mode;
-    int rc = setup_problem(in.g0, ka.p[np]);
+    int rc = setup_problem(in.g0, ka.p[np], false);
     if (rc) return rc;
     if (in.has_g1) {
       DV_REQUIRE(in.g1.mode == in.g0.mode && in.g1.a_mode == 0 && in.g1.K == in.g0.K && in.g1.N == in.g0.N,
                  "pbk: the two problems of a phase must share mode, N and K");
-      rc = setup_problem(in.g1, ka.p[np + 1]);
+      rc = setup_problem(in.g1, ka.p[np + 1], false);
       if (rc) return rc;
     }
     ph.tiles = ka.p[np].tiles + (in.has_g1 ? ka.p[np + 1].tiles : 0);
@@ -2017,6 +2085,17 @@ int launch_pbk(const PbkPhaseIn* phases, int n, float* workspace, unsigned* bar,
 }
 
 int launch_gemm(const GemmDesc& d, cudaStream_t stream) { return launch_gemm_pair(d, nullptr, stream); }
+
+#ifdef DV_GEMM_TRACE
+long long* g_gemm_trace = nullptr;
+extern "C" long long* dv_gemm_trace_buffer() {
+  if (!g_gemm_trace) {
+    cudaMalloc(&g_gemm_trace, 4096 * 12 * sizeof(long long));
+    cudaMemset(g_gemm_trace, 0, 4096 * 12 * sizeof(long long));
+  }
+  return g_gemm_trace;
+}
+#endif
 
 int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream) {
   static const bool no_split = getenv("DV_GEMM_NOSPLIT") != nullptr;
@@ -2061,6 +2140,9 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
     if (ka.p[i].tiles > 0) ka.p[i].kb_per_split = (ka.p[i].k_blocks + ka.splits - 1) / ka.splits;
   ka.total_tiles = ka.p[0].tiles + ka.p[1].tiles;
   ka.pdl_early = pdl_early() ? 1 : 0;
+#ifdef DV_GEMM_TRACE
+  ka.trace = dv_gemm_trace_buffer();
+#endif
   if (ka.p[1].tiles == 0) ka.p[1].pair_tiles = 0;
   ka.total_pair_tiles = ka.p[0].pair_tiles + ka.p[1].pair_tiles;
   // CTA pairs (cta_group::2) once every SM pair has a 256-row tile: ~570 cycles per k-block instead
@@ -2097,11 +2179,11 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
                d0.cC, d0.N, d0.kt, ka.p[0].swap ? " sw" : "", pair ? " 2cta" : "", ka.splits,
                d0.conv_store);
     else if (d1 != nullptr)
-      snprintf(tag, sizeof(tag), "gemm B%d M%d+%d N%d K%d s%d%s e%d", d0.batch, d0.M, d1->M, d0.N, K0,
-               ka.splits, pair ? " 2cta" : "", d0.mode);
+      snprintf(tag, sizeof(tag), "gemm B%d M%d+%d N%d K%d s%d%s e%d%s", d0.batch, d0.M, d1->M, d0.N, K0,
+               ka.splits, pair ? " 2cta" : "", d0.mode, ka.p[0].flat_M ? " flat" : "");
     else
-      snprintf(tag, sizeof(tag), "gemm B%d M%d N%d K%d s%d%s e%d", d0.batch, d0.M, d0.N, K0, ka.splits,
-               pair ? " 2cta" : "", d0.mode);
+      snprintf(tag, sizeof(tag), "gemm B%d M%d N%d K%d s%d%s e%d%s", d0.batch, d0.M, d0.N, K0, ka.splits,
+               pair ? " 2cta" : "", d0.mode, ka.p[0].flat_M ? " flat" : "");
   }
   const int pid = prof_begin(d0.a_mode == 1 ? PROF_CONV : PROF_GEMM, flops, bytes, stream, tag);
   rc = launch_args(ka, d0.mode, pair, stream);
