@@ -126,17 +126,22 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// the second barrier of a split-K launch orders nothing in memory: it only keeps a CTA (its shared memory) alive until
+// every peer has consumed the values it loaded from it, which the in-order issue of the consuming stores already implies
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// (not volatile, no memory clobber: the partial tiles are written before the cluster barrier, which is the compiler fence;
+// the loads may then be scheduled together with the epilogue's global loads instead of in front of them)
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(addr)
-               : "memory");
+  asm("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 
@@ -965,8 +970,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         float v[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) v[i] = 0.f;
-#pragma unroll 1
-        for (int p = 0; p < k.splits; ++p) {  // fixed order: bit-reproducible sums
+#pragma unroll 2
+        for (int p = 0; p < k.splits; ++p) {  // fixed order: bit-reproducible sums (splits is 2, 4 or 8)
           const uint32_t peer = map_to_cta(part0, static_cast<uint32_t>(p));
 #pragma unroll
           for (int i = 0; i < W / 4; ++i) {
@@ -983,7 +988,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     // nobody leaves while a peer may still read its shared memory
     __syncwarp();
-    cluster_sync_all();
+    cluster_sync_relaxed();
   }
 
   DV_GT(threadIdx.x == 64, 8);   // epilogue / reduction done

@@ -83,6 +83,13 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __nv_bfloa
 __device__ __forceinline__ float silu_fast(float x) {
   return __fdividef(x, 1.0f + __expf(-x));
 }
+// x * sigmoid(x) = 0.5 x (1 + tanh(0.5 x)): ONE trip through the XU pipe (MUFU.TANH) instead of two (EX2 + RCP)
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // y = silu?( (x - mean) * rstd * gamma + beta ): same thread -> channel-vector mapping as the
 // statistics pass, so the per-channel affine a*x + b is hoisted out of the pixel loop.
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat1
                                                               __nv_bfloat16* __restrict__ y, int HW,
                                                               int C, int G, int do_silu,
                                                               int pix_per_cta) {
+  // do_silu: 0 none, 1 = x / (1 + e^-x) (EX2 + RCP), 2 = 0.5 x (1 + tanh(0.5 x)) (one MUFU)
   const int f = blockIdx.y;
   const int vec_per_pix = C / 8;
   const int cpg = C / G;
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __nv_bfloat1
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float r = fmaf(e[k], a[k], b[k]);
-      e[k] = do_silu ? silu_fast(r) : r;
+      e[k] = do_silu == 2 ? silu_tanh(r) : (do_silu ? silu_fast(r) : r);
     }
     uint4 o;
     o.x = pack_bf16x2(e[0], e[1]);
@@ -288,7 +296,8 @@ int launch_tap_gather(const float* planes, const float* bias, __nv_bfloat16* out
 // large, while small tensors still spread over >= 2 CTAs per SM
 static int gn_pix_per_cta(int HW, int frames, int C) {
   const int pstep = kGnThreads / (C / 8);
-  int ppc = pstep * 16;
+  static const int mult = getenv("DV_GN_PPC") ? atoi(getenv("DV_GN_PPC")) : 16;
+  int ppc = pstep * mult;
   while (ppc > pstep * 4 && static_cast<long long>((HW + ppc - 1) / ppc) * frames < 2 * sm_count()) ppc /= 2;
   return ppc;
 }
@@ -314,6 +323,8 @@ int launch_gn_apply(const __nv_bfloat16* x, const double* acc, int replicas, lon
   DV_REQUIRE(C % 8 == 0 && C % G == 0 && kGnThreads % (C / 8) == 0, "gn_apply: C=%d G=%d", C, G);
   const int ppc = gn_pix_per_cta(HW, frames, C);
   dim3 grid((HW + ppc - 1) / ppc, frames);
+  static const bool silu_exp = getenv("DV_GN_SILU_EXP") != nullptr;   // A/B switch: the two-MUFU form
+  if (silu_on && !silu_exp) silu_on = 2;
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(frames) * HW * C * 4.0, stream, "gn_apply");
   DV_CHECK_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(kGnThreads), 0, stream, 1, x, acc, replicas,
                            replica_stride, 1.0 / (static_cast<double>(HW) * (C / G)), eps, gamma, beta, y,
