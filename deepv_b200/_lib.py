@@ -104,6 +104,7 @@ SIGNATURES = {
     "dv_vae_plan_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "dv_vae_plan_destroy": (None, [_vp]),
     "dv_vae_plan_flops": (_d, [_vp]),
+    "dv_vae_plan_set_first_frame": (_i, [_vp, _i]),
     "dv_vae_decode": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "dv_vae_enc_plan_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "dv_vae_enc_plan_destroy": (None, [_vp]),

@@ -40,6 +40,7 @@ struct HaloArgs {
   CUtensorMap tmPix, tmW;
   GemmDesc d;
   int T, H, W, tiles_w, tiles_h, c_blocks, tiles, n_chunks, pdl_early;
+  int t0;   // first output frame computed (GemmDesc::conv_t0)
 };
 
 __device__ __forceinline__ void decode(const HaloArgs& a, int tile, int* b, int* t, int* h0, int* w0, int* chunk) {
@@ -50,8 +51,9 @@ __device__ __forceinline__ void decode(const HaloArgs& a, int tile, int* b, int*
   const int f = tile / per_frame;
   *w0 = (r % a.tiles_w) * kTileW;
   *h0 = (r / a.tiles_w) * kTileH;
-  *t = f % a.T;
-  *b = f / a.T;
+  const int nt = a.T - a.t0;
+  *t = a.t0 + f % nt;
+  *b = f / nt;
 }
 
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
@@ -292,7 +294,10 @@ int launch_conv_halo(const GemmDesc& d, cudaStream_t stream) {
   a.c_blocks = d.cC / 64;
   a.n_chunks = (d.N + 127) / 128;
   a.pdl_early = pdl_early() ? 1 : 0;
-  const long long tiles = static_cast<long long>(d.batch) * d.cT * a.tiles_w * a.tiles_h * a.n_chunks;
+  a.t0 = d.conv_t0;
+  DV_REQUIRE(a.t0 >= 0 && a.t0 < d.cT, "conv: first frame %d of %d", a.t0, d.cT);
+  const int nT = d.cT - a.t0;   // frames computed
+  const long long tiles = static_cast<long long>(d.batch) * nT * a.tiles_w * a.tiles_h * a.n_chunks;
   if (tiles < sm_count() || tiles >= (1ll << 30)) return 1;   // small problems: the generic path splits K
   {
     // rows padded up to the 32-row tile and the last, partly filled wave are wasted work here, while the
@@ -325,12 +330,12 @@ int launch_conv_halo(const GemmDesc& d, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = a.tiles < sm_count() ? a.tiles : sm_count();
-  const double pixels = static_cast<double>(d.batch) * d.cT * d.cH * d.cW;
+  const double pixels = static_cast<double>(d.batch) * nT * d.cH * d.cW;
   const double flops = 2.0 * pixels * 27.0 * d.cC * d.N;
   const double bytes = 2.0 * (pixels * d.cC + 27.0 * d.cC * d.N + pixels * d.N);
   char tag[56] = "";
   if (prof_on())
-    snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k3 halo e%d", d.cT, d.cH, d.cW, d.cC, d.N, d.conv_store);
+    snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k3 halo e%d", nT, d.cH, d.cW, d.cC, d.N, d.conv_store);
   const int pid = prof_begin(PROF_CONV, flops, bytes, stream, tag);
   DV_CHECK_CUDA(launch_pdl(conv_halo_kernel, dim3(grid), dim3(kHaloThreads), kHaloSmem, stream, 1, a));
   prof_end(pid, stream);

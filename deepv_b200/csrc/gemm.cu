@@ -62,6 +62,7 @@ struct Problem {
   int c_blocks;          // conv: Cin / 64
   int swap;              // conv, Cout <= 128: weights are the M operand, 16x16 pixels the N operand
   int oT, oH, oW;        // conv: output dims (input dims over the strides)
+  int oT0;               // conv: first output frame computed (GemmDesc::conv_t0); m-tiles cover frames [oT0, oT)
   int sT, sH, sW;        // conv: strides (1 or 2)
   // dense problems whose batch rows are contiguous in A and in the output run as ONE problem of flat_B * flat_M rows
   // (d.M = flat_B * flat_M, d.batch = 1): a 128-row (CTA pair: 256-row) tile then wastes at most one partial tile per
@@ -163,7 +164,7 @@ __device__ __forceinline__ RowCtx make_row(const Problem& a, const TileCoord& tc
   r.ct = r.ch = r.cw = 0;
   if (d.a_mode == 1) {
     const int per_frame = a.tiles_w * a.tiles_h;
-    r.ct = tc.m_tile / per_frame;
+    r.ct = a.oT0 + tc.m_tile / per_frame;
     const int q = tc.m_tile % per_frame;
     r.ch = (q / a.tiles_w) * 8 + (row_in_tile >> 4);
     r.cw = (q % a.tiles_w) * 16 + (row_in_tile & 15);
@@ -648,7 +649,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const Problem& a, const Ti
                                                       int half) {
   const GemmDesc& d = a.d;
   const int per_frame = a.tiles_w * a.tiles_h;
-  const int ct = tc.m_tile / per_frame;
+  const int ct = a.oT0 + tc.m_tile / per_frame;
   const int r = tc.m_tile % per_frame;
   const int h0 = (r / a.tiles_w) * 16, w0 = (r % a.tiles_w) * 16;
   const int c = quarter * 32 + lane;  // output channel of this thread
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         int ct = 0, h0 = 0, w0 = 0;
         if (d.a_mode == 1) {
           const int per_frame = a.tiles_w * a.tiles_h;
-          ct = tc.m_tile / per_frame;
+          ct = a.oT0 + tc.m_tile / per_frame;
           const int r = tc.m_tile % per_frame;
           h0 = (r / a.tiles_w) * (a.swap ? 16 : 8);
           w0 = (r % a.tiles_w) * 16;
@@ -1233,7 +1234,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_pair_kernel(const __grid_con
         int ct = 0, h0 = 0, w0 = 0;
         if (d.a_mode == 1) {
           const int per_frame = a.tiles_w * a.tiles_h;
-          ct = tc.m_tile / per_frame;
+          ct = a.oT0 + tc.m_tile / per_frame;
           const int r = tc.m_tile % per_frame;
           h0 = (r / a.tiles_w) * 8;
           w0 = (r % a.tiles_w) * 16;
@@ -1805,7 +1806,10 @@ static int setup_problem(const GemmDesc& d_in, Problem& pr, bool allow_flat = tr
                pr.oW);
     pr.tiles_w = pr.oW / 16;
     pr.tiles_h = pr.swap ? (pr.oH + 15) / 16 : pr.oH / 8;
-    pr.m_tiles = pr.oT * pr.tiles_w * pr.tiles_h;
+    pr.oT0 = d.conv_t0;
+    DV_REQUIRE(pr.oT0 >= 0 && pr.oT0 < pr.oT && (pr.oT0 == 0 || pr.sT * pr.sH * pr.sW == 1),
+               "conv: first frame %d of %d (stride-1 convs only)", pr.oT0, pr.oT);
+    pr.m_tiles = (pr.oT - pr.oT0) * pr.tiles_w * pr.tiles_h;
   } else {
     DV_REQUIRE(d.mode != EPI_CONV, "EPI_CONV needs the conv operand");
     DV_REQUIRE(d.K % 64 == 0, "gemm: K=%d must be a multiple of 64", d.K);
@@ -1815,6 +1819,7 @@ static int setup_problem(const GemmDesc& d_in, Problem& pr, bool allow_flat = tr
     pr.tiles_w = pr.tiles_h = 1;
     pr.m_tiles = (d.M + BM - 1) / BM;
     pr.oT = pr.oH = pr.oW = 0;
+    pr.oT0 = 0;
     pr.sT = pr.sH = pr.sW = 1;
   }
   pr.k_blocks = K / BK;
@@ -1943,7 +1948,7 @@ static double plan_splits(long long tiles, int k_blocks, bool allow_split, int* 
 }
 
 static double problem_flops(const GemmDesc& d, int K, const Problem& pr) {
-  const double rows = static_cast<double>(d.a_mode == 1 ? (double)pr.oT * pr.oH * pr.oW : d.M) * d.batch;
+  const double rows = static_cast<double>(d.a_mode == 1 ? (double)(pr.oT - pr.oT0) * pr.oH * pr.oW : d.M) * d.batch;
   return 2.0 * rows * d.N * K;
 }
 
@@ -2170,7 +2175,7 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
 
   const int K0 = ka.p[0].k_blocks * BK;
   double flops = problem_flops(d0, K0, ka.p[0]);
-  double rows = static_cast<double>(d0.a_mode == 1 ? (double)ka.p[0].oT * ka.p[0].oH * ka.p[0].oW : d0.M) * d0.batch;
+  double rows = static_cast<double>(d0.a_mode == 1 ? (double)(ka.p[0].oT - ka.p[0].oT0) * ka.p[0].oH * ka.p[0].oW : d0.M) * d0.batch;
   double bytes = 2.0 * (rows * K0 / (d0.a_mode == 1 ? d0.kt * d0.kh * d0.kw : 1) + (double)d0.N * K0 + rows * d0.N);
   if (d1 != nullptr) {
     const int K1 = ka.p[1].k_blocks * BK;
@@ -2180,7 +2185,7 @@ int launch_gemm_pair(const GemmDesc& d0, const GemmDesc* d1, cudaStream_t stream
   char tag[56] = "";
   if (prof_on()) {
     if (d0.a_mode == 1)
-      snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k%d%s%s s%d e%d", d0.cT, d0.cH, d0.cW,
+      snprintf(tag, sizeof(tag), "conv T%d H%d W%d Ci%d N%d k%d%s%s s%d e%d", d0.cT - d0.conv_t0, d0.cH, d0.cW,
                d0.cC, d0.N, d0.kt, ka.p[0].swap ? " sw" : "", pair ? " 2cta" : "", ka.splits,
                d0.conv_store);
     else if (d1 != nullptr)

@@ -79,6 +79,7 @@ struct GemmDesc {
   // CONV
   int conv_store;              // ConvStore
   int conv_drop_first;         // INTERLEAVE_T: drop output frame 0 (vae.py:408-409)
+  int conv_t0;                 // compute conv output frames [conv_t0, T) only (stride-1 convs; frame indices stay absolute)
   const void* residual;        // bf16, same layout as out (PLAIN store only), may be null
   int out_C;                   // channels of the stored tensor (N, N/4 or N/2)
   // CONV: optional fused GroupNorm statistics of the STORED tensor (vae.py:161-167): the epilogue

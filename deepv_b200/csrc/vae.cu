@@ -34,7 +34,7 @@ int launch_latent_tile(const void* z, int is_bf16, __nv_bfloat16* out, int C, in
                        int y0, int x0, int th, int tw, int Cpad, cudaStream_t stream);
 // conv with <= 4 output channels from per-tap partial products (EPI_TAPS planes), vae.py:225-252
 int launch_tap_gather(const float* planes, const float* bias, __nv_bfloat16* out, int T, int H, int W,
-                      int Cout, cudaStream_t stream);
+                      int Cout, int t_first, cudaStream_t stream);
 }  // namespace dv
 
 struct dv_vae {
@@ -55,6 +55,7 @@ struct TileOut {
 struct dv_vae_plan {
   dv_vae* v = nullptr;
   int T = 0, h = 0, w = 0, tile = 0, Tout = 0;
+  int first_frame = 0;          // decode output frames [first_frame, Tout) only (dv_vae_plan_set_first_frame)
   int rows = 0, cols = 0;
   std::vector<int> ys, xs;      // latent tile origins
   std::vector<TileOut> tiles;   // rows * cols
@@ -80,6 +81,7 @@ struct BlendArgs {
   const TileOut* tiles;
   int rows, cols, Tout, Hout, Wout, limit, extent;
   int nch = 3;  // channels written (decoder: 3; encoder: 2z moments)
+  int t_first = 0;  // frames [t_first, Tout) are blended and written (trimmed decode)
 };
 
 template <int DEPTH>
@@ -114,15 +116,17 @@ __device__ float blended(const BlendArgs& a, int i, int j, int t, int y, int x, 
 template <typename T>
 __global__ void blend_kernel(BlendArgs a, T* __restrict__ out) {
   // out: [nch][Tout][Hout][Wout]; x fastest -> coalesced stores
-  const long long total = static_cast<long long>(a.nch) * a.Tout * a.Hout * a.Wout;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int nT = a.Tout - a.t_first;
+  const long long total = static_cast<long long>(a.nch) * nT * a.Hout * a.Wout;
+  long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int X = idx % a.Wout;
   long long r = idx / a.Wout;
   const int Y = r % a.Hout;
   r /= a.Hout;
-  const int t = r % a.Tout;
-  const int c = r / a.Tout;
+  const int t = a.t_first + static_cast<int>(r % nT);
+  const int c = r / nT;
+  idx = ((static_cast<long long>(c) * a.Tout + t) * a.Hout + Y) * a.Wout + X;
   const int i = min(Y / a.limit, a.rows - 1), j = min(X / a.limit, a.cols - 1);
   // depth 3 covers every dependency chain of a row-major sweep (corner -> up -> up-left)
   const float v = blended<3>(a, i, j, t, Y - i * a.limit, X - j * a.limit, c);
@@ -145,6 +149,7 @@ struct Act {  // channels-last activation
   __nv_bfloat16* p;
   int T, H, W, C;
   double* gn = nullptr;  // GroupNorm statistics accumulated by the producer, or null
+  int t0 = 0;            // frames [t0, T) hold data (a trimmed decode computes only what the kept frames depend on)
   long long elems() const { return static_cast<long long>(T) * H * W * C; }
 };
 
@@ -177,11 +182,16 @@ struct Runner {
 
   // causal conv (vae.py:225-252) as implicit GEMM
   // `stats`: also accumulate the GroupNorm statistics of the output (its consumer is a norm)
+  // `t0`: first frame of the CONV output to compute (before an interleave store doubles the frame index)
   Act conv(const std::string& name, const Act& x, int cout, int ks, int store, int drop_first,
            const __nv_bfloat16* residual, __nv_bfloat16* outbuf, int w_rows = -1, bool stats = false,
-           int sT = 1, int sH = 1, int sW = 1) {
+           int sT = 1, int sH = 1, int sW = 1, int t0 = 0) {
     Act y;
     y.p = outbuf;
+    if ((std::max(0, t0 - (ks - 1)) < x.t0 || (t0 > 0 && sT * sH * sW != 1)) && rc == 0) {
+      set_error("vae: conv %s from frame %d needs input frames from %d, have %d", name.c_str(), t0, t0 - (ks - 1), x.t0);
+      rc = DV_ERR_INVALID;
+    }
     y.T = (x.T - 1) / sT + 1;  // causal: (kt-1) zero frames in front, then a VALID conv (vae.py:229-231)
     y.H = x.H / sH;
     y.W = x.W / sW;
@@ -194,8 +204,9 @@ struct Runner {
       y.T = 2 * x.T - (drop_first ? 1 : 0);
       y.C = cout / 2;
     }
+    y.t0 = store == CONV_INTERLEAVE_T ? std::max(0, 2 * t0 - (drop_first ? 1 : 0)) : t0;
     note(y);
-    flops += 2.0 * y.T * (x.H / sH) * (x.W / sW) * cout * static_cast<double>(ks * ks * ks) * x.C;
+    flops += 2.0 * ((x.T - 1) / sT + 1 - t0) * (x.H / sH) * (x.W / sW) * cout * static_cast<double>(ks * ks * ks) * x.C;
     const int G = pl->v->cfg.norm_groups;
     if (stats && y.C % G == 0 && (y.C / G == 4 || y.C / G == 8 || y.C / G == 16)) y.gn = new_gn_slot();
     if (dry || rc) return y;
@@ -223,6 +234,7 @@ struct Runner {
     d.out = outbuf;
     d.conv_store = store;
     d.conv_drop_first = drop_first;
+    d.conv_t0 = t0;
     d.residual = residual;
     d.out_C = y.C;
     if (rc == 0) rc = launch_gemm(d, st);
@@ -238,31 +250,37 @@ struct Runner {
     if (dry || rc) return y;
     const int G = pl->v->cfg.norm_groups;
     const double* acc = x.gn;
+    // frames [x.t0, T): the statistics are per frame, indexed by the absolute frame
+    const long long foff = static_cast<long long>(x.t0) * x.H * x.W * x.C;
+    const long long aoff = static_cast<long long>(x.t0) * G * 2;
     if (acc == nullptr) {  // producer without fused statistics: one read pass
       double* slot = new_gn_slot();
-      rc = launch_gn_stats(x.p, slot, x.T, x.H * x.W, x.C, G, st);
+      rc = launch_gn_stats(x.p + foff, slot + aoff, x.T - x.t0, x.H * x.W, x.C, G, st);
       acc = slot;
     }
     if (rc == 0)
-      rc = launch_gn_apply(x.p, acc, dv_vae_plan::kGnReplicas, pl->gn_replica_elems,
+      rc = launch_gn_apply(x.p + foff, acc + aoff, dv_vae_plan::kGnReplicas, pl->gn_replica_elems,
                            reinterpret_cast<const float*>(W(name + ".weight")),
-                           reinterpret_cast<const float*>(W(name + ".bias")), outbuf, x.T, x.H * x.W,
+                           reinterpret_cast<const float*>(W(name + ".bias")), outbuf + foff, x.T - x.t0, x.H * x.W,
                            x.C, G, 1e-6f, act ? 1 : 0, st);
     return y;
   }
 
   // CausalResnetBlock3D (vae.py:293-310); x lives in buf[ix], result goes to buf[iout]
-  Act resnet(const std::string& name, const Act& x, int cout, int ia, int ib, int iout) {
+  // `t_out`: first output frame anything downstream depends on; conv1 then starts two frames earlier and the input
+  // must hold frames from t_out - 4 (need_in())
+  Act resnet(const std::string& name, const Act& x, int cout, int ia, int ib, int iout, int t_out = 0) {
     __nv_bfloat16** B = pl->buf;
+    const int t1 = std::max(0, t_out - 2);
     Act a = gn(name + ".norm1", x, true, B[ia]);
-    Act h = conv(name + ".conv1.conv", a, cout, 3, CONV_PLAIN, 0, nullptr, B[ib], -1, true);
+    Act h = conv(name + ".conv1.conv", a, cout, 3, CONV_PLAIN, 0, nullptr, B[ib], -1, true, 1, 1, 1, t1);
     Act a2 = gn(name + ".norm2", h, true, B[ia]);
     const __nv_bfloat16* res = x.p;
     if (x.C != cout) {
-      Act sc = conv(name + ".conv_shortcut.conv", x, cout, 1, CONV_PLAIN, 0, nullptr, B[ib]);
+      Act sc = conv(name + ".conv_shortcut.conv", x, cout, 1, CONV_PLAIN, 0, nullptr, B[ib], -1, false, 1, 1, 1, t_out);
       res = sc.p;  // conv1's output (in B[ib]) has been consumed by norm2 already
     }
-    return conv(name + ".conv2.conv", a2, cout, 3, CONV_PLAIN, 0, res, B[iout], -1, true);
+    return conv(name + ".conv2.conv", a2, cout, 3, CONV_PLAIN, 0, res, B[iout], -1, true, 1, 1, 1, t_out);
   }
 
   // diffusers Attention of the mid block (vae.py:439-445,463-467): per frame, one head of width C
@@ -370,6 +388,30 @@ static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, c
   // buffers: x in B[0]; scratch B[1], B[2]; result B[3] -> rotate
   int cur = 0;
   auto other = [&](int k) { return (cur + k) & 3; };
+  // Trimmed decode (dv_vae_plan_set_first_frame): only output frames >= keep are wanted.  Every 3x3x3 causal conv looks
+  // two frames back at its own temporal resolution, GroupNorm and the mid-block attention are per frame, so walking the
+  // decoder backwards gives the first frame each conv has to compute; the results for the kept frames are bit-identical
+  // to a full decode.  (A continuation iteration of the rollout drops the 25 re-decoded input frames, pipeline.py:327.)
+  const int keep = p->first_frame;
+  int res_t[4][8], sp_t0[4] = {0, 0, 0, 0}, tp_t0[4] = {0, 0, 0, 0};
+  {
+    int n = std::max(0, keep - 2);   // conv_out reads two frames back
+    for (int i = 3; i >= 0; --i) {
+      if (c.temporal_up[i]) {        // output frame o = 2 t - 1 + {0, 1}
+        tp_t0[i] = (n + 1) / 2;
+        n = std::max(0, tp_t0[i] - 2);
+      }
+      if (c.spatial_up[i]) {
+        sp_t0[i] = n;
+        n = std::max(0, n - 2);
+      }
+      for (int j = c.layers_per_block[i] - 1; j >= 0; --j) {
+        res_t[i][j] = n;
+        n = std::max(0, n - 4);      // conv2 and conv1
+      }
+    }
+    // (everything in front of the up blocks runs on all frames)
+  }
   {
     x = r.resnet("decoder.mid_block.resnets.0", x, top, other(1), other(2), other(3));
     cur = other(3);
@@ -382,17 +424,17 @@ static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, c
     const int co = c.block_channels[3 - i];
     for (int j = 0; j < c.layers_per_block[i]; ++j) {
       x = r.resnet("decoder.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), x, co,
-                   other(1), other(2), other(3));
+                   other(1), other(2), other(3), res_t[i][j]);
       cur = other(3);
     }
     if (c.spatial_up[i]) {
       x = r.conv("decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv.conv", x, co * 4, 3,
-                 CONV_SHUFFLE_HW, 0, nullptr, B[other(1)], -1, !c.temporal_up[i]);
+                 CONV_SHUFFLE_HW, 0, nullptr, B[other(1)], -1, !c.temporal_up[i], 1, 1, 1, sp_t0[i]);
       cur = other(1);
     }
     if (c.temporal_up[i]) {
       x = r.conv("decoder.up_blocks." + std::to_string(i) + ".temporal_upsamplers.0.conv.conv", x,
-                 co * 2, 3, CONV_INTERLEAVE_T, 1, nullptr, B[other(1)], -1, true);
+                 co * 2, 3, CONV_INTERLEAVE_T, 1, nullptr, B[other(1)], -1, true, 1, 1, 1, tp_t0[i]);
       cur = other(1);
     }
   }
@@ -406,23 +448,25 @@ static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, c
   y.C = c.out_channels;
   {
     const long long npix = static_cast<long long>(x.T) * x.H * x.W;
-    r.flops += 2.0 * npix * c.out_channels * 27.0 * x.C;
+    const int tA = std::max(0, keep - 2);                       // first frame whose tap planes are needed
+    const long long pixA = static_cast<long long>(tA) * x.H * x.W;
+    r.flops += 2.0 * (npix - pixA) * c.out_channels * 27.0 * x.C;
     if (dry) {
       if (32 * npix * 4 > p->taps_elems) p->taps_elems = 32 * npix * 4;
     } else if (r.rc == 0) {
       GemmDesc d = {};
       d.batch = 1;
-      d.M = static_cast<int>(npix);
+      d.M = static_cast<int>(npix - pixA);
       d.N = 128;  // 27 taps x 4 columns = 108, padded to the 32-column epilogue chunk (weight rows
                   // beyond 108 are zero-filled by TMA; their planes are written but never read)
       d.K = x.C;
-      d.A = x.p;
+      d.A = x.p + pixA * x.C;
       d.a_batch_stride = npix * x.C;
       d.lda = x.C;
       d.W = r.W("decoder.conv_out.conv.weight_taps");
       d.w_rows = 27 * 4;
       d.mode = EPI_TAPS;
-      d.out = p->taps;
+      d.out = p->taps + pixA * 4;   // planes are [tap][pixel][4] fp32 with the full pixel count as the plane stride
       d.ldo = static_cast<int>(npix);
       if (npix >= (1ll << 31) || x.C % 64 != 0) {
         set_error("conv_out: %lld pixels, C=%d", npix, x.C);
@@ -431,7 +475,7 @@ static int run_tile(dv_vae_plan* p, const void* z, int z_bf16, int ti, int tj, c
       if (r.rc == 0) r.rc = launch_gemm(d, st);
       if (r.rc == 0)
         r.rc = launch_tap_gather(p->taps, reinterpret_cast<const float*>(r.W("decoder.conv_out.conv.bias")),
-                                 to.px, x.T, x.H, x.W, c.out_channels, st);
+                                 to.px, x.T, x.H, x.W, c.out_channels, std::min(keep, x.T - 1), st);
     }
   }
   if (dry) {
@@ -519,6 +563,15 @@ extern "C" void dv_vae_plan_destroy(dv_vae_plan* p) {
 
 extern "C" double dv_vae_plan_flops(const dv_vae_plan* p) { return p ? p->flops : 0.0; }
 
+// Decode only output frames [first_frame, Tout) from now on (0 = everything): the frames in front are neither computed
+// nor written.  The kept frames are bit-identical to a full decode (see run_tile).
+extern "C" int dv_vae_plan_set_first_frame(dv_vae_plan* p, int first_frame) {
+  DV_REQUIRE(p && first_frame >= 0 && first_frame < p->Tout, "dv_vae_plan_set_first_frame: frame %d of %d", first_frame,
+             p ? p->Tout : 0);
+  p->first_frame = first_frame;
+  return DV_OK;
+}
+
 extern "C" int dv_vae_plan_geometry(const dv_vae_plan* p, int* rows, int* cols, int* t_out) {
   DV_REQUIRE(p && rows && cols && t_out, "dv_vae_plan_geometry: null argument");
   *rows = p->rows;
@@ -581,7 +634,8 @@ extern "C" int dv_vae_blend(dv_vae_plan* p, void* out_dev, int out_dtype, void* 
   a.extent = (p->tile * scale) / 4;          // blend_extent = tile_sample_min_size * 0.25
   a.limit = p->tile * scale - a.extent;      // row_limit
   if (p->rows == 1 && p->cols == 1) a.limit = (a.Hout > a.Wout ? a.Hout : a.Wout) + 1;
-  const long long total = 3LL * a.Tout * a.Hout * a.Wout;
+  a.t_first = p->first_frame;
+  const long long total = 3LL * (a.Tout - a.t_first) * a.Hout * a.Wout;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   if (out_dtype == DV_DTYPE_BF16)
     blend_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a, reinterpret_cast<__nv_bfloat16*>(out_dev));

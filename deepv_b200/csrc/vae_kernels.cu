@@ -243,9 +243,10 @@ __global__ void latent_tile_kernel(const T* __restrict__ z, __nv_bfloat16* __res
 __global__ void __launch_bounds__(256) tap_gather_kernel(const float4* __restrict__ P,
                                                          const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int T, int H,
-                                                         int W, int Cout) {
+                                                         int W, int Cout, int t_first) {
   const long long npix = static_cast<long long>(T) * H * W;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // frames [t_first, T) only; plane and output indices stay absolute
+  const long long i = static_cast<long long>(t_first) * H * W + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const int w = static_cast<int>(i % W);
   const int h = static_cast<int>((i / W) % H);
@@ -281,12 +282,13 @@ __global__ void __launch_bounds__(256) tap_gather_kernel(const float4* __restric
 }  // namespace
 
 int launch_tap_gather(const float* planes, const float* bias, __nv_bfloat16* out, int T, int H, int W,
-                      int Cout, cudaStream_t stream) {
-  DV_REQUIRE(Cout >= 1 && Cout <= 4, "tap_gather: Cout=%d", Cout);
-  const long long npix = static_cast<long long>(T) * H * W;
+                      int Cout, int t_first, cudaStream_t stream) {
+  DV_REQUIRE(Cout >= 1 && Cout <= 4 && t_first >= 0 && t_first < T, "tap_gather: Cout=%d, first frame %d of %d", Cout,
+             t_first, T);
+  const long long npix = static_cast<long long>(T - t_first) * H * W;
   ProfScope ps(PROF_OTHER, 0.0, static_cast<double>(npix) * (27 * 16.0 + Cout * 2.0), stream, "tap_gather");
   tap_gather_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(planes), bias, out, T, H, W, Cout);
+      reinterpret_cast<const float4*>(planes), bias, out, T, H, W, Cout, t_first);
   DV_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return 0;

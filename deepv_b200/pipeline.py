@@ -231,17 +231,20 @@ class B200Pipeline:
         return latents
 
     @torch.no_grad()
-    def decode_latents_sharded(self, latent_list, shard, out_dtype=None):
+    def decode_latents_sharded(self, latent_list, shard, out_dtype=None, first_frame: int = 0):
         """pipeline.py:695-696 (image + disparity decodes) with the tiles x modalities dealt over
         the ranks of `shard`; returns one video per entry of latent_list on every rank."""
         zs = [self._unnormalise(z) for z in latent_list]
-        return self.vae.decode_many(zs, shard, tile_sample_min_size=256, out_dtype=out_dtype)
+        return self.vae.decode_many(zs, shard, tile_sample_min_size=256, out_dtype=out_dtype, first_frame=first_frame)
 
     @torch.no_grad()
-    def decode_latent(self, latents: torch.Tensor, save_memory: bool = True, out_dtype=None):
+    def decode_latent(self, latents: torch.Tensor, save_memory: bool = True, out_dtype=None, first_frame: int = 0):
+        """pipeline.py:703-725.  `first_frame` (extension, default 0 = the reference's behaviour): only frames
+        [first_frame, T) are computed (bit-identical there, zeros in front) — `B200Rollout` passes 25 in continuation
+        iterations, whose first 25 decoded frames the reference throws away (pipeline.py:327-328)."""
         latents = self._unnormalise(latents)
         if not save_memory:
             raise _lib.DeepVError("decode_latent: only the save_memory=True (256 px tile) branch exists; "
                                   "the reference's 512 px branch crashes (SURVEY.md App. E.2)")
         return self.vae.decode(latents, temporal_chunk=True, window_size=1, tile_sample_min_size=256,
-                               out_dtype=out_dtype).sample
+                               out_dtype=out_dtype, first_frame=first_frame).sample

@@ -117,6 +117,9 @@ class B200Rollout:
         self.pipe, self.prompts = pipe, prompts
         self.lib = pipe.lib
         self.device, self.dtype = pipe.device, pipe.dtype
+        # continuation iterations decode only the frames they keep (bit-identical there; False = decode all 57 as the
+        # reference does before it drops the first 25)
+        self.trim_continuation_decode = True
         self.cfg = pipe.model_cfg
 
     # -- small device helpers ---------------------------------------------------------------------
@@ -288,11 +291,13 @@ class B200Rollout:
         half = (lat.shape[1] - ray) // 2
         z_image, z_disparity = lat[:, :half].contiguous(), lat[:, half:2 * half].contiguous()             # :685-686
         trans3d, trans2d = self.raymap_to_pose(lat)                                                       # :688-692
+        # a continuation iteration keeps frames [25:] of both videos only (pipeline.py:327-328,339,346): decode just those
+        ff = NUM_INPUT_IMAGE if (not first and self.trim_continuation_decode) else 0
         if shard is not None and shard.active:
-            image, disparity = pipe.decode_latents_sharded([z_image, z_disparity], shard)                 # :694-695
+            image, disparity = pipe.decode_latents_sharded([z_image, z_disparity], shard, first_frame=ff)  # :694-695
         else:
-            image = pipe.decode_latent(z_image)
-            disparity = pipe.decode_latent(z_disparity)
+            image = pipe.decode_latent(z_image, first_frame=ff)
+            disparity = pipe.decode_latent(z_disparity, first_frame=ff)
         if cfg.get("no_need_depth", False):
             disparity = torch.zeros_like(disparity)                                                       # :696-697
         if return_latents:

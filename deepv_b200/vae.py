@@ -254,13 +254,14 @@ class B200VAE:
         return self.lib.dv_vae_plan_flops(self._plan(T, h, w, tile))
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, is_init_image=True,
-               temporal_chunk=False, window_size=2, tile_sample_min_size=256, out_dtype=None):
+               temporal_chunk=False, window_size=2, tile_sample_min_size=256, out_dtype=None, first_frame: int = 0):
         """Reference signature vae.py:885-886.  temporal_chunk / window_size do not change the
-        result and are accepted for call compatibility."""
+        result and are accepted for call compatibility.  `first_frame` (extension): compute
+        output frames [first_frame, T_out) only — bit-identical to the full decode there, zeros in front."""
         _lib.require_cuda(z)
         if z.shape[0] != 1:
             outs = [self.decode(z[i:i + 1], True, is_init_image, temporal_chunk, window_size,
-                                tile_sample_min_size, out_dtype).sample for i in range(z.shape[0])]
+                                tile_sample_min_size, out_dtype, first_frame).sample for i in range(z.shape[0])]
             return SimpleNamespace(sample=torch.cat(outs, dim=0))
         if z.dtype not in (torch.float32, torch.bfloat16):
             z = z.float()
@@ -272,6 +273,9 @@ class B200VAE:
         plan = self._plan(T, h, w, tile)
         od = out_dtype or z.dtype
         out = torch.empty((1, 3, 8 * (T - 1) + 1, 8 * h, 8 * w), device=z.device, dtype=od)
+        check(self.lib.dv_vae_plan_set_first_frame(plan, int(first_frame)), "dv_vae_plan_set_first_frame")
+        if first_frame:
+            out[:, :, :first_frame].zero_()
         check(self.lib.dv_vae_decode(plan, z.data_ptr(), _lib.dtype_code(z.dtype), out.data_ptr(),
                                      _lib.dtype_code(od), _lib.stream_ptr()), "dv_vae_decode")
         self._last = z
@@ -302,10 +306,10 @@ class B200VAE:
             self._shard_bufs[key] = bufs
         return self._plans[key], self._shard_bufs[key]
 
-    def decode_many(self, zs, shard, tile_sample_min_size=256, out_dtype=None):
+    def decode_many(self, zs, shard, tile_sample_min_size=256, out_dtype=None, first_frame: int = 0):
         """Decode several latent videos [1,16,T,h,w] of the same shape (rgb, disparity, ...) with
         the (modality, tile) work items dealt over the ranks of `shard`; every rank returns all
-        decoded videos."""
+        decoded videos.  `first_frame`: as in `decode`."""
         from .parallel import decode_items
         zs = [z.contiguous() if z.dtype in (torch.float32, torch.bfloat16) else z.float().contiguous() for z in zs]
         _lib.require_cuda(*zs)
@@ -314,6 +318,8 @@ class B200VAE:
         plans = [self._sharded_plan(T, h, w, tile, m) for m in range(len(zs))]
         n_tiles = len(plans[0][1])
         items = decode_items(len(zs), n_tiles)
+        for pl, _ in plans:
+            check(self.lib.dv_vae_plan_set_first_frame(pl, int(first_frame)), "dv_vae_plan_set_first_frame")
         for i in shard.my_items(len(items)):
             m, t = items[i]
             check(self.lib.dv_vae_decode_tiles(plans[m][0], zs[m].data_ptr(), _lib.dtype_code(zs[m].dtype),
@@ -323,6 +329,8 @@ class B200VAE:
         for m, z in enumerate(zs):
             od = out_dtype or z.dtype
             out = torch.empty((1, 3, 8 * (T - 1) + 1, 8 * h, 8 * w), device=z.device, dtype=od)
+            if first_frame:
+                out[:, :, :first_frame].zero_()
             check(self.lib.dv_vae_blend(plans[m][0], out.data_ptr(), _lib.dtype_code(od), _lib.stream_ptr()),
                   "dv_vae_blend")
             outs.append(out)

@@ -258,6 +258,12 @@ void dv_vae_destroy(dv_vae* v);
 int dv_vae_plan_create(dv_vae* v, int T, int h, int w, int tile_latent, dv_vae_plan** out);
 void dv_vae_plan_destroy(dv_vae_plan* p);
 double dv_vae_plan_flops(const dv_vae_plan* p);
+/* Trimmed decode: from now on dv_vae_decode / dv_vae_decode_tiles / dv_vae_blend of this plan produce output frames
+ * [first_frame, Tout) only (0 = all); frames in front are neither computed nor written.  The kept frames are bit-identical
+ * to a full decode: every causal conv only computes the frames the kept ones depend on (two frames of look-back per 3x3x3
+ * conv at its own temporal resolution).  For the continuation iterations of a rollout, which discard the 25 re-decoded
+ * input frames (pipeline.py:327-328).                                                                                   */
+int dv_vae_plan_set_first_frame(dv_vae_plan* p, int first_frame);
 /* z_dev: [1][16][T][h][w] (dtype), already un-normalised (pipeline.py:705-709);
  * out_dev: [1][3][8(T-1)+1][8h][8w] (dtype)                                                    */
 int dv_vae_decode(dv_vae_plan* p, const void* z_dev, int z_dtype, void* out_dev, int out_dtype,

@@ -106,6 +106,23 @@ def test_vae_production_single_tile_eight_latent_frames(vae_prod):
         assert min(per_frame) >= PSNR_FLOOR_DB
 
 
+@pytest.mark.parametrize("first_frame", [1, 8, 25, 56])
+def test_vae_trimmed_decode_is_bit_identical_on_the_kept_frames(vae_prod, first_frame):
+    """`decode(z, first_frame=k)` (what a continuation iteration of the rollout uses, k = 25: the reference decodes all
+    57 frames and drops the first 25, pipeline.py:327-328) computes, layer by layer, only the frames the kept ones depend
+    on — two frames of look-back per causal 3x3x3 conv — so the kept frames must equal the full decode bit for bit."""
+    cfg, Wc, v32, v16 = vae_prod
+    z = torch.randn(1, 16, 8, 48, 64, generator=torch.Generator().manual_seed(23)).cuda().bfloat16()   # 6 tiles, 57 frames
+    full = v16.decode(z, temporal_chunk=True, window_size=1, tile_sample_min_size=256).sample
+    part = v16.decode(z, temporal_chunk=True, window_size=1, tile_sample_min_size=256, first_frame=first_frame).sample
+    again = v16.decode(z, temporal_chunk=True, window_size=1, tile_sample_min_size=256).sample         # the plan is reset
+    torch.cuda.synchronize()
+    assert part.shape == full.shape == (1, 3, 57, 384, 512)
+    assert torch.equal(part[:, :, first_frame:], full[:, :, first_frame:])
+    assert not part[:, :, :first_frame].any()
+    assert torch.equal(again, full)
+
+
 @pytest.mark.parametrize("video", [(1, 3, 1, 384, 512), (1, 3, 9, 384, 512)])
 def test_vae_production_encode(vae_prod, video):
     """`vae.encode(x)` (vae.py:844-883,954-987,630-689) at the production widths: moments <= 2e-2."""

@@ -202,12 +202,21 @@ def test_generate_i2v_second_iteration_teacher_forced(gpu_rollout, oracle_run):
     t = trace[1]
     start = next(i for i, c in enumerate(tape.calls) if c == ("randn", (1, 38, 8, case["height"] // 8, case["width"] // 8)))
     replay = rc.ReplayTape(tape.draws, tape.calls, start)
-    image, disparity, t3, t2, lat = ro.generate_i2v(
-        t["motion_prompt"], True, ro.frames_from_uint8(t["frames"]), t["input_disparity"].cuda(),
-        t["input_raymap"].cuda(), t["input_history"].cuda(), temp=8, num_inference_steps=1, noise=replay,
-        return_latents=True)
+    args = (t["motion_prompt"], True, ro.frames_from_uint8(t["frames"]), t["input_disparity"].cuda(),
+            t["input_raymap"].cuda(), t["input_history"].cuda())
+    image_k, disparity_k, *_ = ro.generate_i2v(*args, temp=8, num_inference_steps=1, noise=replay, return_latents=True)
+    # the rollout's default decodes only the 32 frames a continuation iteration keeps; the full decode (what the
+    # reference computes before it drops 25 frames) must agree with it bit for bit there
+    ro.trim_continuation_decode = False
+    try:
+        image, disparity, t3, t2, lat = ro.generate_i2v(*args, temp=8, num_inference_steps=1,
+                                                        noise=rc.ReplayTape(tape.draws, tape.calls, start), return_latents=True)
+    finally:
+        ro.trim_continuation_decode = True
     torch.cuda.synchronize()
     assert image.shape == t["images"].shape
+    assert torch.equal(image_k[:, :, 25:], image[:, :, 25:]) and torch.equal(disparity_k[:, :, 25:], disparity[:, :, 25:])
+    assert not image_k[:, :, :25].any()
     e_in = rel_max(lat[:, :, :4], t["latents"][:, :, :4])
     print(f"iteration 1 (teacher-forced): input latents {e_in:.2e}, generated latents "
           f"{rel_max(lat[:, :, 4:], t['latents'][:, :, 4:]):.2e}")
