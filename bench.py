@@ -465,6 +465,7 @@ def roofline_from_profile(path, prof_ms, peaks):
            "avg_launch_us": round(per_launch_ms * 1e3, 2), "launches_per_step": d["launches"],
            "kernel_share_of_step": round(d["ms"] / prof_ms, 4) if prof_ms > 0 else None,
            "peak_source": src, "classes": out, "kernel_time_ms": round(total_ms, 2), "profiled_step_ms": round(prof_ms, 2),
+           "executed_tflop": round(sum(a["flops"] for a in classes.values()) / 1e12, 1),
            "how": "CUDA events on the launching stream around every launch of one extra profiled step (graph replay and "
                   "programmatic-dependent-launch overlap are off while profiling); dominant kernel = the launch shape with the "
                   "largest total time inside the kernel class with the largest share of the step"}
@@ -687,7 +688,11 @@ def run_ours(args):
                     + 2 * work.vae_decode_flops(2)
             sus = peaks.get("bf16_tflops_sustained") or 1400.0
             roofline["whole_step"] = {"algorithmic_tflop": round(alg / 1e12, 1), "tflops_per_gpu": round(alg / 1e12 / (ms / 1e3) / gsz, 1),
-                                      "frac_of_sustained_peak": round(alg / 1e12 / (ms / 1e3) / gsz / sus, 4), "gpus_per_rollout": gsz}
+                                      "frac_of_sustained_peak": round(alg / 1e12 / (ms / 1e3) / gsz / sus, 4), "gpus_per_rollout": gsz,
+                                      "note": "algorithmic_tflop is the REFERENCE's work (deepv_b200/work.py); a continuation iteration "
+                                              "decodes 25 frames per video that the reference throws away and the trimmed decode never "
+                                              "computes, so the FLOPs this rank actually executed are roofline.executed_tflop",
+                                      "executed_frac_of_sustained_peak": round(roofline["executed_tflop"] / (ms / 1e3) / sus, 4)}
             if not args.profile_dump:
                 os.unlink(path)
         lib.dv_profile_reset()
