@@ -102,9 +102,36 @@ def _conv(t, h, w, cin, cout, k=3):
     return 2.0 * t * h * w * cout * cin * k ** 3
 
 
-def vae_decode_tile_flops(t_lat: int, h: int, w: int, chans=VAE_BLOCK_CHANNELS, layers=(3, 3, 3, 3), zc: int = 16) -> float:
+def decode_frame_schedule(first_frame: int, layers=(3, 3, 3, 3), spatial_up=(1, 1, 1, 0), temporal_up=(1, 1, 1, 0)):
+    """First frame each conv of the decoder's up blocks has to compute when only output frames >= first_frame are
+    wanted (the trimmed decode of a continuation iteration; csrc/vae.cu:run_tile walks the decoder backwards the same
+    way): a causal 3x3x3 conv looks two frames back at its own temporal resolution, GroupNorm is per frame, the
+    frame-interleave upsampler maps conv frame t to output frames 2t-1 and 2t.  Returns (res_t[i][j] = first output
+    frame of resnet j of up block i, sp_t0[i], tp_t0[i] = first conv frame of the spatial / temporal upsampler,
+    taps_t0 = first frame conv_out reads)."""
+    n = max(0, first_frame - 2)
+    taps_t0 = n
+    res_t = [[0] * layers[i] for i in range(4)]
+    sp_t0, tp_t0 = [0] * 4, [0] * 4
+    for i in range(3, -1, -1):
+        if temporal_up[i]:
+            tp_t0[i] = (n + 1) // 2
+            n = max(0, tp_t0[i] - 2)
+        if spatial_up[i]:
+            sp_t0[i] = n
+            n = max(0, n - 2)
+        for j in range(layers[i] - 1, -1, -1):
+            res_t[i][j] = n
+            n = max(0, n - 4)
+    return res_t, sp_t0, tp_t0, taps_t0
+
+
+def vae_decode_tile_flops(t_lat: int, h: int, w: int, chans=VAE_BLOCK_CHANNELS, layers=(3, 3, 3, 3), zc: int = 16,
+                          first_frame: int = 0) -> float:
     """One tile [zc, t_lat, h, w] through post_quant_conv + decoder (vae.py:731-751); the temporal windows with
-    their caches are the same contraction as one causal pass."""
+    their caches are the same contraction as one causal pass.  first_frame > 0: the FLOPs the
+    trimmed decode executes (decode_frame_schedule); 0: the reference's work."""
+    res_t, sp_t0, tp_t0, taps_t0 = decode_frame_schedule(first_frame, layers)
     c = list(reversed(chans))            # 512, 512, 256, 128
     f = _conv(t_lat, h, w, zc, zc, 1) + _conv(t_lat, h, w, zc, c[0])
     f += 4 * _conv(t_lat, h, w, c[0], c[0])                              # two mid resnets
@@ -114,16 +141,17 @@ def vae_decode_tile_flops(t_lat: int, h: int, w: int, chans=VAE_BLOCK_CHANNELS, 
     for i, co in enumerate(c):
         for j in range(layers[i]):
             ci = prev if j == 0 else co
-            f += _conv(t, h, w, ci, co) + _conv(t, h, w, co, co)
+            n = res_t[i][j]
+            f += _conv(t - max(0, n - 2), h, w, ci, co) + _conv(t - n, h, w, co, co)
             if ci != co:
-                f += _conv(t, h, w, ci, co, 1)
+                f += _conv(t - n, h, w, ci, co, 1)
         prev = co
         if i < 3:                                                       # spatial then temporal up-sampling
-            f += _conv(t, h, w, co, 4 * co)
+            f += _conv(t - sp_t0[i], h, w, co, 4 * co)
             h, w = 2 * h, 2 * w
-            f += _conv(t, h, w, co, 2 * co)
+            f += _conv(t - tp_t0[i], h, w, co, 2 * co)
             t = 2 * t - 1                                               # first frame dropped (vae.py:408-409)
-    f += _conv(t, h, w, c[-1], 3)
+    f += _conv(t - taps_t0, h, w, c[-1], 3)
     return f
 
 
@@ -132,8 +160,8 @@ def tile_grid(lat_h: int, lat_w: int, tile: int = 32, stride: int = 24):
     return [(min(tile, lat_h - i), min(tile, lat_w - j)) for i in range(0, lat_h, stride) for j in range(0, lat_w, stride)]
 
 
-def vae_decode_flops(t_lat: int, lat_h: int = 48, lat_w: int = 64) -> float:
-    return sum(vae_decode_tile_flops(t_lat, th, tw) for th, tw in tile_grid(lat_h, lat_w))
+def vae_decode_flops(t_lat: int, lat_h: int = 48, lat_w: int = 64, first_frame: int = 0) -> float:
+    return sum(vae_decode_tile_flops(t_lat, th, tw, first_frame=first_frame) for th, tw in tile_grid(lat_h, lat_w))
 
 
 def vae_encode_tile_flops(t_px: int, h: int, w: int, chans=VAE_BLOCK_CHANNELS, layers=(2, 2, 2, 2), zc: int = 16) -> float:
@@ -174,5 +202,7 @@ def rollout_work(n_iterations: int = 2, lat_h: int = 48, lat_w: int = 64, steps=
     enc = vae_encode_flops(1, H, W) + (n_iterations - 1) * (2 * vae_encode_flops(25, H, W))   # image (+ disparity)
     enc += n_iterations * 2 * vae_encode_flops(1, H, W)                                       # history frame, rgb + disparity
     frames = 57 + 32 * (n_iterations - 1)
+    # what B200Rollout executes: continuation iterations decode only the 32 frames they keep (pipeline.py:327-328)
+    dec_exec = 2 * vae_decode_flops(8, lat_h, lat_w) + (n_iterations - 1) * 2 * vae_decode_flops(8, lat_h, lat_w, first_frame=25)
     return dict(mmdit=mm, vae_decode=dec, vae_encode=enc, total=mm + dec + enc, frames=frames,
-                forwards=sum(f["count"] for f in fw))
+                forwards=sum(f["count"] for f in fw), vae_decode_executed=dec_exec, executed=mm + dec_exec + enc)

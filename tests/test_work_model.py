@@ -44,3 +44,23 @@ def test_flops_match_survey_worked_values():
 
 def test_tile_grid_is_the_reference_geometry():
     assert w.tile_grid(48, 64) == [(32, 32), (32, 32), (32, 16), (24, 32), (24, 32), (24, 16)]
+
+
+def test_trimmed_decode_schedule_and_executed_flops():
+    """The frame schedule of the trimmed decode (csrc/vae.cu:run_tile, mirrored by work.decode_frame_schedule) and the work it
+    saves, pinned to what the B200 profiler counted: a rollout executed 2070.5 TFLOP before the trimmed decode
+    (profiles/r02s_bench_rollout.json, classes' achieved x ms) and 1974.7 TFLOP with it (profiles/r02v_bench_rollout.json)."""
+    res_t, sp_t0, tp_t0, taps_t0 = w.decode_frame_schedule(25)
+    assert taps_t0 == 23                                   # conv_out reads two frames back
+    assert res_t[3] == [15, 19, 23]                        # 128-channel level (57 frames): conv2 of resnet j starts here,
+    assert tp_t0[2] == 6 and sp_t0[2] == 4                 # conv1 two frames earlier; upsamplers in front of it (29 frames)
+    assert res_t[2] == [0, 0, 2] and res_t[1] == [0, 0, 0] and res_t[0] == [0, 0, 0]
+    assert w.decode_frame_schedule(0) == ([[0] * 3 for _ in range(4)], [0] * 4, [0] * 4, 0)
+    assert w.vae_decode_flops(8, first_frame=0) == w.vae_decode_flops(8)
+    full, part = w.vae_decode_flops(8), w.vae_decode_flops(8, first_frame=25)
+    assert 0.84 < part / full < 0.86                       # a trimmed decode is ~15 % cheaper
+    r = w.rollout_work(2)
+    assert r["executed"] < r["total"]
+    assert (r["total"] - r["executed"]) / 1e12 == pytest.approx(2070.5 - 1974.7, abs=1.0)
+    assert r["executed"] / 1e12 == pytest.approx(1974.7, rel=5e-3)
+    assert w.rollout_work(1)["executed"] == w.rollout_work(1)["total"]     # the first iteration keeps all 57 frames
