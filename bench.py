@@ -472,6 +472,27 @@ def roofline_from_profile(path, prof_ms, peaks):
     return top
 
 
+def whole_step_summary(roofline, ms, gsz, peaks, rollout, layers):
+    """The whole step against the tensor roofline: algorithmic FLOPs of the workload (deepv_b200/work.py)
+    over the timed step of this rank's rollout group, next to the FLOPs the profiled step actually executed."""
+    from deepv_b200 import work
+    if rollout:
+        rw = work.rollout_work(ROLLOUT_ITERS, LAT_H, LAT_W, STEPS_PER_STAGE)
+        alg, exe_model = rw["total"], rw["executed"]
+    else:
+        alg = 5 * sum(work.mmdit_flops(2, SAMPLE_CLIPS[st], False, n_layers=layers)["total"] for st in range(3)) \
+            + 2 * work.vae_decode_flops(2)
+        exe_model = alg
+    sus = peaks.get("bf16_tflops_sustained") or 1400.0
+    return {"algorithmic_tflop": round(alg / 1e12, 1), "tflops_per_gpu": round(alg / 1e12 / (ms / 1e3) / gsz, 1),
+            "frac_of_sustained_peak": round(alg / 1e12 / (ms / 1e3) / gsz / sus, 4), "gpus_per_rollout": gsz,
+            "note": "algorithmic_tflop is the REFERENCE's work (deepv_b200/work.py); a continuation iteration decodes 25 frames per "
+                    "video that the reference throws away and the trimmed decode never computes, so the FLOPs this rank actually "
+                    "executed are roofline.executed_tflop",
+            "executed_tflop_work_model": round(exe_model / 1e12, 1),
+            "executed_frac_of_sustained_peak": round(roofline.get("executed_tflop", 0.0) / (ms / 1e3) / sus, 4)}
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -678,24 +699,7 @@ def run_ours(args):
             except Exception:
                 pass
             roofline = roofline_from_profile(path, p0.elapsed_time(p1), peaks)
-            # the whole step against the tensor roofline: algorithmic FLOPs of the workload (deepv_b200/work.py,
-            # SURVEY.md §8d) over the timed step of this rank's rollout group
-            from deepv_b200 import work
-            if rollout:
-                rw = work.rollout_work(ROLLOUT_ITERS, LAT_H, LAT_W, STEPS_PER_STAGE)
-                alg, exe_model = rw["total"], rw["executed"]
-            else:
-                alg = 5 * sum(work.mmdit_flops(2, SAMPLE_CLIPS[st], False, n_layers=args.layers)["total"] for st in range(3)) \
-                    + 2 * work.vae_decode_flops(2)
-                exe_model = alg
-            sus = peaks.get("bf16_tflops_sustained") or 1400.0
-            roofline["whole_step"] = {"algorithmic_tflop": round(alg / 1e12, 1), "tflops_per_gpu": round(alg / 1e12 / (ms / 1e3) / gsz, 1),
-                                      "frac_of_sustained_peak": round(alg / 1e12 / (ms / 1e3) / gsz / sus, 4), "gpus_per_rollout": gsz,
-                                      "note": "algorithmic_tflop is the REFERENCE's work (deepv_b200/work.py); a continuation iteration "
-                                              "decodes 25 frames per video that the reference throws away and the trimmed decode never "
-                                              "computes, so the FLOPs this rank actually executed are roofline.executed_tflop",
-                                      "executed_tflop_work_model": round(exe_model / 1e12, 1),
-                                      "executed_frac_of_sustained_peak": round(roofline["executed_tflop"] / (ms / 1e3) / sus, 4)}
+            roofline["whole_step"] = whole_step_summary(roofline, ms, gsz, peaks, rollout, args.layers)
             if not args.profile_dump:
                 os.unlink(path)
         lib.dv_profile_reset()
