@@ -23,7 +23,7 @@ flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-li
          "--expt-relaxed-constexpr"]
 if not so.exists() or "--rebuild" in sys.argv:
     from deepv_b200 import build
-    build.build()
+    build.build(force=not list((ROOT / "deepv_b200" / "build").glob("*.o")))   # (the object files do not travel with gpurun)
     obj = here / f"attention_trace_{poly}.o"
     extra = [f"-DDV_ATTN_POLY_PAIRS={poly}"] if poly is not None else []
     subprocess.check_call(["nvcc", *flags, "-DDV_ATTN_TRACE", *extra, "-c", str(csrc / "attention.cu"), "-o", str(obj)])

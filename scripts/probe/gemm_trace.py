@@ -21,7 +21,7 @@ flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-li
          "--expt-relaxed-constexpr"]
 if not so.exists() or "--rebuild" in sys.argv:
     from deepv_b200 import build
-    build.build()
+    build.build(force=not list((ROOT / "deepv_b200" / "build").glob("*.o")))   # (the object files do not travel with gpurun)
     obj = here / "gemm_trace.o"
     subprocess.check_call(["nvcc", *flags, "-DDV_GEMM_TRACE", "-c", str(csrc / "gemm.cu"), "-o", str(obj)])
     others = [str(o) for o in (ROOT / "deepv_b200" / "build").glob("*.o") if o.name != "gemm.o"]
