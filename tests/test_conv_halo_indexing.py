@@ -10,8 +10,19 @@ import torch.nn.functional as F
 TILE_W, TILE_H, BOX_W, BOX_H = 8, 32, 10, 34
 
 
-def halo_conv_emulated(x, w, bias, store, drop):
-    """x [T,H,W,C] (C % 64 == 0), w [Cout, 27, C] (tap-major K, tap = (dt*3+dy)*3+dx) -> stored tensor."""
+def decode_tile(tile, n_chunks, tiles_w, tiles_h, T, t0):
+    """`decode()` of conv_halo.cu: flat tile index -> (batch, frame, h0, w0, weight chunk); frames [t0, T) only."""
+    chunk = tile % n_chunks
+    tile //= n_chunks
+    per_frame = tiles_w * tiles_h
+    r, f = tile % per_frame, tile // per_frame
+    nt = T - t0
+    return f // nt, t0 + f % nt, (r // tiles_w) * TILE_H, (r % tiles_w) * TILE_W, chunk
+
+
+def halo_conv_emulated(x, w, bias, store, drop, t0=0):
+    """x [T,H,W,C] (C % 64 == 0), w [Cout, 27, C] (tap-major K, tap = (dt*3+dy)*3+dx) -> stored tensor.
+    t0 > 0 (GemmDesc::conv_t0, the trimmed decode): only conv frames [t0, T) are computed, indices stay absolute."""
     T, H, W, C = x.shape
     Cout = w.shape[0]
     c_blocks = C // 64
@@ -21,10 +32,15 @@ def halo_conv_emulated(x, w, bias, store, drop):
     oH, oW = (2 * H, 2 * W) if store == 1 else (H, W)
     out = torch.zeros(oT, oH, oW, out_C)
     wk = w.reshape(Cout, 27 * C)
-    for t in range(T):
-        for h0 in range(0, H, TILE_H):
-            for w0 in range(0, W, TILE_W):
-                for chunk in range(n_chunks):
+    tiles_w, tiles_h = W // TILE_W, (H + TILE_H - 1) // TILE_H
+    seen = set()
+    for tile in range((T - t0) * tiles_w * tiles_h * n_chunks):
+        if True:
+            if True:
+                if True:
+                    b, t, h0, w0, chunk = decode_tile(tile, n_chunks, tiles_w, tiles_h, T, t0)
+                    assert b == 0 and t0 <= t < T and (t, h0, w0, chunk) not in seen
+                    seen.add((t, h0, w0, chunk))
                     rows_w = wk[chunk * 128:(chunk + 1) * 128]                     # TMA box of 128 weight rows
                     acc = torch.zeros(rows_w.shape[0], TILE_H * TILE_W)            # D[channel][pixel n = y*8 + x]
                     for dt in range(3):
@@ -88,3 +104,19 @@ def test_halo_tile_arithmetic_matches_conv3d(T, H, W, C, Cout, store, drop):
         ref = y.view(2, Ch, T, H, W).permute(2, 0, 3, 4, 1).reshape(2 * T, H, W, Ch)[drop:]
     assert got.shape == ref.shape
     assert (got - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("store,drop,t0", [(0, 0, 1), (0, 0, 3), (2, 1, 2), (1, 0, 2)])
+def test_halo_tiles_of_a_trimmed_conv(store, drop, t0):
+    """Frames [t0, T) of the conv output (after the store map: 2*t0 - drop for the frame-interleave store) equal the full
+    conv; nothing in front is written; every (frame, tile, chunk) is visited exactly once."""
+    T, H, W, C, Cout = 4, 32, 8, 64, 128
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(T, H, W, C, generator=g)
+    w = torch.randn(Cout, 27, C, generator=g) * 0.05
+    bias = torch.randn(Cout, generator=g)
+    full = halo_conv_emulated(x, w, bias, store, drop)
+    part = halo_conv_emulated(x, w, bias, store, drop, t0)
+    first = max(0, 2 * t0 - drop) if store == 2 else t0
+    assert torch.equal(part[first:], full[first:])
+    assert not part[:first].any()
