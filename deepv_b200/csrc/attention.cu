@@ -6,22 +6,27 @@
 // "same sample AND frame(q) >= frame(k)" collapses to  k < kv_end[q]  AND  key_bias[b][k] == 0
 // (dead keys = padded text / masked-history tokens, sample id 0 in the reference).
 //
-// One CTA = 128 queries x one head x one batch row, 192 threads, TWO CTAs per SM (256 TMEM columns
-// and ~83 KB of shared memory each) so that one CTA's softmax hides the other's MMAs:
-//   warp 0      TMA producer: Q once, then (K_j, V_j) into a 2-stage ring
-//   warp 1      MMA issuer.  Every MMA takes its A operand FROM TENSOR MEMORY: measured on B200 an
-//               M128 MMA with A in shared memory costs >= 128 cycles whatever N is (the 128-row A
-//               read), which would hold S = Q K^T (N = 128) to half rate and P V (N = 64) to a
-//               quarter; with A in TMEM they run at their math rate.
-//                 S  = Q K_j^T            (M128 N128 K64)   A = Q (bf16, parked in TMEM once)
-//                 O += P V_j              (M128 N64 K128)   A = P (bf16, written over S by the
-//                                                               softmax warps), V MN-major
-//                 l += P 1                (M128 N16 K128)   the softmax row sums come out of the
-//                                                               tensor pipe too (B = a tile of ones)
-//   warps 2-5   softmax, one query row per thread: S from TMEM, running max with a lazy rescale
-//               (O and l are rescaled in TMEM only when the max grows by more than 2^8), P back
-//               into TMEM.  Masking runs only on tiles that hold a frame boundary or dead keys.
-// Query tiles are issued heaviest-first (late frames see the most keys).
+// Four kernels share the scheme (DV_ATTN_PIPE selects; launch_attention at the end of the file):
+//   attn_pipe_kernel<64>   DEFAULT.  CTA = 128 queries x one head x one batch row, 192 threads, 64-key tiles, S double-
+//                          buffered in tensor memory, TWO CTAs per SM (256 TMEM columns, 82 KB shared memory, 158 registers)
+//   attn_pipe_kernel<128>  the same with 128-key tiles: 512 TMEM columns, one CTA per SM
+//   attn_pair_kernel       two query tiles per CTA sharing K / V, one softmax warpgroup each, setmaxnreg 224 / 56
+//   attn_kernel            round 1: S overwritten by P, row sums on the tensor pipe, two CTAs per SM at the 168-register cap
+// Roles in a CTA:
+//   TMA warp    Q once, then (K_j, V_j) into a ring; MMA warp: both run their loops as whole converged warps and elect
+//               the issuing lane inside the instruction (common.cuh w_* forms) — issued from `if (lane == 0)` every
+//               tcgen05.mma / TMA costs ~80 cycles of ELECT / R2UR.BROADCAST loop, which paced the round-1 kernel.
+//               Every MMA takes its A operand FROM TENSOR MEMORY: measured on B200 an M128 MMA with A in shared memory
+//               costs >= 128 cycles whatever N is (the 128-row A read), which would hold S = Q K^T to half rate and
+//               P V (N = 64) to a quarter; with A in TMEM they run at their math rate.
+//                 S  = Q K_j^T            (M128 N=KT K64)   A = Q (bf16, parked in TMEM once)
+//                 O += P V_j              (M128 N64 K=KT)   A = P (bf16, written over S by the softmax warps), V MN-major
+//   4 softmax warps, one query row per thread (softmax_tile): S from TMEM, four independent max chains, running max with
+//               a lazy rescale (O is rescaled in TMEM only when the max grows by more than 2^8), scale-and-shift / row
+//               sums as packed fp32x2, one exponential pair in four as a polynomial on the FMA pipe, P back into TMEM.
+//               Masking runs only on tiles that hold a frame boundary or dead keys.
+// Query tiles are issued heaviest-first (late frames see the most keys).  Measurements: DESIGN.md §3.3,
+// profiles/r02p_attn_modes.txt, scripts/probe/attn_trace.py (-DDV_ATTN_TRACE timeline build).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
