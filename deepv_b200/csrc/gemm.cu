@@ -1,11 +1,12 @@
 // deepv_b200 — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM conv3d.
 //
-// One CTA per SM, 192 threads:
-//   warp 0      TMA producer   (one lane): A/B k-blocks -> 128B-swizzled smem ring
-//   warp 1      MMA issuer     (one lane): tcgen05.mma M=128, N=256, K=16, fp32 accum in TMEM;
-//               also owns TMEM alloc/dealloc
-//   warps 2..5  epilogue       (128 threads, one accumulator row each): tcgen05.ld ->
-//               fused epilogue (compile-time EpiMode) -> vectorised global stores
+// One CTA per SM, 320 threads:
+//   warp 0      TMA producer: A/B k-blocks -> 128B-swizzled smem ring
+//   warp 1      MMA issuer: tcgen05.mma M=128 (CTA pairs: 256), N=256, K=16, fp32 accum in TMEM; also owns TMEM alloc/dealloc
+//               (both run their loops as whole converged warps; the issuing lane is elected inside the instruction —
+//               common.cuh w_* forms — so the operands stay in uniform registers instead of an ELECT / R2UR loop per issue)
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, one accumulator row per thread): tcgen05.ld -> fused epilogue
+//               (compile-time EpiMode) -> shared-memory staging + TMA store / reduce-add, or direct vector stores
 // ONE tile shape, 128 x 256 x 64: measured on B200, an M128 tcgen05.mma with both operands in
 // shared memory takes >= 128 cycles whatever N is (the 128-row A read), so N = 256 is the only
 // width that runs the tensor pipe at rate; a CTA therefore needs ~K*8 cycles per tile and the
@@ -17,7 +18,8 @@
 //     barrier every CTA sums one row-slice over all peers through distributed shared memory in
 //     rank order (deterministic, no atomics, no workspace) and runs the epilogue for that slice.
 // Convolutions with Cout <= 128 swap the operand roles (weights = M side, a 16x16-pixel box =
-// N side).  See gemm.cuh for the operand / epilogue contract.
+// N side).  Dense problems with contiguous batch rows are flattened into one row space (Problem::flat_M); a conv can
+// be asked for output frames [conv_t0, T) only (the trimmed decode).  See gemm.cuh for the operand / epilogue contract.
 #include "gemm.cuh"
 
 #include <cstdio>
